@@ -1,0 +1,222 @@
+/* dsengine.h — C ABI of libdsengine.so, the sm_100a kernel library behind diffsensei_b200.
+ *
+ * The reference (jianzongwu/DiffSensei) has no FFI: every kernel on its UNet sampling path is a
+ * PyTorch library call.  Each entry point below therefore names the reference call site whose
+ * arithmetic it replaces (paths relative to the reference repo root); the Python adapters in
+ * diffsensei_b200/ bind them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless a comment says "host";
+ *   - activations are bf16, channels-last: images are NHWC [B][H][W][C], token tensors [B][N][C]
+ *     (the same memory — a transformer block needs no transpose);
+ *   - norm/bias parameters are fp32; GEMM/conv weights are bf16, K-major ([out][in]);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - no entry point allocates device memory: scratch is passed in by the caller;
+ *   - return value 0 = ok, otherwise a DS_ERR_* code; ds_last_error() gives the message
+ *     (thread-local).  There is no CPU fallback: on a box without an sm_100 device every compute
+ *     entry point returns DS_ERR_CUDA.
+ */
+#ifndef DSENGINE_H_
+#define DSENGINE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DS_OK 0
+#define DS_ERR_INVALID 1 /* bad argument / unsupported shape */
+#define DS_ERR_CUDA 2    /* CUDA runtime / driver error      */
+
+/* library version (major*10000 + minor*100 + patch) and last error message of the calling thread */
+int ds_version(void);
+const char* ds_last_error(void);
+/* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
+uint64_t ds_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GroupNorm (+ optional SiLU), NHWC bf16.                     [HBM-bound]
+ * Replaces diffusers ResnetBlock2D.norm1/norm2 + nonlinearity (GroupNorm(32, eps=1e-5) -> SiLU),
+ * Transformer2DModel.norm (eps=1e-6, no SiLU) and conv_norm_out+conv_act reached from
+ * src/models/unet.py:251-261,281-290,316-338.
+ *   x, y      : [B][HW][C] bf16 (y may alias x)
+ *   gamma/beta: [C] fp32
+ *   stats     : scratch, 2*B*groups floats (mean, rstd) — written then read by the two passes
+ * Statistics are computed in fp32 over the bf16 input (two-pass Welford-free: sum / sum-of-squares
+ * of values centred on a per-group pilot), normalisation + affine + SiLU in fp32, one rounding to bf16.
+ * --------------------------------------------------------------------------------------------- */
+int ds_groupnorm_silu(const void* x, void* y, const float* gamma, const float* beta, float* stats, int B, int HW,
+                      int C, int groups, float eps, int apply_silu, void* stream);
+
+/* LayerNorm over the last dim, bf16 in/out, fp32 affine.     [HBM-bound]
+ * Replaces BasicTransformerBlock.norm1/2/3 (eps 1e-5) and Resampler LayerNorms
+ * (src/models/resampler.py:14,40-41,104). rows x C, C % 8 == 0. */
+int ds_layernorm(const void* x, void* y, const float* gamma, const float* beta, int rows, int C, float eps,
+                 void* stream);
+
+/* Dialog-bbox embedding add, in place on the NHWC conv_in output.   [HBM-bound]
+ * Replaces UNetMangaModel.encode_dialog_bbox (src/models/unet.py:88-114):
+ *   sample[b, y, x, :] += emb[:]  iff (x, y) lies in the union of the half-open pixel boxes
+ *   [int(x1*W), int(x2*W)) x [int(y1*H), int(y2*H)), clamped to the image.
+ * `dialog_bbox` is [B][num_dialogs][4] fp32 holding values ALREADY rounded to the unet dtype
+ * (the reference multiplies in the unet dtype before int(): src/models/unet.py:102-105); set
+ * `round_bf16` = 1 to reproduce the bf16 product rounding (int(bf16(0.9)*152) = 137), 0 for fp32. */
+int ds_dialog_embed_add(void* sample, const float* emb, const float* dialog_bbox, int B, int H, int W, int C,
+                        int num_dialogs, int round_bf16, void* stream);
+
+/* Stand-alone IP attention mask (parity aid only — the fused cross-attention kernel computes the
+ * same predicate in registers and never materialises it).
+ * Replaces MaskedIPAttnProcessor2_0.prepare_attention_mask_ip (src/models/attention_processor.py:115-169).
+ *   bbox : [B][num_ips][4] fp32;  mask out: [B][N][num_dummy + num_ips*tokens_per_ip] fp32 in {0,-10000}
+ *   (identical across heads, so the head dim is not materialised). (H', W') are re-derived from
+ *   (N, aspect_ratio) exactly as the reference does (:131-139). */
+int ds_ip_mask(const float* bbox, float* mask, int B, int N, float aspect_ratio, int num_ips, int tokens_per_ip,
+               int num_dummy, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * bf16 GEMM on tcgen05 tensor cores, TMA-fed, fp32 accumulation in TMEM.      [tensor-bound]
+ *   out[M][Nout] = epilogue( A[M][K] * W[N][K]^T )
+ * Replaces every nn.Linear on the path: attn.to_q/to_k/to_v/to_out (src/models/attention_processor.py:
+ * 56,63-64,84,207,225-226,245-246,261), diffusers FeedForward/GEGLU, Transformer2D proj_in/proj_out,
+ * ResnetBlock2D.time_emb_proj, TimestepEmbedding, Resampler linears (src/models/resampler.py:15-17,43-45,
+ * 100-103), and 1x1 shortcut convs.
+ * Epilogue, applied in fp32 before one rounding to bf16:
+ *   v = acc + bias[n] + rowbias[row / rows_per_batch][n]
+ *   DS_EPI_GEGLU: W/bias rows are packed in blocks of 128 "value" rows followed by their 128 "gate"
+ *                 rows (see diffsensei_b200.weights.pack_geglu); out[:, j] = v_val * gelu_erf(v_gate),
+ *                 Nout = N/2.
+ *   DS_EPI_GELU / DS_EPI_SILU : v = act(v)
+ *   then v += residual[row][n] (bf16) and v *= out_scale (if != 0).
+ * Constraints: K % 8 == 0, lda % 8 == 0 (16-byte TMA strides). M, N, K tails are handled by TMA
+ * zero-fill and masked stores.
+ * --------------------------------------------------------------------------------------------- */
+#define DS_EPI_NONE 0
+#define DS_EPI_GEGLU 1
+#define DS_EPI_GELU 2
+#define DS_EPI_SILU 3
+
+typedef struct {
+  const void* a;        /* bf16 [M][lda]                                  */
+  const void* w;        /* bf16 [N][ldw]  (row = output feature, K-major) */
+  void* out;            /* bf16 [M][ldo]  (or fp32 when out_fp32 != 0)    */
+  const float* bias;    /* [N] or NULL                                    */
+  const float* rowbias; /* [ceil(M/rows_per_batch)][N] or NULL            */
+  const void* residual; /* bf16 [M][ldres] or NULL                        */
+  int32_t M, N, K;
+  int32_t lda, ldw, ldo, ldres;
+  int32_t rows_per_batch; /* only read when rowbias != NULL                */
+  int32_t epilogue;       /* DS_EPI_*                                      */
+  int32_t out_fp32;       /* 1: `out` is fp32                              */
+  float out_scale;        /* 0 or 1: no scaling                            */
+} ds_gemm_args;
+
+int ds_gemm_bf16(const ds_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 3x3 convolution, padding 1, stride 1 or 2, NHWC bf16, as an implicit GEMM on tcgen05:
+ * the A operand is gathered by 4-D TMA tiles (one 8x16-pixel patch x 64 channels per filter tap;
+ * the halo / zero padding is TMA out-of-bounds fill), never materialised.       [tensor-bound]
+ * Replaces nn.Conv2d 3x3 in diffusers ResnetBlock2D.conv1/conv2, Downsample2D.conv (stride 2),
+ * Upsample2D.conv and conv_out, reached from src/models/unet.py:251-261,281-290,316-338.
+ *   x   : [B][H][W][Cin]          w: [Cout][3][3][Cin] bf16 (tap-major K; see weights.pack_conv3x3)
+ *   out : [B][Ho][Wo][Cout],  Ho = (H-1)/stride+1 (same for Wo)
+ *   rowbias : [B][Cout] fp32 or NULL — the ResnetBlock2D time-embedding projection, broadcast over pixels
+ *   residual: bf16 [B][Ho][Wo][Cout] or NULL — the block's skip / shortcut branch
+ * Constraints: Cin % 64 == 0 (conv_in with Cin=4 has its own entry point below).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;
+  const void* w;
+  void* out;
+  const float* bias;
+  const float* rowbias;
+  const void* residual;
+  int32_t B, H, W, Cin, Cout;
+  int32_t stride;
+  int32_t out_fp32;
+  float out_scale;
+} ds_conv3x3_args;
+
+int ds_conv3x3_nhwc(const ds_conv3x3_args* args, void* stream);
+
+/* conv_in: 3x3, Cin = 4 (latent channels), direct CUDA-core kernel (K = 36 is not GEMM-shaped; the op is
+ * bound by writing the [B][H][W][Cout] output).  x: NHWC bf16 [B][H][W][4]; w: fp32 [Cout][3][3][4].
+ * Replaces UNet2DConditionModel.conv_in (src/models/unet.py:206).                       [HBM-bound] */
+int ds_conv_in_3x3(const void* x, const float* w, const float* bias, void* out, int B, int H, int W, int Cout,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused self-attention, head_dim 64, no mask: softmax(Q K^T / 8) V.              [tensor-bound]
+ * Replaces F.scaled_dot_product_attention in AttnProcessor2_0.__call__
+ * (src/models/attention_processor.py:69-81).
+ *   qkv : bf16 [B][N][3*C] — the fused to_q|to_k|to_v projection output (C = heads*64); head h reads
+ *         columns h*64.. of each third, via TMA boxes, so no head transpose is ever materialised
+ *   out : bf16 [B][N][C]
+ * --------------------------------------------------------------------------------------------- */
+int ds_attention_self(const void* qkv, void* out, int B, int N, int heads, void* stream);
+
+/* Fused text + masked-IP cross-attention, head_dim 64:                              [HBM-bound]
+ *   out = softmax(Q Kt^T/8) Vt + scale * softmax(Q Kip^T/8 + M(bbox)) Vip
+ * Replaces both SDPA calls, prepare_attention_mask_ip and the blend in
+ * MaskedIPAttnProcessor2_0.__call__ (src/models/attention_processor.py:231-258).
+ *   q    : bf16 [B][N][C]
+ *   kv_t : bf16 [B][n_text][2*C]  (to_k | to_v of the text tokens; timestep-invariant)
+ *   kv_ip: bf16 [B][n_ip][2*C]    (to_k_ip | to_v_ip of the image tokens, n_ip = num_dummy + num_ips*tokens_per_ip)
+ *   bbox : fp32 [B][num_ips][4];  the additive mask is evaluated in registers with the reference's
+ *          closed-interval linspace membership and derived (H', W') (:131-163); masked keys get -10000.
+ * n_text, n_ip <= 128. */
+typedef struct {
+  const void* q;
+  const void* kv_text;
+  const void* kv_ip;
+  const float* bbox;
+  void* out;
+  int32_t B, N, heads;
+  int32_t n_text, n_ip;
+  int32_t num_ips, tokens_per_ip, num_dummy;
+  float aspect_ratio;
+  float ip_scale;
+} ds_cross_ip_args;
+
+int ds_attention_cross_ip(const ds_cross_ip_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout / glue kernels (all HBM-bound, vectorised)
+ * --------------------------------------------------------------------------------------------- */
+/* NCHW (fp32 or bf16) <-> NHWC bf16 at the diffusers-facing boundary of UNetMangaModel.forward */
+int ds_nchw_to_nhwc(const void* src, int src_is_fp32, void* dst_bf16, int B, int C, int H, int W, void* stream);
+int ds_nhwc_to_nchw(const void* src_bf16, void* dst, int dst_is_fp32, int B, int C, int H, int W, void* stream);
+/* nearest-neighbour resize to (Ho, Wo) (Upsample2D's F.interpolate; src index = floor(dst * in/out)) */
+int ds_upsample_nearest(const void* x, void* y, int B, int H, int W, int C, int Ho, int Wo, void* stream);
+/* channel concat of two NHWC tensors: y[..., :C1] = a, y[..., C1:] = b  (torch.cat([hidden, skip], 1)) */
+int ds_concat_channels(const void* a, const void* b, void* y, int pixels, int C1, int C2, void* stream);
+/* elementwise y = silu(x), n bf16 elements */
+int ds_silu(const void* x, void* y, int64_t n, void* stream);
+/* Timesteps(num_channels, flip_sin_to_cos=True, downscale_freq_shift=0): out[r][:] = [cos | sin](t[r]*w) bf16 */
+int ds_timestep_embedding(const float* t, void* out, int rows, int dim, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CFG blend + DDIM (eta = 0, epsilon-prediction) update, fused.                    [HBM-bound]
+ * Replaces src/pipelines/pipeline_diffsensei.py:315,332-337 (chunk, u + g*(t-u), scheduler.step,
+ * and the torch.cat([latents]*2) for the next step):
+ *   eps   = e_uncond + guidance * (e_text - e_uncond)
+ *   x0    = (x - sqrt(1-a_t) * eps) / sqrt(a_t)
+ *   x_new = sqrt(a_prev) * x0 + sqrt(1-a_prev) * eps
+ *   noise_pred : bf16 NHWC [2*bs][H][W][4] (uncond half first)
+ *   latents    : fp32 [bs][H][W][4] updated in place (fp32 master copy)
+ *   model_in   : bf16 NHWC [2*bs][H][W][4] — x_new duplicated for both CFG halves (next step's UNet input)
+ *   coef       : device pointer to 2 floats {alpha_prod_t, alpha_prod_t_prev} for this step
+ * --------------------------------------------------------------------------------------------- */
+int ds_cfg_ddim_step(const void* noise_pred, float* latents, void* model_in, const float* coef, float guidance,
+                     int bs, int HW, int C, void* stream);
+
+/* Perceiver attention of the character Resampler: 16 latent queries x (n_kv) keys per (character, head),
+ * q and k each pre-scaled by dim_head^-0.25, fp32 softmax (src/models/resampler.py:64-74).
+ *   q: bf16 [Bc][nq][C], kv: bf16 [Bc][n_kv][2*C] (k | v), out: bf16 [Bc][nq][C]; C = heads*64 */
+int ds_resampler_attn(const void* q, const void* kv, void* out, int Bc, int nq, int n_kv, int heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSENGINE_H_ */
