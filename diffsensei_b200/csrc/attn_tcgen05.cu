@@ -1,0 +1,602 @@
+// attn_tcgen05.cu — fused attention for head_dim 64 on tcgen05 tensor cores (sm_100a).
+//
+// (1) flash_attn_kernel — softmax(Q K^T * scale) V with an online softmax, no mask (self-attention of
+//     AttnProcessor2_0, src/models/attention_processor.py:69-81; also used for the Resampler's perceiver
+//     attention, src/models/resampler.py:64-74).  One CTA = one 128-query tile of one (batch, head);
+//     two CTAs are co-resident per SM so one CTA's softmax overlaps the other's MMAs.
+//       warp 0   TMA producer : Q once, then K_j / V_j (128 x 64 tiles, 128-B swizzle) through a 3-slot ring
+//       warp 1   MMA issuer   : S = Q K_j^T (M128 N128 K64) into TMEM; O (+)= P_j V_j (M128 N64 K128),
+//                               V consumed MN-major straight from its [kv][d] TMA tile
+//       warp 2   TMEM allocator (256 columns: S 0..127, O 128..191)
+//       warps 4-7 softmax     : thread <-> query row.  tcgen05.ld S, running max in the log2 domain with LAZY
+//                               rescaling (O/l are only rescaled when the row max grows by > 2^8), exp2,
+//                               P_j -> bf16 into swizzled shared memory as the next MMA's A operand.
+//                               O never leaves TMEM until the final 1/l normalisation.
+//     Q/K/V are addressed by 3-D tensor maps {columns, tokens, batch} over the fused projection output, so
+//     the head split/transposes of the reference (:69-72,80) are never materialised.
+//
+// (2) cross_ip_attn_kernel — out = softmax(Q Kt^T/8) Vt + scale * softmax(Q Kip^T/8 + M(bbox)) Vip
+//     (MaskedIPAttnProcessor2_0, src/models/attention_processor.py:231-258) in ONE pass: text and IP keys are
+//     concatenated along the key axis in shared memory (<= 192 keys), one S = Q [Kt;Kip]^T MMA chain, two
+//     independent softmaxes per row with the normalisers and `scale` folded into P, one O = P [Vt;Vip] chain.
+//     The additive bbox mask M in {0,-10000} (:115-169) is evaluated in registers from the 4 boxes with the
+//     reference's closed-interval / derived-(H',W') semantics (ip_mask.cuh) and never touches memory.
+#include "ds_common.cuh"
+#include "ds_host.h"
+#include "ip_mask.cuh"
+
+namespace ds {
+
+constexpr int kAttnThreads = 256;
+constexpr int kTile = 128;            // query rows per CTA == kv rows per tile
+constexpr int kHd = 64;               // head dim
+constexpr int kTileBytes = kTile * kHd * 2;  // 16 KiB
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 domain
+
+// swizzled (SWIZZLE_128B) byte offset of 16-byte chunk `q16` (0..7) of row `r` inside a [rows][64 bf16] atom
+__device__ __forceinline__ uint32_t sw128_off(int r, int q16) { return r * 128 + ((q16 ^ (r & 7)) << 4); }
+
+__device__ __forceinline__ void st_shared_16(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+struct FlashParams {
+  __nv_bfloat16* out;  // [B][Nq][ldo]
+  int Nq, Nkv, ldo;
+  int q_col0, k_col0, v_col0;  // column of head 0 inside the respective tensor map
+  float scale_log2;            // softmax scale * log2(e)
+};
+
+// =================================================================================================
+// (1) flash attention
+// =================================================================================================
+__global__ void __launch_bounds__(kAttnThreads, 2)
+flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
+  constexpr int RING = 3;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sRing = sQ + kTileBytes;          // RING x 16 KiB, K_0 V_0 K_1 V_1 ...
+  uint8_t* sP = sRing + RING * kTileBytes;   // 2 atoms x 16 KiB: P[128][128] bf16, K-major
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* full = bars + 1;           // [RING]
+  uint64_t* empty = full + RING;       // [RING]
+  uint64_t* s_full = empty + RING;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTile;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int num_kv_tiles = (p.Nkv + kTile - 1) / kTile;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < RING; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;        // columns [0,128)
+  const uint32_t tO = tmem_base + 128;  // columns [128,192)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTileBytes);
+      tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + head * kHd, q0, batch);
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < num_kv_tiles; ++j) {
+        for (int which = 0; which < 2; ++which) {  // K_j then V_j
+          mbar_wait(&empty[slot], ph ^ 1);
+          mbar_arrive_expect_tx(&full[slot], kTileBytes);
+          tma_load_3d(sRing + slot * kTileBytes, which == 0 ? &tmK : &tmV, &full[slot],
+                      (which == 0 ? p.k_col0 : p.v_col0) + head * kHd, j * kTile, batch);
+          if (++slot == RING) {
+            slot = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(kTile, kTile, 0, 0);  // M128 N128, both K-major
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);    // M128 N64, B (=V) MN-major
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < num_kv_tiles; ++j) {
+        // ---- S = Q K_j^T
+        mbar_wait(&full[slot], ph);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sRing + slot * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k)
+          umma_ss(tS, make_sw128_desc(q_addr + k * 32, 1024, 16), make_sw128_desc(k_addr + k * 32, 1024, 16),
+                  idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&empty[slot]);
+        umma_commit(s_full);
+        if (++slot == RING) {
+          slot = 0;
+          ph ^= 1;
+        }
+        // ---- O (+)= P_j V_j
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        mbar_wait(&full[slot], ph);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sRing + slot * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k) {
+          const uint64_t adesc = make_sw128_desc(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 1024, 16);
+          const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048, 1024, 1024);
+          umma_ss(tO, adesc, bdesc, idesc_pv, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[slot]);
+        if (++slot == RING) {
+          slot = 0;
+          ph ^= 1;
+        }
+      }
+      umma_commit(o_full);
+    }
+  } else if (warp >= 4) {
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < num_kv_tiles; ++j) {
+      const int kv_valid = p.Nkv - j * kTile;  // >= 128: whole tile valid
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // ---- pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tS + lane_base + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      }
+      const float m_tile = mx * p.scale_log2;
+      float alpha = 1.0f;
+      bool need = false;
+      if (j == 0) {
+        m_ref = m_tile;
+      } else if (m_tile > m_ref + kRescaleThreshold) {
+        alpha = exp2f(m_ref - m_tile);
+        m_ref = m_tile;
+        l *= alpha;
+        need = true;
+      }
+      if (__any_sync(0xffffffffu, need)) {  // rescale this warp's 32 rows of O in TMEM
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(tO + lane_base + c * 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+          tmem_st32(tO + lane_base + c * 32, raw);
+        }
+        tmem_st_wait();
+      }
+      // ---- pass 2: P = exp2(S*scale - m_ref) -> bf16 -> swizzled smem; row sum
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tS + lane_base + c * 32, raw);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = exp2f(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_ref));
+          pv[i] = (c * 32 + i < kv_valid) ? e : 0.f;
+          lsum += pv[i];
+        }
+        uint8_t* atom = sP + (c >> 1) * kTileBytes;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int q16 = (c & 1) * 4 + q;
+          st_shared_16(atom + sw128_off(row, q16), pack_bf16(pv[q * 8 + 0], pv[q * 8 + 1]),
+                       pack_bf16(pv[q * 8 + 2], pv[q * 8 + 3]), pack_bf16(pv[q * 8 + 4], pv[q * 8 + 5]),
+                       pack_bf16(pv[q * 8 + 6], pv[q * 8 + 7]));
+        }
+      }
+      l += lsum;
+      fence_proxy_async_smem();  // st.shared -> visible to the tensor core's async-proxy reads
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> bf16 -> global
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int q_row = q0 + row;
+    __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.Nq + q_row) * p.ldo + head * kHd;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tO + lane_base + c * 32, raw);
+      tmem_ld_wait();
+      if (q_row < p.Nq) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(raw[q * 8 + 0]) * inv_l, __uint_as_float(raw[q * 8 + 1]) * inv_l);
+          u.y = pack_bf16(__uint_as_float(raw[q * 8 + 2]) * inv_l, __uint_as_float(raw[q * 8 + 3]) * inv_l);
+          u.z = pack_bf16(__uint_as_float(raw[q * 8 + 4]) * inv_l, __uint_as_float(raw[q * 8 + 5]) * inv_l);
+          u.w = pack_bf16(__uint_as_float(raw[q * 8 + 6]) * inv_l, __uint_as_float(raw[q * 8 + 7]) * inv_l);
+          reinterpret_cast<uint4*>(orow + c * 32)[q] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+constexpr int kFlashSmemBytes = kTileBytes * (1 + 3 + 2) + 1024 + 128;
+
+// =================================================================================================
+// (2) fused text + masked-IP cross-attention
+// =================================================================================================
+struct CrossParams {
+  __nv_bfloat16* out;   // [B][N][C]
+  const float* bbox;    // [B][num_ips][4]
+  int N, C;
+  int n_text, n_ip, nt_pad, nip_pad;  // pads are multiples of 16; nt_pad + nip_pad <= 192
+  int num_ips, tokens_per_ip, num_dummy;
+  int Hd, Wd;           // derived (H', W')
+  float ip_scale;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+cross_ip_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKVt,
+                     const __grid_constant__ CUtensorMap tmKVip, const CrossParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int n_keys = p.nt_pad + p.nip_pad;          // multiple of 16, <= 192
+  const int kv_bytes = n_keys * 128;                // [n_keys][64] bf16
+  const int p_atoms = (n_keys + 63) / 64;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTileBytes;
+  uint8_t* sV = sK + ((kv_bytes + 1023) & ~1023);
+  uint8_t* sP = sV + ((kv_bytes + 1023) & ~1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + p_atoms * kTileBytes);
+  uint64_t* ld_full = bars;
+  uint64_t* s_full = bars + 1;
+  uint64_t* p_full = bars + 2;
+  uint64_t* o_full = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTile;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKVt);
+    tma_prefetch_desc(&tmKVip);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(ld_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;        // columns [0, n_keys)
+  const uint32_t tO = tmem_base + 192;  // columns [192, 256)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(ld_full, kTileBytes + 2 * kv_bytes);
+      tma_load_3d(sQ, &tmQ, ld_full, head * kHd, q0, batch);
+      // keys: [text | ip] stacked along the key axis; values likewise (V = second half of the kv columns)
+      tma_load_3d(sK, &tmKVt, ld_full, head * kHd, 0, batch);
+      tma_load_3d(sK + p.nt_pad * 128, &tmKVip, ld_full, head * kHd, 0, batch);
+      tma_load_3d(sV, &tmKVt, ld_full, p.C + head * kHd, 0, batch);
+      tma_load_3d(sV + p.nt_pad * 128, &tmKVip, ld_full, p.C + head * kHd, 0, batch);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc_bf16(kTile, n_keys, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);
+      mbar_wait(ld_full, 0);
+      tc_fence_after();
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+#pragma unroll
+      for (int k = 0; k < kHd / 16; ++k)
+        umma_ss(tS, make_sw128_desc(q_addr + k * 32, 1024, 16), make_sw128_desc(k_addr + k * 32, 1024, 16), idesc_qk,
+                k != 0 ? 1u : 0u);
+      umma_commit(s_full);
+      mbar_wait(p_full, 0);
+      tc_fence_after();
+      for (int k = 0; k < n_keys / 16; ++k) {
+        const uint64_t adesc = make_sw128_desc(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 1024, 16);
+        const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048, 1024, 1024);
+        umma_ss(tO, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
+      }
+      umma_commit(o_full);
+    }
+  } else if (warp >= 4) {
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const int q_row = q0 + row;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t bits =
+        ip_inside_bits(p.bbox + static_cast<size_t>(batch) * p.num_ips * 4, p.num_ips, min(q_row, p.N - 1), p.Hd, p.Wd);
+    constexpr float kScale = 0.125f;  // 1/sqrt(64)
+
+    // score of key column `col` (text part first), or -inf for padding; IP keys get the additive -10000 mask
+    auto score = [&](float s_raw, int col) -> float {
+      if (col < p.nt_pad) return col < p.n_text ? s_raw * kScale : -INFINITY;
+      const int k = col - p.nt_pad;
+      if (k >= p.n_ip) return -INFINITY;
+      return s_raw * kScale + (ip_key_open(bits, k, p.tokens_per_ip, p.num_dummy) ? 0.0f : -10000.0f);
+    };
+
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    const int chunks = n_keys / 16;
+    const int t_chunks = p.nt_pad / 16;
+    // pass 1: maxima
+    float m_t = -INFINITY, m_i = -INFINITY;
+    for (int c = 0; c < chunks; ++c) {
+      uint32_t raw[16];
+      tmem_ld16(tS + lane_base + c * 16, raw);
+      tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) mx = fmaxf(mx, score(__uint_as_float(raw[i]), c * 16 + i));
+      if (c < t_chunks)
+        m_t = fmaxf(m_t, mx);
+      else
+        m_i = fmaxf(m_i, mx);
+    }
+    // pass 2: normalisers
+    float l_t = 0.f, l_i = 0.f;
+    for (int c = 0; c < chunks; ++c) {
+      uint32_t raw[16];
+      tmem_ld16(tS + lane_base + c * 16, raw);
+      tmem_ld_wait();
+      const float m = c < t_chunks ? m_t : m_i;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s += exp2f((score(__uint_as_float(raw[i]), c * 16 + i) - m) * kLog2e);
+      if (c < t_chunks)
+        l_t += s;
+      else
+        l_i += s;
+    }
+    const float w_t = 1.0f / l_t, w_i = p.ip_scale / l_i;
+    // pass 3: P = [softmax_text | scale * softmax_ip] -> bf16 -> swizzled smem
+    for (int c = 0; c < chunks; ++c) {
+      uint32_t raw[16];
+      tmem_ld16(tS + lane_base + c * 16, raw);
+      tmem_ld_wait();
+      const float m = c < t_chunks ? m_t : m_i;
+      const float w = c < t_chunks ? w_t : w_i;
+      float pv[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pv[i] = exp2f((score(__uint_as_float(raw[i]), c * 16 + i) - m) * kLog2e) * w;
+      uint8_t* atom = sP + (c >> 2) * kTileBytes;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int q16 = (c & 3) * 2 + q;
+        st_shared_16(atom + sw128_off(row, q16), pack_bf16(pv[q * 8 + 0], pv[q * 8 + 1]),
+                     pack_bf16(pv[q * 8 + 2], pv[q * 8 + 3]), pack_bf16(pv[q * 8 + 4], pv[q * 8 + 5]),
+                     pack_bf16(pv[q * 8 + 6], pv[q * 8 + 7]));
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(p_full);
+
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.N + q_row) * p.C + head * kHd;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tO + lane_base + c * 32, raw);
+      tmem_ld_wait();
+      if (q_row < p.N) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(raw[q * 8 + 0]), __uint_as_float(raw[q * 8 + 1]));
+          u.y = pack_bf16(__uint_as_float(raw[q * 8 + 2]), __uint_as_float(raw[q * 8 + 3]));
+          u.z = pack_bf16(__uint_as_float(raw[q * 8 + 4]), __uint_as_float(raw[q * 8 + 5]));
+          u.w = pack_bf16(__uint_as_float(raw[q * 8 + 6]), __uint_as_float(raw[q * 8 + 7]));
+          reinterpret_cast<uint4*>(orow + c * 32)[q] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static bool make_tok_map(CUtensorMap* m, const void* base, int cols, int ld, int tokens, int batch, int box_rows) {
+  const uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(tokens), static_cast<uint64_t>(batch)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(tokens) * ld * 2};
+  const uint32_t box[3] = {kHd, static_cast<uint32_t>(box_rows), 1};
+  return encode_tmap_bf16(m, base, 3, dims, strides, box, nullptr);
+}
+
+static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const void* v, int ldkv, int kv_cols,
+                        int k_col0, int v_col0, void* out, int ldo, int B, int Nq, int Nkv, int heads, float scale,
+                        cudaStream_t st) {
+  DeviceInfo dev;
+  if (!get_device(&dev)) return DS_ERR_CUDA;
+  CUtensorMap tmQ, tmK, tmV;
+  if (!make_tok_map(&tmQ, q, q_cols, ldq, Nq, B, kTile)) return DS_ERR_CUDA;
+  if (!make_tok_map(&tmK, k, kv_cols, ldkv, Nkv, B, kTile)) return DS_ERR_CUDA;
+  if (!make_tok_map(&tmV, v, kv_cols, ldkv, Nkv, B, kTile)) return DS_ERR_CUDA;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlashSmemBytes));
+    attr_set = true;
+  }
+  FlashParams p;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.Nq = Nq;
+  p.Nkv = Nkv;
+  p.ldo = ldo;
+  p.q_col0 = 0;
+  p.k_col0 = k_col0;
+  p.v_col0 = v_col0;
+  p.scale_log2 = scale * kLog2e;
+  dim3 grid((Nq + kTile - 1) / kTile, heads, B);
+  flash_attn_kernel<<<grid, kAttnThreads, kFlashSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  DS_LAUNCH_OK("flash_attn_kernel");
+  return DS_OK;
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+extern "C" int ds_attention_self(const void* qkv, void* out, int B, int N, int heads, void* stream) {
+  DS_REQUIRE(qkv && out, "ds_attention_self: NULL pointer");
+  DS_REQUIRE(B > 0 && N > 0 && heads > 0, "ds_attention_self: bad shape");
+  DS_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "ds_attention_self: pointers must be 16-byte aligned");
+  const int C = heads * kHd;
+  // one tensor map over the fused [B][N][3C] projection; K and V are column offsets C and 2C
+  return launch_flash(qkv, 3 * C, 3 * C, qkv, qkv, 3 * C, 3 * C, C, 2 * C, out, C, B, N, N, heads, 0.125f,
+                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ds_resampler_attn(const void* q, const void* kv, void* out, int Bc, int nq, int n_kv, int heads,
+                                 void* stream) {
+  DS_REQUIRE(q && kv && out, "ds_resampler_attn: NULL pointer");
+  DS_REQUIRE(Bc > 0 && nq > 0 && n_kv > 0 && heads > 0, "ds_resampler_attn: bad shape");
+  DS_REQUIRE((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "ds_resampler_attn: pointers must be 16-byte aligned");
+  const int C = heads * kHd;
+  // (q * d^-1/4)(k * d^-1/4)^T == q k^T / sqrt(d)   (src/models/resampler.py:69-70)
+  return launch_flash(q, C, C, kv, kv, 2 * C, 2 * C, 0, C, out, C, Bc, nq, n_kv, heads, 0.125f,
+                      static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ds_attention_cross_ip(const ds_cross_ip_args* a, void* stream) {
+  DS_REQUIRE(a != nullptr, "ds_attention_cross_ip: args is NULL");
+  DS_REQUIRE(a->q && a->kv_text && a->kv_ip && a->bbox && a->out, "ds_attention_cross_ip: NULL pointer");
+  DS_REQUIRE(a->B > 0 && a->N > 0 && a->heads > 0, "ds_attention_cross_ip: bad shape");
+  DS_REQUIRE(a->n_text > 0 && a->n_ip > 0, "ds_attention_cross_ip: n_text and n_ip must be positive");
+  DS_REQUIRE(a->num_ips > 0 && a->num_ips <= kMaxIps && a->tokens_per_ip > 0 && a->num_dummy >= 0 &&
+                 a->num_dummy + a->num_ips * a->tokens_per_ip == a->n_ip,
+             "ds_attention_cross_ip: n_ip (%d) != num_dummy (%d) + num_ips (%d) * tokens_per_ip (%d)", a->n_ip,
+             a->num_dummy, a->num_ips, a->tokens_per_ip);
+  const int nt_pad = (a->n_text + 15) / 16 * 16, nip_pad = (a->n_ip + 15) / 16 * 16;
+  DS_REQUIRE(nt_pad + nip_pad <= 192, "ds_attention_cross_ip: padded key count %d exceeds 192", nt_pad + nip_pad);
+  int Hd, Wd;
+  if (!derive_hw(a->N, a->aspect_ratio, &Hd, &Wd)) {
+    set_error("ds_attention_cross_ip: cannot factor N=%d for aspect_ratio=%f", a->N, a->aspect_ratio);
+    return DS_ERR_INVALID;
+  }
+  DeviceInfo dev;
+  if (!get_device(&dev)) return DS_ERR_CUDA;
+  const int C = a->heads * kHd;
+  CUtensorMap tmQ, tmT, tmI;
+  if (!make_tok_map(&tmQ, a->q, C, C, a->N, a->B, kTile)) return DS_ERR_CUDA;
+  if (!make_tok_map(&tmT, a->kv_text, 2 * C, 2 * C, a->n_text, a->B, nt_pad)) return DS_ERR_CUDA;
+  if (!make_tok_map(&tmI, a->kv_ip, 2 * C, 2 * C, a->n_ip, a->B, nip_pad)) return DS_ERR_CUDA;
+  const int n_keys = nt_pad + nip_pad;
+  const int kv_bytes = ((n_keys * 128) + 1023) & ~1023;
+  const int smem = kTileBytes + 2 * kv_bytes + ((n_keys + 63) / 64) * kTileBytes + 1024 + 128;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    DS_CUDA_OK(cudaFuncSetAttribute(cross_ip_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  CrossParams p;
+  p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.bbox = a->bbox;
+  p.N = a->N;
+  p.C = C;
+  p.n_text = a->n_text;
+  p.n_ip = a->n_ip;
+  p.nt_pad = nt_pad;
+  p.nip_pad = nip_pad;
+  p.num_ips = a->num_ips;
+  p.tokens_per_ip = a->tokens_per_ip;
+  p.num_dummy = a->num_dummy;
+  p.Hd = Hd;
+  p.Wd = Wd;
+  p.ip_scale = a->ip_scale;
+  dim3 grid((a->N + kTile - 1) / kTile, a->heads, a->B);
+  cross_ip_attn_kernel<<<grid, kAttnThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmT, tmI, p);
+  DS_LAUNCH_OK("cross_ip_attn_kernel");
+  return DS_OK;
+}

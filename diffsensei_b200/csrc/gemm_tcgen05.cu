@@ -39,7 +39,7 @@ struct GemmParams {
   void* out;
   int M, N, K;
   int n_out;  // output columns (N, or N/2 for GEGLU)
-  int ldo, ldres, rows_per_batch;
+  int ldo, ldres, rows_per_batch, ldrb;
   int epilogue, out_fp32;
   float out_scale;
   int num_m_tiles, num_n_tiles, num_k_iters;
@@ -227,7 +227,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (nw0 + j < p.N) v[j] += __ldg(p.bias + nw0 + j);
         }
         if (p.rowbias) {
-          const float* rb = p.rowbias + static_cast<long long>(batch) * p.N + nw0;
+          const float* rb = p.rowbias + static_cast<long long>(batch) * p.ldrb + nw0;
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -411,6 +411,7 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
   p.ldo = a->ldo;
   p.ldres = a->ldres;
   p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : 1;
+  p.ldrb = a->rowbias_ld > 0 ? a->rowbias_ld : a->N;
   p.epilogue = a->epilogue;
   p.out_fp32 = a->out_fp32;
   p.out_scale = a->out_scale == 1.0f ? 0.0f : a->out_scale;
@@ -457,6 +458,7 @@ extern "C" int ds_conv3x3_nhwc(const ds_conv3x3_args* a, void* stream) {
   p.ldo = a->Cout;
   p.ldres = a->Cout;
   p.rows_per_batch = 1;
+  p.ldrb = a->rowbias_ld > 0 ? a->rowbias_ld : a->Cout;
   p.epilogue = DS_EPI_NONE;
   p.out_fp32 = a->out_fp32;
   p.out_scale = a->out_scale == 1.0f ? 0.0f : a->out_scale;

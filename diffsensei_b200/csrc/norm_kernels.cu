@@ -1,0 +1,283 @@
+// norm_kernels.cu — GroupNorm(+SiLU) and LayerNorm for channels-last bf16 activations (HBM-bound).
+//
+// GroupNorm on NHWC: a group's channels are interleaved with every other group's inside each pixel, so the
+// coalesced decomposition is by PIXEL RANGE, not by group: a CTA streams a contiguous run of pixels (all
+// channels, 16-byte vectors, every thread pinned to the same 8 channels), accumulates per-channel
+// sum / sum-of-squares in registers, folds them to the 32 groups through shared memory and publishes one
+// double-precision atomicAdd pair per (sample, group).  The apply pass re-reads x (walking the chunks in the
+// reverse order so the tail of the stats pass is still resident in the 126 MB L2), normalises, applies
+// gamma/beta and SiLU in fp32 and rounds once to bf16.
+// Algorithmic bytes: read x + write y = 4 B/element; the stats re-read is overhead (roofline.traffic shows it).
+//
+// Replaces diffusers ResnetBlock2D.norm1/norm2+SiLU, Transformer2DModel.norm, conv_norm_out+conv_act
+// (reached from src/models/unet.py:251-261,281-290,316-338) and BasicTransformerBlock / Resampler LayerNorms
+// (src/models/resampler.py:14,40-41,104).
+#include "ds_common.cuh"
+#include "ds_host.h"
+
+namespace ds {
+
+
+// blockDim.x = cv * rpb  (cv = C/8 vectors per pixel, rpb pixels processed per sweep)
+__global__ void gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int HW, int C, int groups,
+                                int chunks_per_sample, int ppc) {
+  extern __shared__ double sh[];  // [2*groups]
+  const int cv = C >> 3;
+  const int rpb = blockDim.x / cv;
+  const int cvec = threadIdx.x % cv;
+  const int prow = threadIdx.x / cv;
+  const int b = blockIdx.x / chunks_per_sample;
+  const int chunk = blockIdx.x - b * chunks_per_sample;
+  const int p0 = chunk * ppc;
+  const int p1 = min(p0 + ppc, HW);
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sh[i] = 0.0;
+  __syncthreads();
+
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const uint4* base = x + (static_cast<size_t>(b) * HW) * cv + cvec;
+  int p = p0 + prow;
+  // 4 independent 16-byte loads in flight per thread
+  for (; p + 3 * rpb < p1; p += 4 * rpb) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(base + static_cast<size_t>(p + k * rpb) * cv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = bf16_lo(w[j]), c = bf16_hi(w[j]);
+        s[2 * j] += a;
+        q[2 * j] += a * a;
+        s[2 * j + 1] += c;
+        q[2 * j + 1] += c * c;
+      }
+    }
+  }
+  for (; p < p1; p += rpb) {
+    const uint4 u = __ldg(base + static_cast<size_t>(p) * cv);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = bf16_lo(w[j]), c = bf16_hi(w[j]);
+      s[2 * j] += a;
+      q[2 * j] += a * a;
+      s[2 * j + 1] += c;
+      q[2 * j + 1] += c * c;
+    }
+  }
+  // fold this thread's 8 channels into their groups (runs of equal group id merged before the atomic)
+  const int cpg = C / groups;
+  const int c0 = cvec * 8;
+  int g_run = c0 / cpg;
+  double rs = 0.0, rq = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    if (g != g_run) {
+      atomicAdd(&sh[2 * g_run], rs);
+      atomicAdd(&sh[2 * g_run + 1], rq);
+      g_run = g;
+      rs = rq = 0.0;
+    }
+    rs += static_cast<double>(s[j]);
+    rq += static_cast<double>(q[j]);
+  }
+  atomicAdd(&sh[2 * g_run], rs);
+  atomicAdd(&sh[2 * g_run + 1], rq);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
+    atomicAdd(&stats[static_cast<size_t>(b) * 2 * groups + i], sh[i]);
+}
+
+template <bool kSilu>
+__global__ void gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
+                                int groups, float eps, int chunks_per_sample, int ppc) {
+  const int cv = C >> 3;
+  const int rpb = blockDim.x / cv;
+  const int cvec = threadIdx.x % cv;
+  const int prow = threadIdx.x / cv;
+  // reverse chunk order: the most recently streamed part of x is the most likely to still be in L2
+  const int rb = gridDim.x - 1 - blockIdx.x;
+  const int b = rb / chunks_per_sample;
+  const int chunk = rb - b * chunks_per_sample;
+  const int p0 = chunk * ppc;
+  const int p1 = min(p0 + ppc, HW);
+
+  const int cpg = C / groups;
+  const double inv_n = 1.0 / (static_cast<double>(HW) * cpg);
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cvec * 8 + j;
+    const int g = c / cpg;
+    const double mean = stats[static_cast<size_t>(b) * 2 * groups + 2 * g] * inv_n;
+    double var = stats[static_cast<size_t>(b) * 2 * groups + 2 * g + 1] * inv_n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float ga = __ldg(gamma + c), be = __ldg(beta + c);
+    sc[j] = rstd * ga;
+    sf[j] = be - static_cast<float>(mean) * rstd * ga;
+  }
+  const size_t off = (static_cast<size_t>(b) * HW) * cv + cvec;
+  const uint4* xb = x + off;
+  uint4* yb = y + off;
+  auto norm8 = [&](const uint4& u) -> uint4 {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = fmaf(bf16_lo(w[j]), sc[2 * j], sf[2 * j]);
+      float c = fmaf(bf16_hi(w[j]), sc[2 * j + 1], sf[2 * j + 1]);
+      if (kSilu) {
+        a = silu_f(a);
+        c = silu_f(c);
+      }
+      o[j] = pack_bf16(a, c);
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  int p = p0 + prow;
+  for (; p + 3 * rpb < p1; p += 4 * rpb) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(xb + static_cast<size_t>(p + k * rpb) * cv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) yb[static_cast<size_t>(p + k * rpb) * cv] = norm8(u[k]);
+  }
+  for (; p < p1; p += rpb) yb[static_cast<size_t>(p) * cv] = norm8(__ldg(xb + static_cast<size_t>(p) * cv));
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, the whole row held in registers (two-pass mean / variance, fp32).
+// ------------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void layernorm_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int rows, int C, float eps) {
+  const int cv = C >> 3;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const uint4* xr = x + static_cast<size_t>(warp) * cv;
+  uint4* yr = y + static_cast<size_t>(warp) * cv;
+  float v[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < cv) {
+      const uint4 u = __ldg(xr + vi);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[i][2 * j] = bf16_lo(w[j]);
+        v[i][2 * j + 1] = bf16_hi(w[j]);
+        sum += v[i][2 * j] + v[i][2 * j + 1];
+      }
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(C);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < cv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(C) + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < cv) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi + 1);
+      const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o[j] = pack_bf16((v[i][2 * j] - mean) * rstd * ga[2 * j] + be[2 * j],
+                         (v[i][2 * j + 1] - mean) * rstd * ga[2 * j + 1] + be[2 * j + 1]);
+      yr[vi] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+}  // namespace ds
+
+extern "C" int ds_groupnorm_silu(const void* x, void* y, const float* gamma, const float* beta, float* stats, int B,
+                                 int HW, int C, int groups, float eps, int apply_silu, void* stream) {
+  using namespace ds;
+  DS_REQUIRE(x && y && gamma && beta && stats, "ds_groupnorm_silu: NULL pointer");
+  DS_REQUIRE(B > 0 && HW > 0 && C > 0 && groups > 0, "ds_groupnorm_silu: bad shape");
+  DS_REQUIRE(C % 8 == 0 && C % groups == 0, "ds_groupnorm_silu: C (%d) must be a multiple of 8 and of groups (%d)", C,
+             groups);
+  DS_REQUIRE(C <= 8192, "ds_groupnorm_silu: C (%d) > 8192 unsupported", C);
+  DS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
+             "ds_groupnorm_silu: x/y must be 16-byte and stats 8-byte aligned");
+  DeviceInfo dev;
+  if (!get_device(&dev)) return DS_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int cv = C / 8;
+  int rpb = 256 / cv;
+  if (rpb < 1) rpb = 1;
+  const int threads = cv * rpb;
+  DS_REQUIRE(threads <= 1024, "ds_groupnorm_silu: C too large for one CTA row");
+  // pixels per CTA: aim at ~8 CTAs per SM over the whole tensor, at least 4 sweeps of the CTA's pixel rows
+  long long ppc = (static_cast<long long>(B) * HW + dev.num_sms * 8 - 1) / (dev.num_sms * 8);
+  if (ppc < 4 * rpb) ppc = 4 * rpb;
+  ppc = ((ppc + 4 * rpb - 1) / (4 * rpb)) * (4 * rpb);
+  const int chunks = static_cast<int>((HW + ppc - 1) / ppc);
+  double* dstats = reinterpret_cast<double*>(stats);
+  DS_CUDA_OK(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * B * groups, st));
+  gn_stats_kernel<<<B * chunks, threads, sizeof(double) * 2 * groups, st>>>(static_cast<const uint4*>(x), dstats, HW,
+                                                                            C, groups, chunks, (int)ppc);
+  DS_LAUNCH_OK("gn_stats_kernel");
+  if (apply_silu)
+    gn_apply_kernel<true><<<B * chunks, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), dstats,
+                                                          gamma, beta, HW, C, groups, eps, chunks, (int)ppc);
+  else
+    gn_apply_kernel<false><<<B * chunks, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y),
+                                                           dstats, gamma, beta, HW, C, groups, eps, chunks, (int)ppc);
+  DS_LAUNCH_OK("gn_apply_kernel");
+  return DS_OK;
+}
+
+extern "C" int ds_layernorm(const void* x, void* y, const float* gamma, const float* beta, int rows, int C, float eps,
+                            void* stream) {
+  using namespace ds;
+  DS_REQUIRE(x && y && gamma && beta, "ds_layernorm: NULL pointer");
+  DS_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, "ds_layernorm: rows>0 and C %% 8 == 0 required (rows=%d C=%d)", rows, C);
+  DS_REQUIRE(C <= 4096, "ds_layernorm: C (%d) > 4096 unsupported", C);
+  DS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0,
+             "ds_layernorm: pointers must be 16-byte aligned");
+  DeviceInfo dev;
+  if (!get_device(&dev)) return DS_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 256;
+  const int blocks = (rows + 7) / 8;
+  const int cv = C / 8;
+  if (cv <= 32 * 4)
+    layernorm_kernel<4><<<blocks, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), gamma, beta,
+                                                    rows, C, eps);
+  else if (cv <= 32 * 8)
+    layernorm_kernel<8><<<blocks, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), gamma, beta,
+                                                    rows, C, eps);
+  else
+    layernorm_kernel<16><<<blocks, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), gamma, beta,
+                                                     rows, C, eps);
+  DS_LAUNCH_OK("layernorm_kernel");
+  return DS_OK;
+}

@@ -1,0 +1,328 @@
+"""Tensor-level wrappers over the libdsengine C ABI.
+
+Each function validates the tensor contract (device, dtype, contiguity, shape), enqueues exactly the named
+kernel(s) on torch's current CUDA stream and returns the output tensor.  PyTorch is used for device memory
+and streams only — there is no eager fallback: on a non-CUDA tensor these raise ``DsEngineError``.
+Layouts: activations bf16 channels-last (NHWC / [B, N, C]); norm and bias parameters fp32; GEMM/conv weights
+bf16 [out, in] (see include/dsengine.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_GEGLU, EPI_GELU, EPI_NONE, EPI_SILU, Conv3x3Args, CrossIpArgs, DsEngineError, GemmArgs,
+                   check, lib)
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req_rows(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    """2-D tensor whose rows are contiguous (a column slice of a wider contiguous table is allowed)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != dtype or t.dim() != 2 or t.stride(1) != 1:
+        raise DsEngineError(f"{name}: expected a 2-D CUDA {dtype} tensor with unit column stride")
+    return t
+
+
+def _req(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise DsEngineError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise DsEngineError(f"{name}: tensor is on {t.device}; diffsensei_b200 has no CPU path")
+    if t.dtype != dtype:
+        raise DsEngineError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise DsEngineError(f"{name}: tensor must be contiguous (shape {tuple(t.shape)}, strides {t.stride()})")
+    if ndim is not None and t.dim() != ndim:
+        raise DsEngineError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------- norms
+def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float,
+                   silu: bool = True, out: Optional[torch.Tensor] = None,
+                   stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) on channels-last bf16 ``x`` of shape [B, ..., C] (everything between is 'pixels')."""
+    _req(x, bf16, "groupnorm_silu.x")
+    B, Cc = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * Cc)
+    _req(gamma, f32, "groupnorm_silu.gamma", 1)
+    _req(beta, f32, "groupnorm_silu.beta", 1)
+    if gamma.numel() != Cc or beta.numel() != Cc:
+        raise DsEngineError("groupnorm_silu: gamma/beta must have C elements")
+    out = torch.empty_like(x) if out is None else _req(out, bf16, "groupnorm_silu.out")
+    if stats is None:
+        stats = torch.empty(4 * B * groups, dtype=f32, device=x.device)
+    elif stats.numel() < 4 * B * groups:
+        raise DsEngineError("groupnorm_silu: stats scratch too small")
+    check(lib.ds_groupnorm_silu(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
+                                B, HW, Cc, groups, eps, int(silu), _stream()), "ds_groupnorm_silu")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, bf16, "layernorm.x")
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    _req(gamma, f32, "layernorm.gamma", 1)
+    _req(beta, f32, "layernorm.beta", 1)
+    out = torch.empty_like(x) if out is None else _req(out, bf16, "layernorm.out")
+    check(lib.ds_layernorm(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, Cc, eps, _stream()),
+          "ds_layernorm")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- bbox kernels
+def dialog_embed_add_(sample: torch.Tensor, emb: torch.Tensor, dialog_bbox: torch.Tensor,
+                      round_bf16: bool = True) -> torch.Tensor:
+    """In place: sample[b, y, x, :] += emb inside the union of the (truncated, clamped) dialog boxes."""
+    _req(sample, bf16, "dialog_embed_add.sample", 4)
+    B, H, W, Cc = sample.shape
+    _req(emb, f32, "dialog_embed_add.emb", 1)
+    _req(dialog_bbox, f32, "dialog_embed_add.dialog_bbox", 3)
+    if dialog_bbox.shape[0] != B or dialog_bbox.shape[2] != 4:
+        raise DsEngineError("dialog_embed_add: dialog_bbox must be [B, num_dialogs, 4]")
+    check(lib.ds_dialog_embed_add(sample.data_ptr(), emb.data_ptr(), dialog_bbox.data_ptr(), B, H, W, Cc,
+                                  dialog_bbox.shape[1], int(round_bf16), _stream()), "ds_dialog_embed_add")
+    return sample
+
+
+def ip_mask(bbox: torch.Tensor, seq_len: int, aspect_ratio: float, tokens_per_ip: int, num_dummy: int) -> torch.Tensor:
+    """Stand-alone additive IP mask [B, seq_len, num_dummy + num_ips*tokens_per_ip] fp32 (parity aid)."""
+    _req(bbox, f32, "ip_mask.bbox", 3)
+    B, num_ips, _ = bbox.shape
+    out = torch.empty(B, seq_len, num_dummy + num_ips * tokens_per_ip, dtype=f32, device=bbox.device)
+    check(lib.ds_ip_mask(bbox.data_ptr(), out.data_ptr(), B, seq_len, float(aspect_ratio), num_ips, tokens_per_ip,
+                         num_dummy, _stream()), "ds_ip_mask")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- GEMM / conv
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_NONE,
+         residual: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
+         out: Optional[torch.Tensor] = None, out_fp32: bool = False, out_scale: float = 0.0) -> torch.Tensor:
+    """out[..., Nout] = epilogue(a[..., K] @ w[N, K]^T) on tcgen05; ``a`` may have any leading dims."""
+    _req(a, bf16, "gemm.a")
+    _req(w, bf16, "gemm.w", 2)
+    K = a.shape[-1]
+    M = a.numel() // K
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise DsEngineError(f"gemm: a has K={K} but w is {tuple(w.shape)}")
+    n_out = N // 2 if epilogue == EPI_GEGLU else N
+    if bias is not None:
+        _req(bias, f32, "gemm.bias", 1)
+        if bias.numel() != N:
+            raise DsEngineError("gemm: bias must have N elements")
+    if rowbias is not None:
+        _req_rows(rowbias, f32, "gemm.rowbias")
+        if rowbias.shape[1] != N or rows_per_batch <= 0 or rowbias.shape[0] * rows_per_batch < M:
+            raise DsEngineError("gemm: rowbias must be [ceil(M/rows_per_batch), N]")
+    rowbias_ld = 0 if rowbias is None else rowbias.stride(0)
+    out_shape = tuple(a.shape[:-1]) + (n_out,)
+    if out is None:
+        out = torch.empty(out_shape, dtype=f32 if out_fp32 else bf16, device=a.device)
+    else:
+        _req(out, f32 if out_fp32 else bf16, "gemm.out")
+        if out.numel() != M * n_out:
+            raise DsEngineError(f"gemm: out has {out.numel()} elements, expected {M * n_out}")
+    if residual is not None:
+        _req(residual, bf16, "gemm.residual")
+        if residual.numel() != M * n_out:
+            raise DsEngineError("gemm: residual must match the output shape")
+    args = GemmArgs(a=a.data_ptr(), w=w.data_ptr(), out=out.data_ptr(), bias=_ptr(bias), rowbias=_ptr(rowbias),
+                    residual=_ptr(residual), M=M, N=N, K=K, lda=K, ldw=K, ldo=n_out, ldres=n_out,
+                    rows_per_batch=rows_per_batch, rowbias_ld=rowbias_ld, epilogue=epilogue, out_fp32=int(out_fp32), out_scale=out_scale)
+    check(lib.ds_gemm_bf16(C.byref(args), _stream()), "ds_gemm_bf16")
+    return out
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, stride: int = 1,
+            rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None, out_fp32: bool = False) -> torch.Tensor:
+    """3x3 / pad 1 conv on NHWC bf16 ``x``; ``w`` is packed [Cout, 3, 3, Cin] bf16 (weights.pack_conv3x3)."""
+    _req(x, bf16, "conv3x3.x", 4)
+    B, H, W, Cin = x.shape
+    _req(w, bf16, "conv3x3.w", 4)
+    Cout = w.shape[0]
+    if tuple(w.shape[1:]) != (3, 3, Cin):
+        raise DsEngineError(f"conv3x3: w must be [Cout,3,3,{Cin}], got {tuple(w.shape)}")
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if bias is not None:
+        _req(bias, f32, "conv3x3.bias", 1)
+    if rowbias is not None:
+        _req_rows(rowbias, f32, "conv3x3.rowbias")
+        if tuple(rowbias.shape) != (B, Cout):
+            raise DsEngineError("conv3x3: rowbias must be [B, Cout]")
+    if out is None:
+        out = torch.empty(B, Ho, Wo, Cout, dtype=f32 if out_fp32 else bf16, device=x.device)
+    else:
+        _req(out, f32 if out_fp32 else bf16, "conv3x3.out")
+        if out.numel() != B * Ho * Wo * Cout:
+            raise DsEngineError("conv3x3: out has the wrong number of elements")
+    if residual is not None:
+        _req(residual, bf16, "conv3x3.residual")
+        if residual.numel() != B * Ho * Wo * Cout:
+            raise DsEngineError("conv3x3: residual must match the output shape")
+    args = Conv3x3Args(x=x.data_ptr(), w=w.data_ptr(), out=out.data_ptr(), bias=_ptr(bias), rowbias=_ptr(rowbias),
+                       residual=_ptr(residual), B=B, H=H, W=W, Cin=Cin, Cout=Cout, stride=stride,
+                       rowbias_ld=0 if rowbias is None else rowbias.stride(0),
+                       out_fp32=int(out_fp32), out_scale=0.0)
+    check(lib.ds_conv3x3_nhwc(C.byref(args), _stream()), "ds_conv3x3_nhwc")
+    return out
+
+
+def conv_in(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None):
+    """conv_in: NHWC bf16 [B,H,W,4] -> [B,H,W,Cout]; ``w`` fp32 [Cout,3,3,4]."""
+    _req(x, bf16, "conv_in.x", 4)
+    B, H, W, Cin = x.shape
+    if Cin != 4:
+        raise DsEngineError("conv_in: the latent must have 4 channels")
+    _req(w, f32, "conv_in.w", 4)
+    Cout = w.shape[0]
+    if bias is not None:
+        _req(bias, f32, "conv_in.bias", 1)
+    out = torch.empty(B, H, W, Cout, dtype=bf16, device=x.device) if out is None else _req(out, bf16, "conv_in.out")
+    check(lib.ds_conv_in_3x3(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), B, H, W, Cout, _stream()),
+          "ds_conv_in_3x3")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def attention_self(qkv: torch.Tensor, heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(QK^T/8)V from the fused projection ``qkv`` [B, N, 3*heads*64] -> [B, N, heads*64]."""
+    _req(qkv, bf16, "attention_self.qkv", 3)
+    B, N, C3 = qkv.shape
+    if C3 != 3 * heads * 64:
+        raise DsEngineError(f"attention_self: last dim {C3} != 3*heads*64")
+    if out is None:
+        out = torch.empty(B, N, heads * 64, dtype=bf16, device=qkv.device)
+    else:
+        _req(out, bf16, "attention_self.out")
+    check(lib.ds_attention_self(qkv.data_ptr(), out.data_ptr(), B, N, heads, _stream()), "ds_attention_self")
+    return out
+
+
+def attention_cross_ip(q: torch.Tensor, kv_text: torch.Tensor, kv_ip: torch.Tensor, bbox: torch.Tensor, heads: int,
+                       aspect_ratio: float, ip_scale: float, tokens_per_ip: int, num_dummy: int,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(q, bf16, "attention_cross_ip.q", 3)
+    B, N, Cc = q.shape
+    _req(kv_text, bf16, "attention_cross_ip.kv_text", 3)
+    _req(kv_ip, bf16, "attention_cross_ip.kv_ip", 3)
+    _req(bbox, f32, "attention_cross_ip.bbox", 3)
+    if Cc != heads * 64 or kv_text.shape[2] != 2 * Cc or kv_ip.shape[2] != 2 * Cc:
+        raise DsEngineError("attention_cross_ip: channel dims do not match heads*64")
+    if kv_text.shape[0] != B or kv_ip.shape[0] != B or bbox.shape[0] != B or bbox.shape[2] != 4:
+        raise DsEngineError("attention_cross_ip: batch dims do not match")
+    out = torch.empty_like(q) if out is None else _req(out, bf16, "attention_cross_ip.out")
+    args = CrossIpArgs(q=q.data_ptr(), kv_text=kv_text.data_ptr(), kv_ip=kv_ip.data_ptr(), bbox=bbox.data_ptr(),
+                       out=out.data_ptr(), B=B, N=N, heads=heads, n_text=kv_text.shape[1], n_ip=kv_ip.shape[1],
+                       num_ips=bbox.shape[1], tokens_per_ip=tokens_per_ip, num_dummy=num_dummy,
+                       aspect_ratio=float(aspect_ratio), ip_scale=float(ip_scale))
+    check(lib.ds_attention_cross_ip(C.byref(args), _stream()), "ds_attention_cross_ip")
+    return out
+
+
+def resampler_attn(q: torch.Tensor, kv: torch.Tensor, heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(q, bf16, "resampler_attn.q", 3)
+    _req(kv, bf16, "resampler_attn.kv", 3)
+    Bc, nq, Cc = q.shape
+    if Cc != heads * 64 or kv.shape[0] != Bc or kv.shape[2] != 2 * Cc:
+        raise DsEngineError("resampler_attn: shape mismatch")
+    out = torch.empty_like(q) if out is None else _req(out, bf16, "resampler_attn.out")
+    check(lib.ds_resampler_attn(q.data_ptr(), kv.data_ptr(), out.data_ptr(), Bc, nq, kv.shape[1], heads, _stream()),
+          "ds_resampler_attn")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- glue
+def nchw_to_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if x.dtype not in (f32, bf16):
+        raise DsEngineError(f"nchw_to_nhwc: unsupported dtype {x.dtype}")
+    _req(x, x.dtype, "nchw_to_nhwc.x", 4)
+    B, Cc, H, W = x.shape
+    out = torch.empty(B, H, W, Cc, dtype=bf16, device=x.device) if out is None else _req(out, bf16, "nchw_to_nhwc.out")
+    check(lib.ds_nchw_to_nhwc(x.data_ptr(), int(x.dtype == f32), out.data_ptr(), B, Cc, H, W, _stream()),
+          "ds_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, dtype=f32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, bf16, "nhwc_to_nchw.x", 4)
+    B, H, W, Cc = x.shape
+    if dtype not in (f32, bf16):
+        raise DsEngineError(f"nhwc_to_nchw: unsupported dtype {dtype}")
+    out = torch.empty(B, Cc, H, W, dtype=dtype, device=x.device) if out is None else _req(out, dtype, "nhwc_to_nchw.out")
+    check(lib.ds_nhwc_to_nchw(x.data_ptr(), out.data_ptr(), int(dtype == f32), B, Cc, H, W, _stream()),
+          "ds_nhwc_to_nchw")
+    return out
+
+
+def upsample_nearest(x: torch.Tensor, Ho: int, Wo: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, bf16, "upsample_nearest.x", 4)
+    B, H, W, Cc = x.shape
+    out = torch.empty(B, Ho, Wo, Cc, dtype=bf16, device=x.device) if out is None else _req(out, bf16, "upsample.out")
+    check(lib.ds_upsample_nearest(x.data_ptr(), out.data_ptr(), B, H, W, Cc, Ho, Wo, _stream()), "ds_upsample_nearest")
+    return out
+
+
+def concat_channels(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(a, bf16, "concat_channels.a")
+    _req(b, bf16, "concat_channels.b")
+    C1, C2 = a.shape[-1], b.shape[-1]
+    pixels = a.numel() // C1
+    if b.numel() // C2 != pixels:
+        raise DsEngineError("concat_channels: pixel counts differ")
+    if out is None:
+        out = torch.empty(tuple(a.shape[:-1]) + (C1 + C2,), dtype=bf16, device=a.device)
+    else:
+        _req(out, bf16, "concat_channels.out")
+    check(lib.ds_concat_channels(a.data_ptr(), b.data_ptr(), out.data_ptr(), pixels, C1, C2, _stream()),
+          "ds_concat_channels")
+    return out
+
+
+def silu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, bf16, "silu.x")
+    out = torch.empty_like(x) if out is None else _req(out, bf16, "silu.out")
+    check(lib.ds_silu(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "ds_silu")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[cos | sin](t * w) features, bf16 [rows, dim] (diffusers Timesteps(flip_sin_to_cos=True, shift=0))."""
+    _req(t, f32, "timestep_embedding.t", 1)
+    rows = t.numel()
+    out = torch.empty(rows, dim, dtype=bf16, device=t.device) if out is None else _req(out, bf16, "timestep.out")
+    check(lib.ds_timestep_embedding(t.data_ptr(), out.data_ptr(), rows, dim, _stream()), "ds_timestep_embedding")
+    return out
+
+
+def cfg_ddim_step_(noise_pred: torch.Tensor, latents: torch.Tensor, model_in: torch.Tensor, coef: torch.Tensor,
+                   guidance: float) -> None:
+    """In place: latents (fp32 NHWC [bs,H,W,4]) <- DDIM(CFG(noise_pred)); model_in (bf16 [2bs,H,W,4]) <- cat[x]*2."""
+    _req(noise_pred, bf16, "cfg_ddim_step.noise_pred", 4)
+    _req(latents, f32, "cfg_ddim_step.latents", 4)
+    _req(model_in, bf16, "cfg_ddim_step.model_in", 4)
+    _req(coef, f32, "cfg_ddim_step.coef", 1)
+    bs, H, W, Cc = latents.shape
+    if noise_pred.shape != (2 * bs, H, W, Cc) or model_in.shape != (2 * bs, H, W, Cc) or coef.numel() < 2:
+        raise DsEngineError("cfg_ddim_step: shape mismatch")
+    check(lib.ds_cfg_ddim_step(noise_pred.data_ptr(), latents.data_ptr(), model_in.data_ptr(), coef.data_ptr(),
+                               float(guidance), bs, H * W, Cc, _stream()), "ds_cfg_ddim_step")
+
+
+launch_count = _lib.launch_count

@@ -1,0 +1,227 @@
+"""DiffSenseiPipeline — the sampling loop of the reference pipeline on the B200 engine.
+
+Mirrors ``src/pipelines/pipeline_diffsensei.py``:
+  * ``register_manga_modules`` (:73-79), ``check_inputs`` (:81-102, same ValueErrors), ``set_ip_scale`` (:172-178)
+  * ``prepare_ip_image_embeds`` (:104-154) from the image-encoder outputs onward: pad to ``max_num_ips``, zero the
+    padded characters, Resampler(pos) and Resampler(zeros), optional paste of MLLM-adapted embeds (:143-145),
+    repeat to ``num_samples``; ``prepare_dialog_bbox`` (:156-170)
+  * the CFG denoise loop (:293-337) — ``denoise``: the hot path.
+Out of scope this round ("next" ring): the SDXL text encoders, CLIP / Magi image encoders and
+the VAE.  ``__call__`` keeps the reference's keyword surface but takes their OUTPUTS as tensors
+(``prompt_embeds`` ..., ``clip_image_embeds`` / ``magi_image_embeds``) and returns latents; passing a raw
+``prompt`` string without embeddings raises, it does not fall back to anything.
+
+Loop structure on the GPU (one process per GPU, one stream):
+  once per panel : K|V projections of text and IP tokens for all cross-attention layers, time-embedding
+                   row-bias table for all T steps, (alpha_t, alpha_prev) table
+  per step       : ONE CUDA-graph replay = UNet forward (NHWC bf16) + fused CFG/DDIM update, preceded by two
+                   tiny device-to-device copies that select this step's row of the two tables.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from .scheduler import DDIMScheduler
+from .unet import UNetMangaEngine
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+class DiffSenseiPipeline:
+    def __init__(self, unet: UNetMangaEngine, scheduler: Optional[DDIMScheduler] = None, vae_scale_factor: int = 8,
+                 default_sample_size: int = 128):
+        self.unet = unet
+        self.scheduler = scheduler or DDIMScheduler()
+        self.vae_scale_factor = vae_scale_factor
+        self.default_sample_size = default_sample_size
+        self.image_proj_model = None
+        self.magi_image_encoder = None
+        self._guidance_scale = 5.0
+        self._graph = None
+        self._graph_key = None
+
+    # ------------------------------------------------------------------------------ reference surface
+    def register_manga_modules(self, magi_image_encoder=None, image_proj_model=None):
+        self.magi_image_encoder = magi_image_encoder
+        self.image_proj_model = image_proj_model
+
+    @property
+    def guidance_scale(self):
+        return self._guidance_scale
+
+    @property
+    def do_classifier_free_guidance(self):
+        return self._guidance_scale > 1
+
+    def check_inputs(self, prompt, prompt_2, ip_images, ip_image_embeds, ip_bbox):
+        if prompt is None:
+            raise ValueError(f"`prompt` has to be of type `str` but is {type(prompt)}")
+        elif prompt is not None and not isinstance(prompt, str):
+            raise ValueError(f"`prompt` has to be of type `str` but is {type(prompt)}")
+        elif prompt_2 is not None and not isinstance(prompt_2, str):
+            raise ValueError(f"`prompt_2` has to be of type `str` but is {type(prompt_2)}")
+        if len(ip_images) > 0 and ip_image_embeds is not None:
+            raise ValueError("`ip_images` and `ip_image_embeds` can not be input together!")
+        num_ips = len(ip_image_embeds) if ip_image_embeds is not None else len(ip_images)
+        if num_ips != len(ip_bbox):
+            raise ValueError(f"`ip_images` must have the same length as `ip_bbox`. But they are in length {num_ips} "
+                             f"and {len(ip_bbox)}!")
+
+    def set_ip_scale(self, scale):
+        self.unet.set_ip_scale(scale)
+
+    def prepare_ip_image_embeds(self, clip_image_embeds: torch.Tensor, magi_image_embeds: torch.Tensor,
+                                ip_image_embeds: Optional[torch.Tensor], ip_bbox: List[List[float]], num_samples: int):
+        """clip_image_embeds (1, n, S, D) / magi_image_embeds (1, n, Dm) for the n <= max_num_ips real characters."""
+        cfg = self.unet.cfg
+        dev = self.unet.device
+        m = cfg.max_num_ips
+        ip_bbox = [list(b) for b in ip_bbox[:m]]
+        num_ips = min(clip_image_embeds.shape[1], m)
+        clip = torch.zeros(1, m, *clip_image_embeds.shape[2:], dtype=clip_image_embeds.dtype, device=dev)
+        magi = torch.zeros(1, m, magi_image_embeds.shape[-1], dtype=magi_image_embeds.dtype, device=dev)
+        clip[0, :num_ips] = clip_image_embeds[0, :num_ips].to(dev)      # padded characters stay zero (:131-132)
+        magi[0, :num_ips] = magi_image_embeds[0, :num_ips].to(dev)
+        while len(ip_bbox) < m:
+            ip_bbox.append([0.0, 0.0, 0.0, 0.0])                        # :121-122
+        image_embeds = self.image_proj_model(clip, magi)                               # :133
+        negative_image_embeds = self.image_proj_model(torch.zeros_like(clip), torch.zeros_like(magi))   # :135
+        bbox = torch.tensor(ip_bbox, dtype=f32).unsqueeze(0).to(dev)                   # :137 (stays fp32)
+        neg_bbox = torch.zeros_like(bbox)
+        nv = cfg.num_vision_tokens
+        if ip_image_embeds is not None:                                                # :143-145
+            ip_image_embeds = ip_image_embeds[:m]
+            n, _, dim = ip_image_embeds.shape
+            image_embeds[0, nv:(1 + n) * nv, :] = ip_image_embeds.reshape(1, -1, dim).to(image_embeds)
+        rep = lambda t: t.repeat(num_samples, 1, 1)
+        return rep(negative_image_embeds).to(bf16), rep(image_embeds).to(bf16), rep(neg_bbox), rep(bbox)
+
+    def prepare_dialog_bbox(self, dialog_bbox: List[List[float]], num_samples: int):
+        m = self.unet.cfg.max_num_dialogs
+        dialog_bbox = [list(b) for b in dialog_bbox[:m]]
+        while len(dialog_bbox) < m:
+            dialog_bbox.append([0.0, 0.0, 0.0, 0.0])
+        db = torch.tensor(dialog_bbox, dtype=f32).unsqueeze(0).to(device=self.unet.device, dtype=self.unet.dtype)
+        db = db.repeat(num_samples, 1, 1)                                              # :166-167
+        return torch.zeros_like(db), db
+
+    def prepare_latents(self, num_samples, channels, height, width, generator=None):
+        shape = (num_samples, channels, int(height) // self.vae_scale_factor, int(width) // self.vae_scale_factor)
+        dev = self.unet.device
+        gdev = generator.device if generator is not None else dev
+        lat = torch.randn(shape, generator=generator, device=gdev, dtype=f32).to(dev)
+        return lat * self.scheduler.init_noise_sigma
+
+    # ------------------------------------------------------------------------------ the hot loop
+    @torch.no_grad()
+    def denoise(self, latents: torch.Tensor, prompt_embeds: torch.Tensor, add_text_embeds: torch.Tensor,
+                add_time_ids: torch.Tensor, bbox: torch.Tensor, aspect_ratio: float,
+                dialog_bbox: Optional[torch.Tensor], num_inference_steps: int, guidance_scale: float,
+                use_graph: bool = True, on_step=None) -> torch.Tensor:
+        """pipeline_diffsensei.py:306-337.  ``latents`` NCHW fp32 (bs,4,h,w); conditions already concatenated
+        [negative ; positive] along batch (:293-304).  Returns the final latents, NCHW fp32."""
+        unet, dev = self.unet, self.unet.device
+        bs = latents.shape[0]
+        if prompt_embeds.shape[0] != 2 * bs:
+            raise ValueError("denoise expects CFG-concatenated conditions: prompt_embeds.shape[0] == 2 * num_samples")
+        timesteps = self.scheduler.set_timesteps(num_inference_steps, device=dev)
+        coef_table = self.scheduler.coefficient_table(dev)                              # [T, 2]
+        cond = unet.prepare_conditions(prompt_embeds.to(dev), bbox, aspect_ratio)
+        temb_table = torch.stack([unet.time_rowbias(torch.tensor(float(t)), add_text_embeds, add_time_ids)
+                                  for t in timesteps])                                  # [T, 2bs, sumC] fp32
+        lat = latents.to(device=dev, dtype=f32).permute(0, 2, 3, 1).contiguous()         # fp32 NHWC master copy
+        model_in = torch.cat([lat, lat]).to(bf16).contiguous()                          # :315 (first step only)
+        db, round_bf16 = None, True
+        if dialog_bbox is not None:
+            round_bf16 = dialog_bbox.dtype == bf16
+            db = dialog_bbox.to(device=dev, dtype=f32).contiguous()
+        temb_cur = temb_table[0].clone()
+        coef_cur = coef_table[0].clone()
+
+        def step():
+            eps = unet.forward_nhwc(model_in, temb_cur, cond, db, round_bf16)           # :322-329
+            ops.cfg_ddim_step_(eps, lat, model_in, coef_cur, guidance_scale)            # :332-337 (+ :315 of next)
+
+        graph = None
+        if use_graph:
+            stream = torch.cuda.Stream(device=dev)
+            stream.wait_stream(torch.cuda.current_stream(dev))
+            lat0, min0 = lat.clone(), model_in.clone()
+            with torch.cuda.stream(stream):
+                step()                                   # warm-up outside capture (lazy func attributes, allocator)
+            torch.cuda.current_stream(dev).wait_stream(stream)
+            lat.copy_(lat0)
+            model_in.copy_(min0)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            lat.copy_(lat0)
+            model_in.copy_(min0)
+        for i, t in enumerate(timesteps):
+            temb_cur.copy_(temb_table[i])
+            coef_cur.copy_(coef_table[i])
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
+            if on_step is not None:
+                on_step(i, t, lat)
+        return lat.permute(0, 3, 1, 2).contiguous()
+
+    # ------------------------------------------------------------------------------ reference-shaped entry point
+    @torch.no_grad()
+    def __call__(self, prompt: Optional[str] = None, prompt_2: Optional[str] = None, height: Optional[int] = None,
+                 width: Optional[int] = None, num_inference_steps: int = 40, guidance_scale: float = 5.0,
+                 negative_prompt=None, negative_prompt_2=None, num_samples: int = 1, generator=None,
+                 original_size=None, crops_coords_top_left=(0, 0), target_size=None, min_size_step: int = 8,
+                 ip_images=(), ip_image_embeds: Optional[torch.Tensor] = None, ip_bbox=(), ip_scale: float = 1.0,
+                 dialog_bbox=(),
+                 # outputs of the out-of-scope encoders, required instead of raw prompt / images:
+                 prompt_embeds: Optional[torch.Tensor] = None, negative_prompt_embeds: Optional[torch.Tensor] = None,
+                 pooled_prompt_embeds: Optional[torch.Tensor] = None,
+                 negative_pooled_prompt_embeds: Optional[torch.Tensor] = None,
+                 clip_image_embeds: Optional[torch.Tensor] = None, magi_image_embeds: Optional[torch.Tensor] = None,
+                 latents: Optional[torch.Tensor] = None, output_type: str = "latent", use_graph: bool = True):
+        height = height or self.default_sample_size * self.vae_scale_factor
+        width = width or self.default_sample_size * self.vae_scale_factor
+        original_size = original_size or (height, width)
+        target_size = target_size or (height, width)
+        if prompt_embeds is None:
+            self.check_inputs(prompt, prompt_2, list(ip_images), ip_image_embeds, list(ip_bbox))
+            raise NotImplementedError(
+                "text encoding (encode_prompt, pipeline_diffsensei.py:232-245) is outside the B200 hot path this "
+                "round: pass prompt_embeds / negative_prompt_embeds / pooled_prompt_embeds / "
+                "negative_pooled_prompt_embeds")
+        if len(ip_images) > 0:
+            raise NotImplementedError("image encoding (CLIP / Magi, pipeline_diffsensei.py:125-128) is outside the "
+                                      "hot path this round: pass clip_image_embeds / magi_image_embeds")
+        if output_type != "latent":
+            raise NotImplementedError("VAE decode (pipeline_diffsensei.py:339-367) is outside the hot path this round")
+        n_real = clip_image_embeds.shape[1] if clip_image_embeds is not None else 0
+        num_ips = len(ip_image_embeds) if ip_image_embeds is not None else n_real
+        if num_ips != len(ip_bbox):
+            raise ValueError(f"`ip_images` must have the same length as `ip_bbox`. But they are in length {num_ips} "
+                             f"and {len(ip_bbox)}!")
+        self._guidance_scale = guidance_scale
+        self.set_ip_scale(ip_scale)
+        dev = self.unet.device
+        if latents is None:
+            latents = self.prepare_latents(num_samples, self.unet.config.in_channels, height, width, generator)
+        neg_img, img, neg_bbox, bbox = self.prepare_ip_image_embeds(clip_image_embeds, magi_image_embeds,
+                                                                    ip_image_embeds, list(ip_bbox), num_samples)
+        aspect_ratio = latents.shape[-2] / latents.shape[-1]                            # :272
+        time_ids = torch.tensor([list(original_size) + list(crops_coords_top_left) + list(target_size)],
+                                dtype=f32, device=dev)                                  # _get_add_time_ids
+        neg_db, db = self.prepare_dialog_bbox(list(dialog_bbox), num_samples)
+        rep = lambda t: t.to(dev).repeat(num_samples, 1, 1) if t.dim() == 3 else t.to(dev).repeat(num_samples, 1)
+        pe = torch.cat([rep(negative_prompt_embeds), rep(prompt_embeds)], dim=0).to(bf16)          # :294
+        te = torch.cat([rep(negative_pooled_prompt_embeds), rep(pooled_prompt_embeds)], dim=0)     # :295
+        ti = time_ids.repeat(2 * num_samples, 1)                                                   # :296,302
+        pe = torch.cat([pe, torch.cat([neg_img, img], dim=0)], dim=1)                              # :297,303
+        final = self.denoise(latents, pe, te, ti, torch.cat([neg_bbox, bbox], dim=0), aspect_ratio,
+                             torch.cat([neg_db, db], dim=0), num_inference_steps, guidance_scale, use_graph=use_graph)
+        return SimpleNamespace(images=final, latents=final)

@@ -42,9 +42,10 @@ uint64_t ds_launch_count(void);
  * src/models/unet.py:251-261,281-290,316-338.
  *   x, y      : [B][HW][C] bf16 (y may alias x)
  *   gamma/beta: [C] fp32
- *   stats     : scratch, 2*B*groups floats (mean, rstd) — written then read by the two passes
- * Statistics are computed in fp32 over the bf16 input (two-pass Welford-free: sum / sum-of-squares
- * of values centred on a per-group pilot), normalisation + affine + SiLU in fp32, one rounding to bf16.
+ *   stats     : scratch, 4*B*groups floats (= 2*B*groups doubles: per-(sample, group) sum and sum of
+ *               squares), 8-byte aligned; zeroed, written and read by the call itself
+ * Per-thread partial sums are fp32, every cross-thread accumulation is fp64; normalisation + affine +
+ * SiLU run in fp32 with one rounding to bf16.
  * --------------------------------------------------------------------------------------------- */
 int ds_groupnorm_silu(const void* x, void* y, const float* gamma, const float* beta, float* stats, int B, int HW,
                       int C, int groups, float eps, int apply_silu, void* stream);
@@ -71,7 +72,7 @@ int ds_dialog_embed_add(void* sample, const float* emb, const float* dialog_bbox
  *   bbox : [B][num_ips][4] fp32;  mask out: [B][N][num_dummy + num_ips*tokens_per_ip] fp32 in {0,-10000}
  *   (identical across heads, so the head dim is not materialised). (H', W') are re-derived from
  *   (N, aspect_ratio) exactly as the reference does (:131-139). */
-int ds_ip_mask(const float* bbox, float* mask, int B, int N, float aspect_ratio, int num_ips, int tokens_per_ip,
+int ds_ip_mask(const float* bbox, float* mask, int B, int N, double aspect_ratio, int num_ips, int tokens_per_ip,
                int num_dummy, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -106,6 +107,7 @@ typedef struct {
   int32_t M, N, K;
   int32_t lda, ldw, ldo, ldres;
   int32_t rows_per_batch; /* only read when rowbias != NULL                */
+  int32_t rowbias_ld;     /* row stride of rowbias in floats; 0 means N     */
   int32_t epilogue;       /* DS_EPI_*                                      */
   int32_t out_fp32;       /* 1: `out` is fp32                              */
   float out_scale;        /* 0 or 1: no scaling                            */
@@ -134,6 +136,7 @@ typedef struct {
   const void* residual;
   int32_t B, H, W, Cin, Cout;
   int32_t stride;
+  int32_t rowbias_ld; /* row stride of rowbias in floats; 0 means Cout */
   int32_t out_fp32;
   float out_scale;
 } ds_conv3x3_args;
@@ -175,7 +178,7 @@ typedef struct {
   int32_t B, N, heads;
   int32_t n_text, n_ip;
   int32_t num_ips, tokens_per_ip, num_dummy;
-  float aspect_ratio;
+  double aspect_ratio; /* latent H / W as a Python float (double): pipeline_diffsensei.py:272 */
   float ip_scale;
 } ds_cross_ip_args;
 
