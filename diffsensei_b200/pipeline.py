@@ -117,6 +117,13 @@ class DiffSenseiPipeline:
         return lat * self.scheduler.init_noise_sigma
 
     # ------------------------------------------------------------------------------ the hot loop
+    def make_stepper(self, latents: torch.Tensor, prompt_embeds: torch.Tensor, add_text_embeds: torch.Tensor,
+                     add_time_ids: torch.Tensor, bbox: torch.Tensor, aspect_ratio: float,
+                     dialog_bbox: Optional[torch.Tensor], num_inference_steps: int, guidance_scale: float,
+                     use_graph: bool = True) -> "DenoiseStepper":
+        return DenoiseStepper(self, latents, prompt_embeds, add_text_embeds, add_time_ids, bbox, aspect_ratio,
+                              dialog_bbox, num_inference_steps, guidance_scale, use_graph)
+
     @torch.no_grad()
     def denoise(self, latents: torch.Tensor, prompt_embeds: torch.Tensor, add_text_embeds: torch.Tensor,
                 add_time_ids: torch.Tensor, bbox: torch.Tensor, aspect_ratio: float,
@@ -124,53 +131,13 @@ class DiffSenseiPipeline:
                 use_graph: bool = True, on_step=None) -> torch.Tensor:
         """pipeline_diffsensei.py:306-337.  ``latents`` NCHW fp32 (bs,4,h,w); conditions already concatenated
         [negative ; positive] along batch (:293-304).  Returns the final latents, NCHW fp32."""
-        unet, dev = self.unet, self.unet.device
-        bs = latents.shape[0]
-        if prompt_embeds.shape[0] != 2 * bs:
-            raise ValueError("denoise expects CFG-concatenated conditions: prompt_embeds.shape[0] == 2 * num_samples")
-        timesteps = self.scheduler.set_timesteps(num_inference_steps, device=dev)
-        coef_table = self.scheduler.coefficient_table(dev)                              # [T, 2]
-        cond = unet.prepare_conditions(prompt_embeds.to(dev), bbox, aspect_ratio)
-        temb_table = torch.stack([unet.time_rowbias(torch.tensor(float(t)), add_text_embeds, add_time_ids)
-                                  for t in timesteps])                                  # [T, 2bs, sumC] fp32
-        lat = latents.to(device=dev, dtype=f32).permute(0, 2, 3, 1).contiguous()         # fp32 NHWC master copy
-        model_in = torch.cat([lat, lat]).to(bf16).contiguous()                          # :315 (first step only)
-        db, round_bf16 = None, True
-        if dialog_bbox is not None:
-            round_bf16 = dialog_bbox.dtype == bf16
-            db = dialog_bbox.to(device=dev, dtype=f32).contiguous()
-        temb_cur = temb_table[0].clone()
-        coef_cur = coef_table[0].clone()
-
-        def step():
-            eps = unet.forward_nhwc(model_in, temb_cur, cond, db, round_bf16)           # :322-329
-            ops.cfg_ddim_step_(eps, lat, model_in, coef_cur, guidance_scale)            # :332-337 (+ :315 of next)
-
-        graph = None
-        if use_graph:
-            stream = torch.cuda.Stream(device=dev)
-            stream.wait_stream(torch.cuda.current_stream(dev))
-            lat0, min0 = lat.clone(), model_in.clone()
-            with torch.cuda.stream(stream):
-                step()                                   # warm-up outside capture (lazy func attributes, allocator)
-            torch.cuda.current_stream(dev).wait_stream(stream)
-            lat.copy_(lat0)
-            model_in.copy_(min0)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                step()
-            lat.copy_(lat0)
-            model_in.copy_(min0)
-        for i, t in enumerate(timesteps):
-            temb_cur.copy_(temb_table[i])
-            coef_cur.copy_(coef_table[i])
-            if graph is not None:
-                graph.replay()
-            else:
-                step()
+        st = self.make_stepper(latents, prompt_embeds, add_text_embeds, add_time_ids, bbox, aspect_ratio, dialog_bbox,
+                               num_inference_steps, guidance_scale, use_graph)
+        for i, t in enumerate(st.timesteps):
+            st.step(i)
             if on_step is not None:
-                on_step(i, t, lat)
-        return lat.permute(0, 3, 1, 2).contiguous()
+                on_step(i, t, st.lat)
+        return st.latents_nchw()
 
     # ------------------------------------------------------------------------------ reference-shaped entry point
     @torch.no_grad()
@@ -225,3 +192,85 @@ class DiffSenseiPipeline:
         final = self.denoise(latents, pe, te, ti, torch.cat([neg_bbox, bbox], dim=0), aspect_ratio,
                              torch.cat([neg_db, db], dim=0), num_inference_steps, guidance_scale, use_graph=use_graph)
         return SimpleNamespace(images=final, latents=final)
+
+
+class DenoiseStepper:
+    """Per-panel state of the denoise loop (pipeline_diffsensei.py:306-337), resident on one GPU.
+
+    Construction does everything that is timestep-invariant: the K|V projections of the text / IP tokens for all
+    cross-attention layers, the time-embedding row-bias table and the DDIM coefficient table for all T steps, and
+    (``use_graph``) captures ONE iteration — UNet forward + fused CFG/DDIM update — into a CUDA graph.
+    ``step(i)`` runs iteration i on device-resident latents; ``step_host(i, x)`` is the same call with HOST
+    buffers (pinned fp32 NCHW latents in, updated latents out), i.e. what a caller on the other side of the
+    plugin boundary sees.
+    """
+
+    @torch.no_grad()
+    def __init__(self, pipe: DiffSenseiPipeline, latents, prompt_embeds, add_text_embeds, add_time_ids, bbox,
+                 aspect_ratio, dialog_bbox, num_inference_steps, guidance_scale, use_graph=True):
+        unet, dev = pipe.unet, pipe.unet.device
+        self.unet, self.dev, self.guidance = unet, dev, float(guidance_scale)
+        bs = latents.shape[0]
+        if prompt_embeds.shape[0] != 2 * bs:
+            raise ValueError("denoise expects CFG-concatenated conditions: prompt_embeds.shape[0] == 2 * num_samples")
+        self.timesteps = pipe.scheduler.set_timesteps(num_inference_steps, device=dev)
+        self.coef_table = pipe.scheduler.coefficient_table(dev)                         # [T, 2]
+        self.cond = unet.prepare_conditions(prompt_embeds.to(dev), bbox, aspect_ratio)
+        self.temb_table = torch.stack([unet.time_rowbias(torch.tensor(float(t)), add_text_embeds, add_time_ids)
+                                       for t in self.timesteps])                        # [T, 2bs, sumC] fp32
+        self.lat = latents.to(device=dev, dtype=f32).permute(0, 2, 3, 1).contiguous()    # fp32 NHWC master copy
+        self.model_in = torch.cat([self.lat, self.lat]).to(bf16).contiguous()           # :315 (first step only)
+        self.db, self.round_bf16 = None, True
+        if dialog_bbox is not None:
+            self.round_bf16 = dialog_bbox.dtype == bf16
+            self.db = dialog_bbox.to(device=dev, dtype=f32).contiguous()
+        self.temb_cur = self.temb_table[0].clone()
+        self.coef_cur = self.coef_table[0].clone()
+        self._host_in = None
+        self.graph = None
+        if use_graph:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            lat0, min0 = self.lat.clone(), self.model_in.clone()
+            with torch.cuda.stream(side):
+                self._launch()                           # warm-up outside capture (function attributes, allocator)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.lat.copy_(lat0)
+            self.model_in.copy_(min0)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._launch()
+            self.lat.copy_(lat0)
+            self.model_in.copy_(min0)
+
+    def _launch(self):
+        eps = self.unet.forward_nhwc(self.model_in, self.temb_cur, self.cond, self.db, self.round_bf16)   # :322-329
+        ops.cfg_ddim_step_(eps, self.lat, self.model_in, self.coef_cur, self.guidance)   # :332-337 (+ :315 of next)
+
+    @torch.no_grad()
+    def step(self, i: int) -> None:
+        self.temb_cur.copy_(self.temb_table[i])
+        self.coef_cur.copy_(self.coef_table[i])
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._launch()
+
+    @torch.no_grad()
+    def step_host(self, i: int, latents_host: torch.Tensor, out_host: torch.Tensor) -> torch.Tensor:
+        """latents_host / out_host: pinned fp32 NCHW (bs,4,h,w) HOST tensors.  H2D + step + D2H, then waits."""
+        if self._host_in is None:
+            self._host_in = torch.empty(latents_host.shape, dtype=f32, device=self.dev)
+        self._host_in.copy_(latents_host, non_blocking=True)                            # H2D
+        nhwc = self._host_in.permute(0, 2, 3, 1)
+        self.lat.copy_(nhwc)
+        bs = self.lat.shape[0]
+        self.model_in[:bs].copy_(nhwc)
+        self.model_in[bs:].copy_(nhwc)
+        self.step(i)
+        out_host.copy_(self.lat.permute(0, 3, 1, 2), non_blocking=True)                 # D2H
+        torch.cuda.current_stream(self.dev).synchronize()
+        return out_host
+
+    def latents_nchw(self) -> torch.Tensor:
+        return self.lat.permute(0, 3, 1, 2).contiguous()

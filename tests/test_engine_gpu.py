@@ -1,0 +1,170 @@
+"""End-to-end parity of the engine against the CPU oracle on identical weights, latents and embeddings:
+UNetMangaEngine.forward, the Resampler, and the CFG + DDIM denoise loop (graph replay vs eager launches).
+Tolerances from BASELINE.md §3: bf16 engine vs fp32 oracle rel-L2 <= 3e-2 on the UNet output after one step."""
+import dataclasses
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_l2
+
+pytestmark = pytest.mark.gpu
+bf16, f32 = torch.bfloat16, torch.float32
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    import diffsensei_b200 as ds
+    from oracle.unet import OracleUNet
+    torch.manual_seed(0)
+    oracle = OracleUNet(ds.TINY).eval()
+    oracle.set_ip_scale(0.6)
+    engine = ds.UNetMangaEngine(ds.TINY, DEV)
+    engine.set_manga_modules(max_num_ips=4, num_vision_tokens=16, max_num_dialogs=8)
+    engine.load_state_dict(oracle.state_dict())
+    engine.set_ip_scale(0.6)
+    return ds, oracle, engine
+
+
+def _inputs(cfg, bs, h, w, seed=1, n_chars=2, dialogs=True):
+    g = torch.Generator().manual_seed(seed)
+    lat = torch.randn(bs, 4, h, w, generator=g)
+    ehs = torch.randn(2 * bs, 77 + 80, cfg.cross_attention_dim, generator=g)
+    pooled = torch.randn(2 * bs, cfg.pooled_text_dim, generator=g)
+    time_ids = torch.tensor([[h * 8.0, w * 8.0, 0, 0, h * 8.0, w * 8.0]] * (2 * bs))
+    boxes = [[.05, .10, .50, .95], [.50, .15, .95, .90], [.30, .55, .70, 1.0], [.00, .00, .30, .40]]
+    pos = boxes[:n_chars] + [[0.0] * 4] * (4 - n_chars)
+    bbox = torch.tensor([[[0.0] * 4] * 4] * bs + [pos] * bs)
+    dialog = None
+    if dialogs:
+        d = [[.05, .05, .30, .20], [.70, .05, .95, .22], [.40, .80, .65, .97]] + [[0.0] * 4] * 5
+        dialog = torch.tensor([[[0.0] * 4] * 8] * bs + [d] * bs)
+    return lat, ehs, pooled, time_ids, bbox, dialog
+
+
+@pytest.mark.parametrize("h,w,n_chars,dialogs", [(16, 24, 2, True), (16, 16, 1, False), (18, 27, 4, True),
+                                                 (17, 22, 3, True)])
+def test_unet_forward_matches_oracle(tiny, h, w, n_chars, dialogs):
+    """UNetMangaModel.forward surface (NCHW in/out, kwargs as the pipeline passes them, unet.py:116-132);
+    18x27 and 17x22 are not multiples of 4 -> exercises the forward_upsample_size path (unet.py:152-162,312-313)
+    and odd feature maps."""
+    ds, oracle, engine = tiny
+    lat, ehs, pooled, time_ids, bbox, dialog = _inputs(ds.TINY, 1, h, w, n_chars=n_chars, dialogs=dialogs)
+    x = torch.cat([lat] * 2)
+    ar = h / w
+    want = oracle(x, 741, ehs, pooled, time_ids, bbox, ar, dialog)
+    out = engine.forward(x.to(DEV), torch.tensor(741), ehs.to(DEV, bf16),
+                         added_cond_kwargs={"text_embeds": pooled.to(DEV), "time_ids": time_ids.to(DEV)},
+                         cross_attention_kwargs={"bbox": bbox.to(DEV), "aspect_ratio": ar},
+                         dialog_bbox=None if dialog is None else dialog.to(DEV))
+    assert isinstance(out, ds.UNet2DConditionOutput) and out.sample.shape == x.shape and out.sample.dtype == f32
+    assert rel_l2(out.sample, want) < 3e-2
+    tup = engine.forward(x.to(DEV), 741, ehs.to(DEV, bf16),
+                         added_cond_kwargs={"text_embeds": pooled.to(DEV), "time_ids": time_ids.to(DEV)},
+                         cross_attention_kwargs={"bbox": bbox.to(DEV), "aspect_ratio": ar},
+                         dialog_bbox=None if dialog is None else dialog.to(DEV), return_dict=False)
+    assert isinstance(tup, tuple) and torch.equal(tup[0], out.sample)
+
+
+def test_unet_api_errors(tiny):
+    ds, _oracle, engine = tiny
+    x = torch.zeros(2, 4, 16, 16, device=DEV)
+    with pytest.raises(ValueError, match="bbox"):
+        engine.forward(x, 1, torch.zeros(2, 157, 128, device=DEV), added_cond_kwargs={"text_embeds": 0, "time_ids": 0})
+    with pytest.raises(NotImplementedError):
+        engine.forward(x, 1, torch.zeros(2, 157, 128, device=DEV), attention_mask=torch.ones(2, 4))
+    fresh = ds.UNetMangaEngine(ds.TINY, DEV)
+    with pytest.raises(RuntimeError, match="load_state_dict"):
+        fresh.forward(x, 1, torch.zeros(2, 157, 128, device=DEV))
+    with pytest.raises(KeyError):
+        fresh.load_state_dict({"conv_in.weight": torch.zeros(64, 4, 3, 3)})
+    assert len(engine.attn_processors) == 2 * engine.num_cross_layers
+    assert engine.config.max_num_ips == 4 and engine.dtype == bf16
+
+
+def test_ip_scale_and_bbox_actually_steer_the_output(tiny):
+    ds, oracle, engine = tiny
+    lat, ehs, pooled, time_ids, bbox, dialog = _inputs(ds.TINY, 1, 16, 24)
+    x = torch.cat([lat] * 2)
+    kw = dict(added_cond_kwargs={"text_embeds": pooled.to(DEV), "time_ids": time_ids.to(DEV)},
+              dialog_bbox=dialog.to(DEV))
+    run = lambda bb: engine.forward(x.to(DEV), 500, ehs.to(DEV, bf16),
+                                    cross_attention_kwargs={"bbox": bb.to(DEV), "aspect_ratio": 16 / 24}, **kw).sample
+    base = run(bbox)
+    moved = bbox.clone()
+    moved[1, 0] = torch.tensor([.5, .5, 1.0, 1.0])
+    assert not torch.equal(run(moved), base)
+    engine.set_ip_scale(0.0)
+    oracle.set_ip_scale(0.0)
+    try:
+        assert rel_l2(run(bbox), oracle(x, 500, ehs, pooled, time_ids, bbox, 16 / 24, dialog)) < 3e-2
+        assert not torch.equal(run(bbox), base)
+    finally:
+        engine.set_ip_scale(0.6)
+        oracle.set_ip_scale(0.6)
+
+
+def test_denoise_loop_matches_oracle_and_graph_equals_eager(tiny):
+    """pipeline_diffsensei.py:306-337 for 4 DDIM steps at guidance 7.5; reports per-step drift."""
+    ds, oracle, engine = tiny
+    from oracle.ddim import denoise_loop
+    bs, h, w = 2, 16, 24
+    lat, ehs, pooled, time_ids, bbox, dialog = _inputs(ds.TINY, bs, h, w, seed=3)
+    ref_steps = []
+    want = denoise_loop(oracle, lat, ehs, pooled, time_ids, bbox, h / w, dialog, 7.5, 4,
+                        on_step=lambda i, t, x: ref_steps.append(x.clone()))
+    pipe = ds.DiffSenseiPipeline(engine)
+    got_steps = []
+    eager = pipe.denoise(lat, ehs, pooled, time_ids, bbox, h / w, dialog, 4, 7.5, use_graph=False,
+                         on_step=lambda i, t, x: got_steps.append(x.permute(0, 3, 1, 2).float().cpu().clone()))
+    drift = [rel_l2(g, r) for g, r in zip(got_steps, ref_steps)]
+    print("per-step latent rel-L2 drift vs oracle:", ["%.2e" % d for d in drift])
+    assert drift[0] < 1.5e-2 and max(drift) < 6e-2
+    assert rel_l2(eager, want) < 6e-2
+    graphed = pipe.denoise(lat, ehs, pooled, time_ids, bbox, h / w, dialog, 4, 7.5, use_graph=True)
+    assert torch.equal(graphed, eager)            # same kernels, same order: bit-identical
+
+
+def test_pipeline_call_surface(tiny):
+    ds, _oracle, engine = tiny
+    from oracle.resampler import OracleResampler
+    torch.manual_seed(5)
+    kw = dataclasses.asdict(ds.RESAMPLER_TINY)
+    ref = OracleResampler(**kw).eval()
+    res = ds.ResamplerEngine(**kw, device=DEV)
+    res.load_state_dict(ref.state_dict())
+    pipe = ds.DiffSenseiPipeline(engine)
+    pipe.register_manga_modules(None, res)
+    g = torch.Generator().manual_seed(7)
+    pe, npe = torch.randn(1, 77, 128, generator=g), torch.randn(1, 77, 128, generator=g)
+    pp, npp = torch.randn(1, 96, generator=g), torch.randn(1, 96, generator=g)
+    clip, magi = torch.randn(1, 2, 33, 64, generator=g), torch.randn(1, 2, 32, generator=g)
+    out = pipe(prompt="a manga panel", height=128, width=192, num_inference_steps=3, guidance_scale=7.5,
+               num_samples=2, generator=torch.Generator().manual_seed(0), ip_bbox=[[.1, .1, .5, .9], [.5, .2, .9, .9]],
+               ip_scale=0.6, dialog_bbox=[[.05, .05, .3, .2]], prompt_embeds=pe, negative_prompt_embeds=npe,
+               pooled_prompt_embeds=pp, negative_pooled_prompt_embeds=npp, clip_image_embeds=clip,
+               magi_image_embeds=magi)
+    assert out.images.shape == (2, 4, 16, 24) and torch.isfinite(out.images).all()
+    with pytest.raises(ValueError, match="same length as `ip_bbox`"):
+        pipe(prompt="x", prompt_embeds=pe, negative_prompt_embeds=npe, pooled_prompt_embeds=pp,
+             negative_pooled_prompt_embeds=npp, clip_image_embeds=clip, magi_image_embeds=magi, ip_bbox=[[0, 0, 1, 1]])
+    with pytest.raises(NotImplementedError, match="text encoding"):
+        pipe(prompt="x", ip_bbox=[])
+
+
+def test_resampler_matches_executed_reference():
+    import diffsensei_b200 as ds
+    g = torch.load(os.path.join(GOLDEN, "resampler_tiny.pt"), weights_only=False)
+    res = ds.ResamplerEngine(**g["kwargs"], device=DEV)
+    res.load_state_dict(g["state_dict"])
+    out = res(g["x"], g["magi"])
+    assert out.shape == (1, 80, 128) and res.dtype() == bf16
+    assert rel_l2(out.float(), g["out"]) < 2e-2
+    assert rel_l2(res(torch.zeros_like(g["x"]), torch.zeros_like(g["magi"])).float(), g["out_zero"]) < 2e-2
+
+
+def test_smoke_entry_point():
+    import __graft_entry__
+    __graft_entry__.smoke()

@@ -1,0 +1,85 @@
+"""Host-side logic that needs no GPU: weight naming / packing, schedule, pipeline argument handling."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from diffsensei_b200.config import RESAMPLER_TINY, SDXL_MANGA, TINY
+from diffsensei_b200.scheduler import DDIMScheduler
+from diffsensei_b200.weights import (pack_conv3x3, pack_geglu, random_state_dict, resampler_param_shapes,
+                                     unet_param_shapes)
+from oracle.ddim import DDIMSchedule
+from oracle.resampler import OracleResampler
+from oracle.unet import OracleUNet
+
+
+def test_unet_key_names_and_shapes_match_oracle_module():
+    sd = OracleUNet(TINY).state_dict()
+    sh = unet_param_shapes(TINY)
+    assert set(sd) == set(sh)
+    assert all(tuple(sd[k].shape) == sh[k] for k in sh)
+    assert "dialog_bbox_embedding" in sh
+    assert "down_blocks.1.attentions.0.transformer_blocks.0.attn2.processor.to_k_ip.weight" in sh
+
+
+def test_sdxl_topology_counts():
+    sh = unet_param_shapes(SDXL_MANGA)
+    n = sum(torch.Size(s).numel() for s in sh.values())
+    assert abs(n - 2.908e9) < 5e6                                   # 2.57 B UNet + 0.34 B IP projections
+    assert sum(k.endswith("to_k_ip.weight") for k in sh) == 70      # 70 cross-attention sites
+    assert sum(".resnets." in k and k.endswith("conv1.weight") for k in sh) == 17
+
+
+def test_resampler_key_names_match_oracle_module():
+    import dataclasses
+    kw = dataclasses.asdict(RESAMPLER_TINY)
+    sd = OracleResampler(**kw).state_dict()
+    sh = resampler_param_shapes(RESAMPLER_TINY)
+    assert set(sd) == set(sh) and all(tuple(sd[k].shape) == sh[k] for k in sh)
+
+
+def test_random_state_dict_clones_ip_projections():
+    sd = random_state_dict(unet_param_shapes(TINY), 0, "cpu")
+    k = "mid_block.attentions.0.transformer_blocks.0.attn2"
+    assert torch.equal(sd[k + ".processor.to_k_ip.weight"], sd[k + ".to_k.weight"])     # unet.py:72-75
+
+
+def test_pack_geglu_is_a_row_permutation_with_the_documented_block_structure():
+    c = 64
+    w, b = (torch.randn(8 * c, c) / 8).to(torch.bfloat16).float(), torch.randn(8 * c)
+    wp, bp = pack_geglu(w, b)
+    x = torch.randn(5, c)
+    val, gate = F.linear(x, w, b).chunk(2, dim=-1)
+    want = val * F.gelu(gate)
+    y = F.linear(x, wp.float(), bp)                                  # [5, 8c] in packed order
+    y = y.reshape(5, -1, 2, 128)
+    got = (y[:, :, 0] * F.gelu(y[:, :, 1])).reshape(5, -1)
+    assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)           # pure permutation: exact up to fp32 order
+
+
+def test_pack_conv3x3_tap_major():
+    w = torch.randn(8, 64, 3, 3)
+    p = pack_conv3x3(w)
+    assert p.shape == (8, 3, 3, 64) and p.dtype == torch.bfloat16
+    assert torch.equal(p[3, 1, 2].float(), w[3, :, 1, 2].to(torch.bfloat16).float())
+
+
+def test_ddim_schedule_matches_oracle():
+    a, b = DDIMScheduler(), DDIMSchedule()
+    for n in (4, 20, 30, 50):
+        assert a.set_timesteps(n) == b.set_timesteps(n)
+        assert a.timesteps[0] == (n - 1) * (1000 // n) + 1 and a.timesteps[-1] == 1   # leading spacing, offset 1
+        for t in a.timesteps:
+            assert a.coefficients(t) == b.coefficients(t)
+    assert a.set_timesteps(50)[:3] == [981, 961, 941]
+
+
+def test_pipeline_check_inputs_raises_like_reference():
+    from diffsensei_b200.pipeline import DiffSenseiPipeline
+    pipe = DiffSenseiPipeline.__new__(DiffSenseiPipeline)
+    with pytest.raises(ValueError, match="`prompt` has to be of type `str`"):
+        pipe.check_inputs(None, None, [], None, [])
+    with pytest.raises(ValueError, match="can not be input together"):
+        pipe.check_inputs("a", None, [object()], torch.zeros(1, 16, 8), [[0, 0, 1, 1]])
+    with pytest.raises(ValueError, match="must have the same length as `ip_bbox`"):
+        pipe.check_inputs("a", None, [object(), object()], None, [[0, 0, 1, 1]])
+    pipe.check_inputs("a", None, [object()], None, [[0, 0, 1, 1]])

@@ -1,0 +1,265 @@
+"""Parity of every C-ABI kernel against the CPU oracle / a plain fp32 torch restatement of the same op,
+on the same seeded inputs (bf16-rounded where the kernel takes bf16).  Tolerances: the kernels round ONCE to
+bf16 at the output (relative 2^-8 = 3.9e-3), so per-op rel-L2 must be <= 1e-2; index / mask
+work must be bit-exact."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+bf16, f32 = torch.bfloat16, torch.float32
+DEV = "cuda"
+
+
+def _r(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(bf16)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from diffsensei_b200 import ops as o
+    return o
+
+
+# ---------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("B,H,W,C,silu,eps", [(2, 16, 24, 64, True, 1e-5), (2, 7, 9, 320, True, 1e-5),
+                                              (1, 32, 32, 1280, False, 1e-6), (3, 5, 3, 960, True, 1e-5),
+                                              (2, 64, 64, 640, True, 1e-5), (1, 1, 1, 64, True, 1e-5)])
+def test_groupnorm_silu(ops, B, H, W, C, silu, eps):
+    x = _r(B, H, W, C, seed=1) * 1.7 + 0.3
+    gamma, beta = torch.randn(C) * 0.2 + 1, torch.randn(C) * 0.1
+    want = F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, eps)
+    want = (F.silu(want) if silu else want).permute(0, 2, 3, 1)
+    got = ops.groupnorm_silu(x.to(DEV), gamma.to(DEV), beta.to(DEV), 32, eps, silu)
+    assert rel_l2(got.float(), want) < 6e-3
+    inplace = x.to(DEV).clone()
+    ops.groupnorm_silu(inplace, gamma.to(DEV), beta.to(DEV), 32, eps, silu, out=inplace)
+    assert torch.equal(inplace, got)
+
+
+@pytest.mark.parametrize("rows,C", [(77, 128), (300, 640), (64, 1280), (5, 2048), (33, 256)])
+def test_layernorm(ops, rows, C):
+    x = _r(rows, C, seed=2) * 2 + 0.5
+    gamma, beta = torch.randn(C) * 0.2 + 1, torch.randn(C) * 0.1
+    want = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    got = ops.layernorm(x.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-5)
+    assert rel_l2(got.float(), want) < 6e-3
+
+
+# ---------------------------------------------------------------------------------------------- bbox kernels
+def test_dialog_embed_matches_executed_reference(ops):
+    for case in torch.load(os.path.join(GOLDEN, "dialog_embed.pt"), weights_only=False):
+        is_bf16 = case["sample"].dtype == bf16
+        sample = case["sample"].to(bf16).permute(0, 2, 3, 1).contiguous().to(DEV)
+        got = ops.dialog_embed_add_(sample, case["emb"].float().to(DEV), case["dialog_bbox"].float().to(DEV), is_bf16)
+        want = case["out"].float().permute(0, 2, 3, 1)
+        if is_bf16:      # identical dtype path: bit-exact, including int(bf16(0.9)*152) = 137
+            assert torch.equal(got.float().cpu(), want)
+        else:            # fp32 reference vs bf16 storage: the SET of touched pixels must be identical
+            base = case["sample"].float().permute(0, 2, 3, 1)
+            assert torch.equal((got.float().cpu() - base.to(bf16).float()).abs().sum(-1) > 0,
+                               (want - base).abs().sum(-1) > 0)
+
+
+def test_ip_mask_bit_exact_vs_reference_kats_and_all_buckets(ops):
+    from oracle import attention as A
+    for kat in torch.load(os.path.join(GOLDEN, "ip_mask_kats.pt"), weights_only=False):
+        got = ops.ip_mask(kat["bbox"].to(DEV), kat["N"], kat["aspect_ratio"], 16, 16)
+        assert torch.equal(got.cpu() == 0, kat["open"])
+        assert set(got.unique().tolist()) <= {0.0, -10000.0}
+    bb = torch.tensor([[[.05, .10, .50, .95], [.50, .15, .95, .90], [.30, .55, .70, 1.0], [0.0, 0.0, .30, .40]],
+                       [[0.0] * 4] * 4, [[1 / 3, 0.25, 2 / 3, 0.75], [0.5, 0.5, 0.5, 0.5], [0, 0, 1, 1], [.2, 0, .2, 1]]])
+    tab = torch.load(os.path.join(GOLDEN, "derived_hw_table.pt"), weights_only=False)
+    for bh, bw, _d, fh, fw, _dh, _dw in tab.tolist():      # every (bucket, level) shape incl. the 5 quirk cases
+        n, ar = fh * fw, (bh // 8) / (bw // 8)
+        got = ops.ip_mask(bb.to(DEV), n, ar, 16, 16)
+        assert torch.equal(got.cpu() == 0, A.ip_open_mask(bb, n, ar, 16, 16)), (bh, bw, n)
+
+
+# ---------------------------------------------------------------------------------------------- GEMM / conv
+@pytest.mark.parametrize("M,N,K", [(77, 256, 128), (300, 200, 72), (1024, 640, 320), (16, 1280, 2816), (4096, 320, 64)])
+def test_gemm_bias_residual(ops, M, N, K):
+    a, w = _r(M, K, seed=3), _r(N, K, seed=4, scale=K ** -0.5)
+    bias, res = torch.randn(N) * 0.3, _r(M, N, seed=5)
+    want = F.linear(a.float(), w.float(), bias) + res.float()
+    got = ops.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), residual=res.to(DEV))
+    assert rel_l2(got.float(), want) < 5e-3
+    got32 = ops.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), residual=res.to(DEV), out_fp32=True)
+    assert rel_l2(got32, want) < 1e-5
+
+
+def test_gemm_geglu_matches_diffusers_feedforward(ops):
+    from diffsensei_b200.weights import pack_geglu
+    c, M = 128, 333
+    x = _r(M, c, seed=6)
+    w, b = _r(8 * c, c, seed=7, scale=c ** -0.5), torch.randn(8 * c) * 0.2
+    val, gate = F.linear(x.float(), w.float(), b).chunk(2, dim=-1)
+    want = val * F.gelu(gate)
+    wp, bp = pack_geglu(w.float(), b)
+    got = ops.gemm(x.to(DEV), wp.to(DEV), bp.to(DEV), epilogue=ops.EPI_GEGLU)
+    assert got.shape == (M, 4 * c) and rel_l2(got.float(), want) < 6e-3
+
+
+def test_gemm_activations_and_rowbias(ops):
+    a, w = _r(512, 192, seed=8), _r(256, 192, seed=9, scale=192 ** -0.5)
+    rb = torch.randn(4, 1000)[:, 100:356]
+    base = F.linear(a.float(), w.float()) + rb.repeat_interleave(128, 0)
+    rbd = torch.randn(4, 1000)
+    rbd[:, 100:356] = rb
+    got = ops.gemm(a.to(DEV), w.to(DEV), rowbias=rbd.to(DEV)[:, 100:356], rows_per_batch=128)   # strided table slice
+    assert rel_l2(got.float(), base) < 5e-3
+    assert rel_l2(ops.gemm(a.to(DEV), w.to(DEV), epilogue=ops.EPI_SILU).float(), F.silu(F.linear(a.float(), w.float()))) < 6e-3
+    assert rel_l2(ops.gemm(a.to(DEV), w.to(DEV), epilogue=ops.EPI_GELU).float(), F.gelu(F.linear(a.float(), w.float()))) < 6e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 16, 24, 64, 128, 1), (2, 19, 13, 128, 64, 1),
+                                                   (1, 16, 32, 64, 128, 2), (2, 19, 13, 64, 64, 2),
+                                                   (1, 8, 8, 320, 4, 1), (2, 32, 32, 192, 320, 1)])
+def test_conv3x3(ops, B, H, W, Cin, Cout, stride):
+    from diffsensei_b200.weights import pack_conv3x3
+    x = _r(B, H, W, Cin, seed=10)
+    w = _r(Cout, Cin, 3, 3, seed=11, scale=(9 * Cin) ** -0.5)
+    bias, temb = torch.randn(Cout) * 0.2, torch.randn(B, Cout) * 0.5
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, stride=stride, padding=1) + temb[:, :, None, None]
+    res = _r(*want.permute(0, 2, 3, 1).shape, seed=12)
+    want = want.permute(0, 2, 3, 1) + res.float()
+    got = ops.conv3x3(x.to(DEV), pack_conv3x3(w.float()).to(DEV), bias.to(DEV), stride=stride, rowbias=temb.to(DEV),
+                      residual=res.to(DEV))
+    assert got.shape == want.shape and rel_l2(got.float(), want) < 5e-3
+
+
+def test_conv_in(ops):
+    x = _r(2, 17, 23, 4, seed=13)
+    w, b = torch.randn(64, 4, 3, 3) * 0.2, torch.randn(64) * 0.1
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1)
+    got = ops.conv_in(x.to(DEV), w.permute(0, 2, 3, 1).contiguous().to(DEV), b.to(DEV))
+    assert rel_l2(got.float(), want) < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def test_attention_self_vs_executed_reference(ops):
+    g = torch.load(os.path.join(GOLDEN, "attn_self.pt"), weights_only=False)
+    hs = g["hs"].to(bf16)
+    wqkv = torch.cat([g["to_q"], g["to_k"], g["to_v"]], 0).to(bf16)
+    qkv = ops.gemm(hs.to(DEV), wqkv.to(DEV))
+    a = ops.attention_self(qkv, g["heads"])
+    out = ops.gemm(a, g["to_out_w"].to(bf16).to(DEV), g["to_out_b"].to(DEV))
+    assert rel_l2(out.float(), g["out"]) < 1.5e-2        # three chained bf16 roundings vs the fp32 reference
+
+
+def test_attention_cross_ip_vs_executed_reference(ops):
+    g = torch.load(os.path.join(GOLDEN, "attn_cross_ip.pt"), weights_only=False)
+    hs, ehs = g["hs"].to(bf16).to(DEV), g["ehs"].to(bf16).to(DEV)
+    end = ehs.shape[1] - (g["num_ip_tokens"] + g["num_dummy"])
+    q = ops.gemm(hs, g["to_q"].to(bf16).to(DEV))
+    kv_t = ops.gemm(ehs[:, :end].contiguous(), torch.cat([g["to_k"], g["to_v"]], 0).to(bf16).to(DEV))
+    kv_i = ops.gemm(ehs[:, end:].contiguous(), torch.cat([g["to_k_ip"], g["to_v_ip"]], 0).to(bf16).to(DEV))
+    a = ops.attention_cross_ip(q, kv_t, kv_i, g["bbox"].to(DEV), g["heads"], g["aspect_ratio"], g["scale"], 16, 16)
+    out = ops.gemm(a, g["to_out_w"].to(bf16).to(DEV), g["to_out_b"].to(DEV))
+    assert rel_l2(out.float(), g["out"]) < 1.5e-2
+
+
+def test_engine_processors_follow_the_diffusers_protocol(ops):
+    """The nn.Module processors called exactly like diffusers' Attention.forward calls them."""
+    import types
+    from diffsensei_b200 import AttnProcessor2_0, MaskedIPAttnProcessor2_0
+    g = torch.load(os.path.join(GOLDEN, "attn_cross_ip.pt"), weights_only=False)
+
+    def lin(w, b=None):
+        m = torch.nn.Linear(w.shape[1], w.shape[0], bias=b is not None)
+        m.weight.data, m.bias = w.clone(), (None if b is None else torch.nn.Parameter(b.clone()))
+        return m.to(DEV, bf16)
+
+    attn = types.SimpleNamespace(heads=g["heads"], spatial_norm=None, group_norm=None, norm_cross=False,
+                                 residual_connection=False, rescale_output_factor=1.0, to_q=lin(g["to_q"]),
+                                 to_k=lin(g["to_k"]), to_v=lin(g["to_v"]),
+                                 to_out=[lin(g["to_out_w"], g["to_out_b"]), torch.nn.Identity()])
+    proc = MaskedIPAttnProcessor2_0(hidden_size=128, cross_attention_dim=64, num_ip_tokens=64, num_dummy_tokens=16)
+    proc.load_state_dict({"to_k_ip.weight": g["to_k_ip"], "to_v_ip.weight": g["to_v_ip"]})
+    proc = proc.to(DEV, bf16)
+    proc.scale = g["scale"]
+    out = proc(attn, g["hs"].to(DEV, bf16), encoder_hidden_states=g["ehs"].to(DEV, bf16), bbox=g["bbox"].to(DEV),
+               aspect_ratio=g["aspect_ratio"], dialog_bbox=None)
+    assert rel_l2(out.float(), g["out"]) < 1.5e-2
+    s = torch.load(os.path.join(GOLDEN, "attn_self.pt"), weights_only=False)
+    attn1 = types.SimpleNamespace(heads=s["heads"], spatial_norm=None, group_norm=None, norm_cross=False,
+                                  residual_connection=False, rescale_output_factor=1.0, to_q=lin(s["to_q"]),
+                                  to_k=lin(s["to_k"]), to_v=lin(s["to_v"]),
+                                  to_out=[lin(s["to_out_w"], s["to_out_b"]), torch.nn.Identity()])
+    out = AttnProcessor2_0()(attn1, s["hs"].to(DEV, bf16), bbox=g["bbox"].to(DEV), aspect_ratio=1.0, dialog_bbox=None)
+    assert rel_l2(out.float(), s["out"]) < 1.5e-2
+    assert sorted(proc.state_dict()) == ["to_k_ip.weight", "to_v_ip.weight"] and hasattr(proc, "scale")
+
+
+@pytest.mark.parametrize("B,N,heads", [(1, 128, 1), (2, 200, 2), (1, 1000, 3), (2, 64, 1)])
+def test_attention_self_vs_oracle_sdpa(ops, B, N, heads):
+    from oracle.attention import sdpa
+    C = heads * 64
+    qkv = _r(B, N, 3 * C, seed=14, scale=1.5)
+    q, k, v = (t.float().view(B, N, heads, 64).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
+    want = sdpa(q, k, v).transpose(1, 2).reshape(B, N, C)
+    assert rel_l2(ops.attention_self(qkv.to(DEV), heads).float(), want) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------- glue
+def test_layout_upsample_concat_silu_timestep(ops):
+    x = torch.randn(2, 4, 9, 13)
+    nhwc = ops.nchw_to_nhwc(x.to(DEV))
+    assert torch.equal(nhwc.cpu(), x.to(bf16).permute(0, 2, 3, 1))
+    assert torch.equal(ops.nhwc_to_nchw(nhwc, f32).cpu(), x.to(bf16).float())
+    y = _r(2, 5, 7, 64, seed=15)
+    for (ho, wo) in ((10, 14), (9, 13), (11, 15)):
+        want = F.interpolate(y.float().permute(0, 3, 1, 2), size=(ho, wo), mode="nearest").permute(0, 2, 3, 1)
+        assert torch.equal(ops.upsample_nearest(y.to(DEV), ho, wo).float().cpu(), want)
+    a, b = _r(3, 5, 64, seed=16), _r(3, 5, 192, seed=17)
+    assert torch.equal(ops.concat_channels(a.to(DEV), b.to(DEV)).cpu(), torch.cat([a, b], -1))
+    assert rel_l2(ops.silu(y.to(DEV)).float(), F.silu(y.float())) < 4e-3
+    from oracle.unet import timestep_sinusoid
+    t = torch.tensor([981.0, 1.0, 500.0, 1024.0])
+    for dim in (320, 256, 64):
+        assert (ops.timestep_embedding(t.to(DEV), dim).float().cpu() - timestep_sinusoid(t, dim)).abs().max() < 8e-3
+
+
+def test_cfg_ddim_step(ops):
+    from oracle.ddim import DDIMSchedule
+    sch = DDIMSchedule()
+    t = sch.set_timesteps(50)[7]
+    a_t, a_prev = sch.coefficients(t)
+    bs, H, W = 2, 6, 5
+    eps, lat = _r(2 * bs, H, W, 4, seed=18), torch.randn(bs, H, W, 4)
+    eu, et = eps.float().chunk(2)
+    want = sch.step(eu + 7.5 * (et - eu), t, lat)
+    latd, mi = lat.to(DEV).clone(), torch.empty(2 * bs, H, W, 4, dtype=bf16, device=DEV)
+    ops.cfg_ddim_step_(eps.to(DEV), latd, mi, torch.tensor([a_t, a_prev], device=DEV), 7.5)
+    assert rel_l2(latd, want) < 1e-5
+    assert torch.equal(mi[:bs], mi[bs:]) and torch.equal(mi[:bs].cpu(), latd.cpu().to(bf16))
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties
+def test_full_size_properties_cfg2(ops):
+    """BASELINE cfg2 shapes, checked through size-independent properties (the oracle is too slow here)."""
+    torch.manual_seed(0)
+    # GroupNorm without affine/SiLU: every (sample, group) of the output has mean 0, variance 1
+    x = (torch.randn(8, 128, 128, 320, device=DEV) * 2 + 1).to(bf16)
+    y = ops.groupnorm_silu(x, torch.ones(320, device=DEV), torch.zeros(320, device=DEV), 32, 1e-5, False)
+    g = y.float().view(8, 128 * 128, 32, 10)
+    assert g.mean(dim=(1, 3)).abs().max() < 2e-3 and (g.var(dim=(1, 3), unbiased=False) - 1).abs().max() < 5e-3
+    del x, y, g
+    # softmax rows sum to one: with V == const the attention output is that constant
+    B, N, heads = 8, 4096, 10
+    qkv = torch.randn(B, N, 3 * heads * 64, device=DEV).to(bf16)
+    qkv[:, :, 2 * heads * 64:] = 0.75
+    out = ops.attention_self(qkv, heads)
+    assert (out.float() - 0.75).abs().max() < 1e-2
+    # linearity of the conv in its input:  conv(2x) - bias == 2 (conv(x) - bias)
+    from diffsensei_b200.weights import pack_conv3x3
+    xc = torch.randn(8, 64, 64, 640, device=DEV).to(bf16)
+    w = pack_conv3x3(torch.randn(640, 640, 3, 3, device=DEV) * (9 * 640) ** -0.5)
+    y1, y2 = ops.conv3x3(xc, w, out_fp32=True), ops.conv3x3(xc * 2, w, out_fp32=True)
+    assert rel_l2(y2, 2 * y1) < 1e-6
