@@ -187,65 +187,142 @@ def kernel_rooflines(ds, peaks, device):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_sample(steps, warmup, log=lambda *a: None):
+def unet_flops(cfg, B, h, w, hoist_kv=False):
+    """Analytic 2*MAC count of one UNetMangaModel.forward (conv 2*9*Cin*Cout*H*W*B, linear 2*in*out*tokens,
+    SDPA 4*N*Nk*C*B), the formula behind SURVEY.md §8d's 54.8 TFLOP for cfg2."""
+    from diffsensei_b200.weights import resnet_io, transformer_sites
+    ch = cfg.block_out_channels
+    n = len(ch)
+    res = [(h, w)]
+    for _ in range(n - 1):
+        res.append(((res[-1][0] - 1) // 2 + 1, (res[-1][1] - 1) // 2 + 1))
+    level_of = {}
+    for i, c in enumerate(ch):
+        for j in range(cfg.layers_per_block):
+            level_of[f"down_blocks.{i}.resnets.{j}"] = i
+            level_of[f"down_blocks.{i}.attentions.{j}"] = i
+    for k in ("mid_block.resnets.0", "mid_block.resnets.1", "mid_block.attentions.0"):
+        level_of[k] = n - 1
+    for i in range(n):
+        for j in range(cfg.layers_per_block + 1):
+            level_of[f"up_blocks.{i}.resnets.{j}"] = n - 1 - i
+            level_of[f"up_blocks.{i}.attentions.{j}"] = n - 1 - i
+    f = 2.0 * 9 * cfg.in_channels * ch[0] * h * w * B                         # conv_in
+    for p, cin, cout in resnet_io(cfg):
+        hh, ww = res[level_of[p]]
+        px = hh * ww * B
+        f += 2.0 * 9 * cin * cout * px + 2.0 * 9 * cout * cout * px + 2.0 * cfg.time_embed_dim * cout * B
+        if cin != cout:
+            f += 2.0 * cin * cout * px
+    n_text, n_ip = 77, cfg.num_ip_tokens + cfg.num_dummy_tokens
+    for p, c, depth in transformer_sites(cfg):
+        hh, ww = res[level_of[p]]
+        N = hh * ww
+        tok = N * B
+        f += 2 * 2.0 * c * c * tok                                            # proj_in / proj_out
+        per = 4 * 2.0 * c * c * tok + 4.0 * N * N * c * B                     # attn1 q,k,v,out + SDPA
+        per += 2 * 2.0 * c * c * tok + 4.0 * N * (n_text + n_ip) * c * B      # attn2 q,out + both SDPAs
+        if not hoist_kv:
+            per += 2 * 2.0 * cfg.cross_attention_dim * c * (n_text + n_ip) * B
+        per += 2.0 * c * 8 * c * tok + 2.0 * 4 * c * c * tok                  # GEGLU FF
+        f += depth * per
+    for i in range(n - 1):
+        hh, ww = res[i + 1]
+        f += 2.0 * 9 * ch[i] * ch[i] * hh * ww * B                            # downsample conv (stride 2)
+    rev = list(reversed(ch))
+    for i in range(n - 1):
+        hh, ww = res[n - 2 - i]
+        f += 2.0 * 9 * rev[i] * rev[i] * hh * ww * B                          # upsample conv at the doubled size
+    f += 2.0 * 9 * ch[0] * cfg.out_channels * h * w * B                       # conv_out
+    td = cfg.time_embed_dim
+    f += 2.0 * B * (ch[0] * td + td * td + cfg.projection_class_embeddings_input_dim * td + td * td)
+    return f
+
+
+def cpu_reference_sample(steps, warmup, budget_s=150.0, log=lambda *a: None):
     """The reference's CPU path: its processors' arithmetic + the diffusers SDXL blocks as restated by the oracle
     (real diffusers / the reference tree do not exist on the GPU box), fp32, all host threads.
-    Bounded sample of the cfg2 step: B_s of the 8 independent CFG-batch rows at latent 128x128 -> value scaled by
-    B_s/8 (every op on the path is per-sample)."""
+    BOUNDED sample: one CFG row (UNet batch 1) of a square panel whose latent side is chosen so that
+    (steps + warmup) samples fit the time budget; steps/sec of the cfg2 workload = 1 / (t_sample * F_cfg2 /
+    F_sample) with F the analytic FLOP count (`unet_flops`).  Every op on the path is per-sample, so
+    batch rows scale exactly; the resolution scaling is the analytic one and is stated in `sample`."""
     import diffsensei_b200 as ds
     from oracle.ddim import DDIMSchedule
     from oracle.unet import OracleUNet
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     tiny = os.environ.get("DS_BENCH_TINY") == "1"          # plumbing self-test only; never a bench number
     cfg = ds.TINY if tiny else ds.SDXL_MANGA
     t0 = time.time()
-    prev = torch.get_default_dtype()
     with torch.device("meta"):
         model = OracleUNet(cfg)
     model = model.to_empty(device="cpu")
     with torch.no_grad():
-        for name, p in model.named_parameters():      # cheap deterministic fill: timing does not depend on values
+        for name, p in model.named_parameters():          # cheap fill: CPU time does not depend on the values
             if p.dim() == 1 and name.endswith("weight"):
                 p.fill_(1.0)
             elif name.endswith("bias"):
                 p.zero_()
             else:
                 fan_in = p[0].numel() if p.dim() > 1 else p.numel()
-                p.copy_(((torch.arange(p.numel(), dtype=torch.float32) % 257 - 128) / 128.0).view_as(p) * fan_in ** -0.5)
+                p.uniform_(-1.0, 1.0).mul_(fan_in ** -0.5)
     model.eval()
     model.set_ip_scale(IP_SCALE)
-    log(f"[reference] oracle SDXL UNet built in {time.time() - t0:.1f}s on {cores} host threads")
-    torch.set_default_dtype(prev)
-    bs_s = 1                                            # -> UNet batch B_s = 2 (one CFG pair)
-    hw = 16 if tiny else 128
-    lat, ehs, pooled, time_ids, bbox, dialog = synthetic_inputs(cfg, bs_s, hw, hw, 2, "cpu")
+    log(f"[reference] oracle UNet ({sum(p.numel() for p in model.parameters()) / 1e9:.2f} B params) built in "
+        f"{time.time() - t0:.1f}s; {cores} host threads")
     sch = DDIMSchedule()
     ts = sch.set_timesteps(T_STEPS)
 
-    def one_step(i):
-        nonlocal lat
-        eps = model(torch.cat([lat] * 2), ts[i % T_STEPS], ehs, pooled, time_ids, bbox, 1.0, dialog)
-        eu, et = eps.chunk(2)
-        lat = sch.step(eu + GUIDANCE * (et - eu), ts[i % T_STEPS], lat)
+    def make(side):
+        lat, ehs, pooled, time_ids, bbox, dialog = synthetic_inputs(cfg, 1, side, side, 2, "cpu")
+        # one CFG row: the positive branch (second half of the CFG-concatenated conditions)
+        return [lat, ehs[1:], pooled[1:], time_ids[1:], bbox[1:], None]
 
+    def run(state, i):
+        lat, ehs, pooled, time_ids, bbox, dialog = state
+        eps = model(lat, ts[i % T_STEPS], ehs, pooled, time_ids, bbox, 1.0, dialog)
+        state[0] = sch.step(eps, ts[i % T_STEPS], lat)      # scheduler step on the single row (CFG blend needs both)
+
+    # calibrate on a 16x16 latent, then pick the largest side whose (steps + warmup) samples fit the budget
+    probe = make(16)
+    run(probe, 0)
+    t0 = time.time()
+    run(probe, 1)
+    t_probe = time.time() - t0
+    f_probe = unet_flops(cfg, 1, 16, 16)
+    side = 16
+    for cand in (128, 96, 64, 48, 32, 24):
+        est = t_probe * unet_flops(cfg, 1, cand, cand) / f_probe * 0.6     # larger shapes run at higher GFLOP/s
+        if est * (steps + warmup) <= budget_s:
+            side = cand
+            break
+    if tiny:
+        side = 16
+    state = make(side)
     for i in range(warmup):
-        one_step(i)
+        run(state, i)
     t0 = time.time()
     for i in range(steps):
-        one_step(warmup + i)
+        run(state, warmup + i)
     dt = (time.time() - t0) / max(steps, 1)
-    frac = 2 * bs_s / 8.0
-    return {"sec_per_sample": dt, "steps_per_sec": frac / dt, "cores": cores,
-            "sample": f"UNet batch {2 * bs_s} of the 8 CFG-batch rows of one cfg2 step (latent 128x128, fp32), "
-                      f"scaled x{frac:g}"}
+    f_sample = unet_flops(cfg, 1, side, side)
+    f_full = unet_flops(ds.SDXL_MANGA, 8, 128, 128)
+    scale = f_full / f_sample if not tiny else 1.0
+    return {"sec_per_sample": dt, "steps_per_sec": 1.0 / (dt * scale), "cores": cores,
+            "gflops_per_sec": f_sample / dt / 1e9,
+            "sample": f"UNet batch 1 (one CFG row), latent {side}x{side} ({side * 8}x{side * 8} panel), fp32, "
+                      f"{f_sample / 1e12:.3f} TFLOP/sample; scaled to the cfg2 step by the analytic FLOP ratio "
+                      f"{scale:.1f} (cfg2 = {f_full / 1e12:.1f} TFLOP)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    r = cpu_reference_sample(args.steps, args.warmup, log=lambda *a: print(*a, file=sys.stderr))
+    r = cpu_reference_sample(args.steps, args.warmup, budget_s=150.0, log=lambda *a: print(*a, file=sys.stderr))
     line = {"impl": "reference", "metric": METRIC, "value": round(r["steps_per_sec"], 6), "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 / r["steps_per_sec"], 1), "higher_is_better": True, "scaling": "weak",
@@ -253,7 +330,7 @@ def run_reference(args):
             "config": {"workload": "cfg2: 1024x1024 panels, bs=4 (UNet batch 8), 2 character refs, 50 DDIM steps",
                        "note": "reference CPU path = oracle restatement (diffusers absent); bounded sample"},
             "cpu_baseline": {"value": round(r["steps_per_sec"], 6), "unit": UNIT, "cores": r["cores"], "kind": "port",
-                             "sample": r["sample"]},
+                             "sample": r["sample"], "host_gflops": round(r["gflops_per_sec"], 1)},
             "e2e": {"value": round(r["steps_per_sec"], 6), "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -339,9 +416,9 @@ def run_ours(args):
         extra = kernel_rooflines(ds, peaks, dev)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_sample(1, 0, log=lambda *a: print(*a, file=sys.stderr))
+        r = cpu_reference_sample(1, 1, budget_s=45.0, log=lambda *a: print(*a, file=sys.stderr))
         cpu = {"value": round(r["steps_per_sec"], 6), "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": r["sample"] + "; 1 timed sample, no warm-up"}
+               "sample": r["sample"] + "; 1 warm-up + 1 timed sample", "host_gflops": round(r["gflops_per_sec"], 1)}
     if rank == 0:
         tflop = STEP_TFLOP_CFG2 if args.config == "cfg2" else None
         line = {"metric": METRIC, "value": round(steps_per_sec, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -18,7 +18,8 @@
 // (2) cross_ip_attn_kernel — out = softmax(Q Kt^T/8) Vt + scale * softmax(Q Kip^T/8 + M(bbox)) Vip
 //     (MaskedIPAttnProcessor2_0, src/models/attention_processor.py:231-258) in ONE pass: text and IP keys are
 //     concatenated along the key axis in shared memory (<= 192 keys), one S = Q [Kt;Kip]^T MMA chain, two
-//     independent softmaxes per row with the normalisers and `scale` folded into P, one O = P [Vt;Vip] chain.
+//     independent softmaxes per row (unnormalised P in smem, two passes over S), two PV chains into separate
+//     TMEM accumulators (O_ip re-uses the dead S columns), and 1/l_text, scale/l_ip applied in the epilogue.
 //     The additive bbox mask M in {0,-10000} (:115-169) is evaluated in registers from the 4 boxes with the
 //     reference's closed-interval / derived-(H',W') semantics (ip_mask.cuh) and never touches memory.
 #include "ds_common.cuh"
@@ -36,6 +37,13 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 domain
 
 // swizzled (SWIZZLE_128B) byte offset of 16-byte chunk `q16` (0..7) of row `r` inside a [rows][64 bf16] atom
 __device__ __forceinline__ uint32_t sw128_off(int r, int q16) { return r * 128 + ((q16 ^ (r & 7)) << 4); }
+
+// 2^x on the MUFU pipe (ex2.approx.ftz): inputs here are <= ~8, results feed a bf16 rounding
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ void st_shared_16(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d)
@@ -189,16 +197,25 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int kv_valid = p.Nkv - j * kTile;  // >= 128: whole tile valid
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // ---- pass 1: row max
+      // ---- pass 1: row max (two TMEM loads in flight per wait)
+      const bool full_tile = kv_valid >= kTile;  // warp-uniform
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tS + lane_base + c * 32, raw);
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tS + lane_base + c * 32, r0);
+        tmem_ld32(tS + lane_base + c * 32 + 32, r1);
         tmem_ld_wait();
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r0[i]));
+            if (c * 32 + 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r1[i]));
+          }
+        }
       }
       const float m_tile = mx * p.scale_log2;
       float alpha = 1.0f;
@@ -206,7 +223,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       if (j == 0) {
         m_ref = m_tile;
       } else if (m_tile > m_ref + kRescaleThreshold) {
-        alpha = exp2f(m_ref - m_tile);
+        alpha = ex2(m_ref - m_tile);
         m_ref = m_tile;
         l *= alpha;
         need = true;
@@ -225,26 +242,37 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       }
       // ---- pass 2: P = exp2(S*scale - m_ref) -> bf16 -> swizzled smem; row sum
       float lsum = 0.f;
+      const float neg_m = -m_ref;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t raw[32];
         tmem_ld32(tS + lane_base + c * 32, raw);
         tmem_ld_wait();
-        float pv[32];
+        uint32_t pk[16];
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = exp2f(fmaf(__uint_as_float(raw[i]), p.scale_log2, -m_ref));
-          pv[i] = (c * 32 + i < kv_valid) ? e : 0.f;
-          lsum += pv[i];
+          for (int i = 0; i < 16; ++i) {
+            const float e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m));
+            const float e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m));
+            lsum += e0 + e1;
+            pk[i] = pack_bf16(e0, e1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m));
+            float e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m));
+            if (c * 32 + 2 * i >= kv_valid) e0 = 0.f;
+            if (c * 32 + 2 * i + 1 >= kv_valid) e1 = 0.f;
+            lsum += e0 + e1;
+            pk[i] = pack_bf16(e0, e1);
+          }
         }
         uint8_t* atom = sP + (c >> 1) * kTileBytes;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int q16 = (c & 1) * 4 + q;
-          st_shared_16(atom + sw128_off(row, q16), pack_bf16(pv[q * 8 + 0], pv[q * 8 + 1]),
-                       pack_bf16(pv[q * 8 + 2], pv[q * 8 + 3]), pack_bf16(pv[q * 8 + 4], pv[q * 8 + 5]),
-                       pack_bf16(pv[q * 8 + 6], pv[q * 8 + 7]));
-        }
+        for (int q = 0; q < 4; ++q)
+          st_shared_16(atom + sw128_off(row, (c & 1) * 4 + q), pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2],
+                       pk[q * 4 + 3]);
       }
       l += lsum;
       fence_proxy_async_smem();  // st.shared -> visible to the tensor core's async-proxy reads
@@ -371,10 +399,15 @@ cross_ip_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       umma_commit(s_full);
       mbar_wait(p_full, 0);
       tc_fence_after();
+      // two accumulators: O_text (columns 192..255) and O_ip (columns 0..63: S is dead once P is in smem)
+      const int kt = p.nt_pad / 16;
       for (int k = 0; k < n_keys / 16; ++k) {
         const uint64_t adesc = make_sw128_desc(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 1024, 16);
         const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048, 1024, 1024);
-        umma_ss(tO, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
+        if (k < kt)
+          umma_ss(tO, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
+        else
+          umma_ss(tS, adesc, bdesc, idesc_pv, k != kt ? 1u : 0u);
       }
       umma_commit(o_full);
     }
@@ -385,89 +418,118 @@ cross_ip_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
     const uint32_t bits =
         ip_inside_bits(p.bbox + static_cast<size_t>(batch) * p.num_ips * 4, p.num_ips, min(q_row, p.N - 1), p.Hd, p.Wd);
-    constexpr float kScale = 0.125f;  // 1/sqrt(64)
+    // log2-domain scores: t = s * (1/8) * log2(e) + M * log2(e),  M in {0, -10000} (reference :142,162-163)
+    constexpr float kS2 = 0.125f * kLog2e;
+    constexpr float kMask2 = -10000.0f * kLog2e;
+    const int chunks = n_keys / 16;
+    const int t_chunks = p.nt_pad / 16;
+    // chunk-uniform masks when the 16-column chunks line up with the per-character key blocks (SDXL: 16/16)
+    const bool uniform = (p.tokens_per_ip % 16 == 0) && (p.num_dummy % 16 == 0);
 
-    // score of key column `col` (text part first), or -inf for padding; IP keys get the additive -10000 mask
-    auto score = [&](float s_raw, int col) -> float {
-      if (col < p.nt_pad) return col < p.n_text ? s_raw * kScale : -INFINITY;
-      const int k = col - p.nt_pad;
-      if (k >= p.n_ip) return -INFINITY;
-      return s_raw * kScale + (ip_key_open(bits, k, p.tokens_per_ip, p.num_dummy) ? 0.0f : -10000.0f);
+    // additive term of column i of chunk c, and number of valid (non-padding) columns in the chunk
+    auto chunk_valid = [&](int c) -> int {
+      const int v = (c < t_chunks) ? p.n_text - c * 16 : p.n_ip - (c - t_chunks) * 16;
+      return v < 0 ? 0 : (v > 16 ? 16 : v);
+    };
+    auto chunk_add = [&](int c) -> float {  // only meaningful when `uniform`
+      if (c < t_chunks) return 0.0f;
+      return ip_key_open(bits, (c - t_chunks) * 16, p.tokens_per_ip, p.num_dummy) ? 0.0f : kMask2;
+    };
+    auto elem_add = [&](int c, int i) -> float {  // general path
+      if (c < t_chunks) return 0.0f;
+      return ip_key_open(bits, (c - t_chunks) * 16 + i, p.tokens_per_ip, p.num_dummy) ? 0.0f : kMask2;
     };
 
     mbar_wait(s_full, 0);
     tc_fence_after();
-    const int chunks = n_keys / 16;
-    const int t_chunks = p.nt_pad / 16;
-    // pass 1: maxima
+    // ---- pass 1: the two row maxima
     float m_t = -INFINITY, m_i = -INFINITY;
     for (int c = 0; c < chunks; ++c) {
       uint32_t raw[16];
       tmem_ld16(tS + lane_base + c * 16, raw);
       tmem_ld_wait();
+      const int nv = chunk_valid(c);
       float mx = -INFINITY;
+      if (uniform && nv == 16) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) mx = fmaxf(mx, score(__uint_as_float(raw[i]), c * 16 + i));
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        mx = fmaf(mx, kS2, chunk_add(c));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < nv) mx = fmaxf(mx, fmaf(__uint_as_float(raw[i]), kS2, uniform ? chunk_add(c) : elem_add(c, i)));
+      }
       if (c < t_chunks)
         m_t = fmaxf(m_t, mx);
       else
         m_i = fmaxf(m_i, mx);
     }
-    // pass 2: normalisers
+    // ---- pass 2: unnormalised P = 2^(t - m) -> bf16 -> swizzled smem; row sums
     float l_t = 0.f, l_i = 0.f;
     for (int c = 0; c < chunks; ++c) {
       uint32_t raw[16];
       tmem_ld16(tS + lane_base + c * 16, raw);
       tmem_ld_wait();
+      const int nv = chunk_valid(c);
       const float m = c < t_chunks ? m_t : m_i;
-      float s = 0.f;
+      uint32_t pk[8];
+      float sum = 0.f;
+      if (uniform && nv == 16) {
+        const float off = chunk_add(c) - m;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) s += exp2f((score(__uint_as_float(raw[i]), c * 16 + i) - m) * kLog2e);
-      if (c < t_chunks)
-        l_t += s;
-      else
-        l_i += s;
-    }
-    const float w_t = 1.0f / l_t, w_i = p.ip_scale / l_i;
-    // pass 3: P = [softmax_text | scale * softmax_ip] -> bf16 -> swizzled smem
-    for (int c = 0; c < chunks; ++c) {
-      uint32_t raw[16];
-      tmem_ld16(tS + lane_base + c * 16, raw);
-      tmem_ld_wait();
-      const float m = c < t_chunks ? m_t : m_i;
-      const float w = c < t_chunks ? w_t : w_i;
-      float pv[16];
+        for (int i = 0; i < 8; ++i) {
+          const float e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), kS2, off));
+          const float e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), kS2, off));
+          sum += e0 + e1;
+          pk[i] = pack_bf16(e0, e1);
+        }
+      } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) pv[i] = exp2f((score(__uint_as_float(raw[i]), c * 16 + i) - m) * kLog2e) * w;
-      uint8_t* atom = sP + (c >> 2) * kTileBytes;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int q16 = (c & 3) * 2 + q;
-        st_shared_16(atom + sw128_off(row, q16), pack_bf16(pv[q * 8 + 0], pv[q * 8 + 1]),
-                     pack_bf16(pv[q * 8 + 2], pv[q * 8 + 3]), pack_bf16(pv[q * 8 + 4], pv[q * 8 + 5]),
-                     pack_bf16(pv[q * 8 + 6], pv[q * 8 + 7]));
+        for (int i = 0; i < 8; ++i) {
+          float e0 = 0.f, e1 = 0.f;
+          if (2 * i < nv)
+            e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), kS2, (uniform ? chunk_add(c) : elem_add(c, 2 * i)) - m));
+          if (2 * i + 1 < nv)
+            e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), kS2, (uniform ? chunk_add(c) : elem_add(c, 2 * i + 1)) - m));
+          sum += e0 + e1;
+          pk[i] = pack_bf16(e0, e1);
+        }
       }
+      if (c < t_chunks)
+        l_t += sum;
+      else
+        l_i += sum;
+      uint8_t* atom = sP + (c >> 2) * kTileBytes;
+      st_shared_16(atom + sw128_off(row, (c & 3) * 2), pk[0], pk[1], pk[2], pk[3]);
+      st_shared_16(atom + sw128_off(row, (c & 3) * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
     }
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(p_full);
 
+    // ---- epilogue: out = O_text / l_t + scale * O_ip / l_i      (blend BEFORE to_out, reference :258)
+    const float w_t = 1.0f / l_t, w_i = p.ip_scale / l_i;
     mbar_wait(o_full, 0);
     tc_fence_after();
     __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.N + q_row) * p.C + head * kHd;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      uint32_t raw[32];
-      tmem_ld32(tO + lane_base + c * 32, raw);
+      uint32_t rt[32], ri[32];
+      tmem_ld32(tO + lane_base + c * 32, rt);
+      tmem_ld32(tS + lane_base + c * 32, ri);
       tmem_ld_wait();
       if (q_row < p.N) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            o[e] = fmaf(__uint_as_float(rt[q * 8 + e]), w_t, __uint_as_float(ri[q * 8 + e]) * w_i);
           uint4 u;
-          u.x = pack_bf16(__uint_as_float(raw[q * 8 + 0]), __uint_as_float(raw[q * 8 + 1]));
-          u.y = pack_bf16(__uint_as_float(raw[q * 8 + 2]), __uint_as_float(raw[q * 8 + 3]));
-          u.z = pack_bf16(__uint_as_float(raw[q * 8 + 4]), __uint_as_float(raw[q * 8 + 5]));
-          u.w = pack_bf16(__uint_as_float(raw[q * 8 + 6]), __uint_as_float(raw[q * 8 + 7]));
+          u.x = pack_bf16(o[0], o[1]);
+          u.y = pack_bf16(o[2], o[3]);
+          u.z = pack_bf16(o[4], o[5]);
+          u.w = pack_bf16(o[6], o[7]);
           reinterpret_cast<uint4*>(orow + c * 32)[q] = u;
         }
       }

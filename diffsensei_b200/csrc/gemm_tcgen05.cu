@@ -2,13 +2,14 @@
 //
 //   out[M][Nout] = epilogue( A[M][K] * W[N][K]^T ),  fp32 accumulation in TMEM.
 //
-// One CTA per SM (persistent, static round-robin over 128 x BN output tiles), 256 threads:
+// One CTA per SM (persistent, static round-robin over 128 x BN output tiles), 384 threads:
 //   warp 0    TMA producer   : one lane streams A (128x64) and W (BNx64) k-slices into a STAGES-deep
 //                              shared-memory ring (128-byte swizzle), arming a "full" mbarrier per stage
 //   warp 1    MMA issuer     : one lane issues 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into one of
 //                              two TMEM accumulators, tcgen05.commit frees the stage / publishes the tile
 //   warp 2    TMEM allocator : 2*BN columns (double-buffered accumulator)
-//   warps 4-7 epilogue       : tcgen05.ld the finished accumulator (thread <-> output row), apply
+//   warps 4-11 epilogue      : tcgen05.ld the finished accumulator (thread <-> output row; 4 lane quadrants
+//                              x 2 column halves), apply
 //                              bias / row-bias / GEGLU / activation / residual in fp32, round once, store —
 //                              overlapping the next tile's MMAs thanks to the second accumulator
 //
@@ -27,7 +28,7 @@ namespace ds {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;  // 4 control warps + 8 epilogue warps
 constexpr int kABytes = kBM * kBK * 2;  // 16 KiB per stage
 constexpr int kConvTileH = 8;
 constexpr int kConvTileW = 16;
@@ -88,7 +89,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], 8);  // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -173,12 +174,33 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (128 threads <-> 128 rows)
-    const int wq = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------------------------ epilogue: 8 warps = 4 TMEM lane quadrants
+    // (rows) x 2 column halves; thread <-> one output row, 32-column chunks
+    const int wq = warp & 3;             // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;    // which half of the tile's output columns
     const bool geglu = p.epilogue == DS_EPI_GEGLU;
-    constexpr int BNO_FULL = BN;
-    const int bn_out = geglu ? BN / 2 : BNO_FULL;
+    const int bn_out = geglu ? BN / 2 : BN;
+    const int c_begin = half * (bn_out / 2), c_end = c_begin + bn_out / 2;
     const bool vec_ok = (p.n_out % 8 == 0) && (p.ldo % 8 == 0) && (!p.residual || p.ldres % 8 == 0);
+
+    // v[j] += src[j] (src already offset to the chunk's first column n0), guarded by n0 + j < N
+    auto add32 = [&](float(&v)[32], const float* __restrict__ src, int n0) {
+      if (n0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(src) + q);
+          v[q * 4 + 0] += f.x;
+          v[q * 4 + 1] += f.y;
+          v[q * 4 + 2] += f.z;
+          v[q * 4 + 3] += f.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < p.N) v[j] += __ldg(src + j);
+      }
+    };
+
     int iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
       const int acc = iter & 1;
@@ -211,70 +233,63 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
 
-      for (int c0 = 0; c0 < bn_out; c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         const int nw0 = n_blk * BN + c0;      // weight-row index of column 0 of this chunk
         const int no0 = n_blk * bn_out + c0;  // output column of column 0 of this chunk
         if (no0 >= p.n_out) break;            // warp-uniform
+        const bool full_chunk = vec_ok && (no0 + 32 <= p.n_out);
         uint32_t raw[32];
-        float v[32];
         tmem_ld32(t_row + c0, raw);
+        // issue the residual loads before waiting on TMEM so their latency overlaps
+        uint4 rres[4];
+        const bool vec_res = p.residual != nullptr && row_ok && full_chunk;
+        if (vec_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + orow * p.ldres + no0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rres[q] = __ldg(rp + q);
+        }
         tmem_ld_wait();
+        float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nw0 + j < p.N) v[j] += __ldg(p.bias + nw0 + j);
-        }
-        if (p.rowbias) {
-          const float* rb = p.rowbias + static_cast<long long>(batch) * p.ldrb + nw0;
-          if (row_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nw0 + j < p.N) v[j] += __ldg(rb + j);
-          }
-        }
+        if (p.bias) add32(v, p.bias + nw0, nw0);
+        if (p.rowbias && row_ok) add32(v, p.rowbias + static_cast<long long>(batch) * p.ldrb + nw0, nw0);
         if (geglu) {
           uint32_t graw[32];
           tmem_ld32(t_row + BN / 2 + c0, graw);
           tmem_ld_wait();
-          const int ng0 = nw0 + BN / 2;
+          float g[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float g = __uint_as_float(graw[j]);
-            if (p.bias && ng0 + j < p.N) g += __ldg(p.bias + ng0 + j);
-            v[j] = v[j] * gelu_erf_f(g);
-          }
+          for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(graw[j]);
+          if (p.bias) add32(g, p.bias + nw0 + BN / 2, nw0 + BN / 2);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_fast(g[j]);
         } else if (p.epilogue == DS_EPI_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
         } else if (p.epilogue == DS_EPI_SILU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
         }
 
         if (row_ok) {
-          const bool full_chunk = vec_ok && (no0 + 32 <= p.n_out);
-          if (p.residual) {
-            const __nv_bfloat16* rp = p.residual + orow * p.ldres + no0;
-            if (full_chunk) {
+          if (vec_res) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + q);
-                v[q * 8 + 0] += bf16_lo(u.x);
-                v[q * 8 + 1] += bf16_hi(u.x);
-                v[q * 8 + 2] += bf16_lo(u.y);
-                v[q * 8 + 3] += bf16_hi(u.y);
-                v[q * 8 + 4] += bf16_lo(u.z);
-                v[q * 8 + 5] += bf16_hi(u.z);
-                v[q * 8 + 6] += bf16_lo(u.w);
-                v[q * 8 + 7] += bf16_hi(u.w);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (no0 + j < p.n_out) v[j] += __bfloat162float(rp[j]);
+            for (int q = 0; q < 4; ++q) {
+              v[q * 8 + 0] += bf16_lo(rres[q].x);
+              v[q * 8 + 1] += bf16_hi(rres[q].x);
+              v[q * 8 + 2] += bf16_lo(rres[q].y);
+              v[q * 8 + 3] += bf16_hi(rres[q].y);
+              v[q * 8 + 4] += bf16_lo(rres[q].z);
+              v[q * 8 + 5] += bf16_hi(rres[q].z);
+              v[q * 8 + 6] += bf16_lo(rres[q].w);
+              v[q * 8 + 7] += bf16_hi(rres[q].w);
             }
+          } else if (p.residual) {
+            const __nv_bfloat16* rp = p.residual + orow * p.ldres + no0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (no0 + j < p.n_out) v[j] += __bfloat162float(rp[j]);
           }
           if (p.out_scale != 0.0f) {
 #pragma unroll
