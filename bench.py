@@ -128,61 +128,72 @@ def event_time_ms(fn, iters, stream_sync=True):
 
 # ------------------------------------------------------------------------------------------------ kernel rooflines
 def kernel_rooflines(ds, peaks, device):
-    """The dominant kernel and the two north-star kernels, each timed alone with CUDA events (>= 3 warm-ups,
-    a > L2 scratch write between timed launches), vs the measured BURST peaks."""
+    """The dominant kernel and the two north-star kernels, each timed alone with CUDA events on the launching
+    stream: >= 3 warm-ups, then ROUNDS back-to-back launches that rotate over SETS disjoint input/output buffer
+    sets whose total footprint exceeds the 126 MB L2 (so no launch finds its operands cached, and the host's
+    per-launch enqueue latency — ~10 us through ctypes — is hidden behind queued work instead of being billed to
+    a 30 us kernel).  Reported against the measured BURST peaks (kernel timed alone)."""
     ops = ds.ops
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)    # 256 MB > 126 MB L2
+    bf = torch.bfloat16
 
-    def timed(fn, n=12):
-        for _ in range(3):
-            fn()
-        ts = []
-        for _ in range(n):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            e1.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        return statistics.mean(ts)
+    def timed(calls, rounds):
+        for c in calls:
+            c()
+        for c in calls[:3]:
+            c()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(rounds):
+            for c in calls:
+                c()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / (rounds * len(calls))
 
     out = {}
     # dominant kernel: gemm_bf16_tcgen05 at the level-2 FF1/GEGLU shape (60 launches per step, 22.5 of 54.8 TFLOP)
     M, N, K = 8192, 10240, 1280
-    a = torch.randn(M, K, device=device).to(torch.bfloat16)
-    w = (torch.randn(N, K, device=device) * K ** -0.5).to(torch.bfloat16)
+    sets = []
+    for i in range(3):                                   # 3 x (21 + 26 + 42 MB) = 267 MB > L2
+        a = torch.randn(M, K, device=device).to(bf)
+        w = (torch.randn(N, K, device=device) * K ** -0.5).to(bf)
+        o = torch.empty(M, N // 2, dtype=bf, device=device)
+        sets.append((a, w, o))
     b = torch.zeros(N, device=device)
-    o = torch.empty(M, N // 2, dtype=torch.bfloat16, device=device)
-    ms = timed(lambda: ops.gemm(a, w, b, epilogue=ops.EPI_GEGLU, out=o))
+    ms = timed([(lambda s=s: ops.gemm(s[0], s[1], b, epilogue=ops.EPI_GEGLU, out=s[2])) for s in sets], 4)
     flops = 2.0 * M * N * K
     out["roofline"] = {"kernel": "gemm_bf16_tcgen05<256> FF1+GEGLU M8192 N10240 K1280", "bound": "tensor",
                        "achieved": round(flops / ms / 1e9, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                        "frac": round(flops / ms / 1e9 / peaks["bf16_tflops"], 4), "traffic": None,
-                       "ms_per_launch": round(ms, 4), "peak_source": peaks["source"] + " burst (kernel timed alone)"}
-    del a, w, o
+                       "ms_per_launch": round(ms, 4), "peak_source": peaks["source"] + " burst (kernel timed alone)",
+                       "algorithmic_GFLOP": round(flops / 1e9, 1)}
+    del sets
     # fused GroupNorm+SiLU at (8, 128, 128, 320): algorithmic bytes = read x + write y
-    x = torch.randn(8, 128, 128, 320, device=device).to(torch.bfloat16)
-    y = torch.empty_like(x)
     ga, be = torch.ones(320, device=device), torch.zeros(320, device=device)
-    st = torch.empty(4 * 8 * 32, device=device)
-    ms = timed(lambda: ops.groupnorm_silu(x, ga, be, 32, 1e-5, True, out=y, stats=st))
-    gb = 2 * x.numel() * 2 / 1e9
+    sets = []
+    for i in range(4):                                   # 4 x (84 + 84 MB) = 671 MB > L2
+        x = torch.randn(8, 128, 128, 320, device=device).to(bf)
+        sets.append((x, torch.empty_like(x), torch.empty(4 * 8 * 32, device=device)))
+    ms = timed([(lambda s=s: ops.groupnorm_silu(s[0], ga, be, 32, 1e-5, True, out=s[1], stats=s[2])) for s in sets], 4)
+    gb = 2 * sets[0][0].numel() * 2 / 1e9
     out["roofline_gn"] = {"kernel": "gn_stats_kernel + gn_apply_kernel (8,128,128,320) bf16", "bound": "hbm",
                           "achieved": round(gb / (ms * 1e-3), 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": round(gb / (ms * 1e-3) / peaks["hbm_gbs"], 4), "traffic": None,
                           "ms_per_launch": round(ms, 4), "algorithmic_MB": round(gb * 1e3, 1)}
-    del x, y
+    del sets
     # fused self-attention at level 1: B=8, N=4096, 10 heads (4*N^2*C*B flops)
     B, Nn, heads = 8, 4096, 10
-    qkv = torch.randn(B, Nn, 3 * heads * 64, device=device).to(torch.bfloat16)
-    ao = torch.empty(B, Nn, heads * 64, dtype=torch.bfloat16, device=device)
-    ms = timed(lambda: ops.attention_self(qkv, heads, out=ao))
+    sets = []
+    for i in range(2):                                   # 2 x (126 + 42 MB) = 336 MB > L2
+        sets.append((torch.randn(B, Nn, 3 * heads * 64, device=device).to(bf),
+                     torch.empty(B, Nn, heads * 64, dtype=bf, device=device)))
+    ms = timed([(lambda s=s: ops.attention_self(s[0], heads, out=s[1])) for s in sets], 4)
     flops = 4.0 * Nn * Nn * heads * 64 * B
     out["roofline_attn"] = {"kernel": "flash_attn_kernel B8 N4096 h10 d64", "bound": "tensor",
                             "achieved": round(flops / ms / 1e9, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                             "frac": round(flops / ms / 1e9 / peaks["bf16_tflops"], 4), "traffic": None,
-                            "ms_per_launch": round(ms, 4)}
+                            "ms_per_launch": round(ms, 4), "algorithmic_GFLOP": round(flops / 1e9, 1)}
     return out
 
 
