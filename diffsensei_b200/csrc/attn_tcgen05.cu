@@ -193,56 +193,12 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int row = wq * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
     float m_ref = -INFINITY, l = 0.f;
-    for (int j = 0; j < num_kv_tiles; ++j) {
-      const int kv_valid = p.Nkv - j * kTile;  // >= 128: whole tile valid
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      // ---- pass 1: row max (two TMEM loads in flight per wait)
+
+    // One sweep over this row of S: P = 2^(S*scale - m) -> bf16 -> swizzled smem.  Returns the row sum of P and
+    // (via t_max) the largest exponent seen, i.e. (row max of this tile) - m in the log2 domain.
+    auto sweep = [&](float neg_m, int kv_valid, float& t_max) -> float {
       const bool full_tile = kv_valid >= kTile;  // warp-uniform
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; c += 2) {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(tS + lane_base + c * 32, r0);
-        tmem_ld32(tS + lane_base + c * 32 + 32, r1);
-        tmem_ld_wait();
-        if (full_tile) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r0[i]));
-            if (c * 32 + 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r1[i]));
-          }
-        }
-      }
-      const float m_tile = mx * p.scale_log2;
-      float alpha = 1.0f;
-      bool need = false;
-      if (j == 0) {
-        m_ref = m_tile;
-      } else if (m_tile > m_ref + kRescaleThreshold) {
-        alpha = ex2(m_ref - m_tile);
-        m_ref = m_tile;
-        l *= alpha;
-        need = true;
-      }
-      if (__any_sync(0xffffffffu, need)) {  // rescale this warp's 32 rows of O in TMEM
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t raw[32];
-          tmem_ld32(tO + lane_base + c * 32, raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
-          tmem_st32(tO + lane_base + c * 32, raw);
-        }
-        tmem_st_wait();
-      }
-      // ---- pass 2: P = exp2(S*scale - m_ref) -> bf16 -> swizzled smem; row sum
-      float lsum = 0.f;
-      const float neg_m = -m_ref;
+      float lsum = 0.f, tm = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t raw[32];
@@ -252,20 +208,29 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (full_tile) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m));
-            const float e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m));
+            const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
+            const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
+            tm = fmaxf(tm, fmaxf(t0, t1));
+            const float e0 = ex2(t0), e1 = ex2(t1);
             lsum += e0 + e1;
-            pk[i] = pack_bf16(e0, e1);
+            pk[i] = pack_bf16_alu(e0, e1);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m));
-            float e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m));
-            if (c * 32 + 2 * i >= kv_valid) e0 = 0.f;
-            if (c * 32 + 2 * i + 1 >= kv_valid) e1 = 0.f;
+            const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
+            const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
+            float e0 = 0.f, e1 = 0.f;
+            if (c * 32 + 2 * i < kv_valid) {
+              tm = fmaxf(tm, t0);
+              e0 = ex2(t0);
+            }
+            if (c * 32 + 2 * i + 1 < kv_valid) {
+              tm = fmaxf(tm, t1);
+              e1 = ex2(t1);
+            }
             lsum += e0 + e1;
-            pk[i] = pack_bf16(e0, e1);
+            pk[i] = pack_bf16_alu(e0, e1);
           }
         }
         uint8_t* atom = sP + (c >> 1) * kTileBytes;
@@ -273,6 +238,58 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int q = 0; q < 4; ++q)
           st_shared_16(atom + sw128_off(row, (c & 1) * 4 + q), pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2],
                        pk[q * 4 + 3]);
+      }
+      t_max = tm;
+      return lsum;
+    };
+
+    for (int j = 0; j < num_kv_tiles; ++j) {
+      const int kv_valid = p.Nkv - j * kTile;  // >= 128: whole tile valid
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      float lsum, t_max;
+      if (j == 0) {
+        // first tile: exact row max first (nothing to compare against yet)
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(tS + lane_base + c * 32, r0);
+          tmem_ld32(tS + lane_base + c * 32 + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r0[i]));
+            if (c * 32 + 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r1[i]));
+          }
+        }
+        m_ref = mx * p.scale_log2;
+        lsum = sweep(-m_ref, kv_valid, t_max);
+      } else {
+        // OPTIMISTIC single sweep against the running reference max.  Correct as long as no score of this tile
+        // exceeds m_ref by more than 2^8 (P <= 256 is exact enough in bf16 and cannot overflow); otherwise the
+        // affected rows move their reference, O and l are rescaled, and the warp redoes the sweep.
+        lsum = sweep(-m_ref, kv_valid, t_max);
+        const bool need = t_max > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          float alpha = 1.0f;
+          if (need) {
+            alpha = ex2(-t_max);  // 2^(m_ref_old - m_ref_new)
+            m_ref += t_max;
+            l *= alpha;
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {  // rescale this warp's 32 rows of O in TMEM
+            uint32_t raw[32];
+            tmem_ld32(tO + lane_base + c * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+            tmem_st32(tO + lane_base + c * 32, raw);
+          }
+          tmem_st_wait();
+          lsum = sweep(-m_ref, kv_valid, t_max);
+        }
       }
       l += lsum;
       fence_proxy_async_smem();  // st.shared -> visible to the tensor core's async-proxy reads
@@ -481,7 +498,7 @@ cross_ip_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const float e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), kS2, off));
           const float e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), kS2, off));
           sum += e0 + e1;
-          pk[i] = pack_bf16(e0, e1);
+          pk[i] = pack_bf16_alu(e0, e1);
         }
       } else {
 #pragma unroll
@@ -492,7 +509,7 @@ cross_ip_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           if (2 * i + 1 < nv)
             e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), kS2, (uniform ? chunk_add(c) : elem_add(c, 2 * i + 1)) - m));
           sum += e0 + e1;
-          pk[i] = pack_bf16(e0, e1);
+          pk[i] = pack_bf16_alu(e0, e1);
         }
       }
       if (c < t_chunks)

@@ -9,7 +9,9 @@
 //                              two TMEM accumulators, tcgen05.commit frees the stage / publishes the tile
 //   warp 2    TMEM allocator : 2*BN columns (double-buffered accumulator)
 //   warps 4-11 epilogue      : tcgen05.ld the finished accumulator (thread <-> output row; 4 lane quadrants
-//                              x 2 column halves), apply
+//                              x 2 column halves); bf16 outputs are staged as 128-B-swizzled [128][64] smem tiles
+//                              and written with TMA stores (residual tiles arrive by TMA loads into the same
+//                              staging tile), so all epilogue global traffic is full-line and coalesced; apply
 //                              bias / row-bias / GEGLU / activation / residual in fp32, round once, store —
 //                              overlapping the next tile's MMAs thanks to the second accumulator
 //
@@ -21,6 +23,8 @@
 //
 // Reference arithmetic replaced: every nn.Linear / nn.Conv2d on the UNet sampling path
 // (src/models/attention_processor.py:56-84,207-261; diffusers blocks reached from src/models/unet.py:190-338).
+#include <cstdlib>
+
 #include "ds_common.cuh"
 #include "ds_host.h"
 
@@ -42,38 +46,53 @@ struct GemmParams {
   int n_out;  // output columns (N, or N/2 for GEGLU)
   int ldo, ldres, rows_per_batch, ldrb;
   int epilogue, out_fp32;
+  int tma_epilogue;  // 1: stage bf16 output tiles in smem and TMA-store them (residual tiles TMA-loaded)
   float out_scale;
   int num_m_tiles, num_n_tiles, num_k_iters;
   // conv geometry
-  int conv, stride, Ho, Wo, tiles_x, tiles_y, cin_chunks;
+  int conv, stride, Ho, Wo, tiles_x, tiles_y, cin_chunks, conv_B;
 };
 
-template <int BN>
+// PAIR = 1: one CTA owns a 128 x BN tile.  PAIR = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) owns a
+// 256 x BN tile: each CTA holds its own 128 rows of A and HALF of the BN weight rows, the tensor core of each SM
+// reads the other half from its peer's shared memory, so per-SM smem operand traffic per MMA drops from
+// (4 + BN/32) KB to (4 + BN/64) KB and the TMA fill traffic drops likewise — the 1-CTA tiles were capped by the
+// 128 B/clk shared-memory port (BN=256: ~67 %, BN=128: ~50 % tensor-pipe duty; profiles/r01_ncu_summary.md).
+template <int BN, int PAIR>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBRows = BN / PAIR;  // weight rows each CTA stages
+  static constexpr int kBBytes = kBRows * kBK * 2;
+  static constexpr int kStages = (196608 / (kABytes + kBBytes)) > 8 ? 8 : (196608 / (kABytes + kBBytes));
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStageOutBytes = 2 * kBM * 64 * 2;  // two [128][64] bf16 epilogue staging tiles (one per column half)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStageOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, int PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                   const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::kStages;
+  const uint32_t cta_rank = (PAIR == 2) ? cluster_ctarank() : 0u;  // rank inside the CTA pair; 0 = leader
+  const bool leader = cta_rank == 0;
+  const int unit0 = blockIdx.x / PAIR;     // first work unit (a 128*PAIR x BN tile) of this CTA (pair)
+  const int unit_step = gridDim.x / PAIR;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::kBBytes);
+  uint8_t* sOut = sB + STAGES * Cfg::kBBytes;  // 2 x [128][64] bf16, 128-B swizzled (TMA store / residual load)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + Cfg::kStageOutBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;        // [2] residual tile landed (one per column-half group)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -81,58 +100,89 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_epilogue) {
+      tma_prefetch_desc(&tmC);
+      if (p.residual) tma_prefetch_desc(&tmR);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], PAIR);  // pair: the leader's expect_tx arrival + the peer producer's remote arrival
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], 8 * PAIR);  // one arrival per epilogue warp (of both CTAs, on the leader's barrier)
+      mbar_init(&res_bar[i], 1);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (PAIR == 2) {
+      tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR == 2)
+    cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int m_units = (p.num_m_tiles + PAIR - 1) / PAIR;
+  const int total_tiles = m_units * p.num_n_tiles;  // work units; each covers PAIR vertically adjacent M tiles
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         const int n_blk = tile % p.num_n_tiles;
-        const int m_blk = tile / p.num_n_tiles;
+        const int m_blk = (tile / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
         int img = 0, x0 = 0, y0 = 0;
         if (p.conv) {
           const int per_img = p.tiles_x * p.tiles_y;
-          img = m_blk / per_img;
+          img = m_blk / per_img;  // >= B for the odd tail of a pair: every TMA element is then out of bounds (zeros)
           const int rem = m_blk - img * per_img;
           y0 = (rem / p.tiles_x) * kConvTileH;
           x0 = (rem % p.tiles_x) * kConvTileW;
         }
+        const int b_row0 = n_blk * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
         for (int kb = 0; kb < p.num_k_iters; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (PAIR == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          } else if (leader) {
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);  // both CTAs' bytes land on this barrier
+          } else {
+            mbar_arrive_cluster(&full_bar[stage], 0);
+          }
           if (p.conv) {
             const int tap = kb / p.cin_chunks;
             const int cc = kb - tap * p.cin_chunks;
             const int r = tap / 3, s = tap - r * 3;
-            tma_load_4d(sA + stage * kABytes, &tmA, &full_bar[stage], cc * kBK, x0 * p.stride + s - 1,
-                        y0 * p.stride + r - 1, img);
+            if (PAIR == 2)
+              tma_load_4d_pair(sA + stage * kABytes, &tmA, &full_bar[stage], cc * kBK, x0 * p.stride + s - 1,
+                               y0 * p.stride + r - 1, img);
+            else
+              tma_load_4d(sA + stage * kABytes, &tmA, &full_bar[stage], cc * kBK, x0 * p.stride + s - 1,
+                          y0 * p.stride + r - 1, img);
           } else {
-            tma_load_2d(sA + stage * kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM);
+            if (PAIR == 2)
+              tma_load_2d_pair(sA + stage * kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM);
+            else
+              tma_load_2d(sA + stage * kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM);
           }
-          tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN);
+          if (PAIR == 2)
+            tma_load_2d_pair(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, b_row0);
+          else
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, b_row0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -142,12 +192,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+    if (lane == 0 && leader) {  // in a pair only the leader CTA issues (for both SMs' tensor cores)
+      constexpr uint32_t idesc = make_idesc_bf16(kBM * PAIR, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++iter) {
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -162,15 +212,25 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int k = 0; k < kBK / 16; ++k) {
             const uint64_t adesc = make_sw128_desc(a_addr + k * 32, 1024, 16);
             const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 1024, 16);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR == 2)
+              umma_ss_pair(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
+          // stage reusable (in both CTAs) once these MMAs have read it
+          if (PAIR == 2)
+            umma_commit_pair(&empty_bar[stage]);
+          else
+            umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        if (PAIR == 2)  // accumulator complete: wake the epilogue warps of both CTAs
+          umma_commit_pair(&tfull_bar[acc]);
+        else
+          umma_commit(&tfull_bar[acc]);
       }
     }
   } else if (warp >= 4) {
@@ -202,11 +262,23 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     };
 
     int iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    uint32_t res_phase = 0;
+    // hand the accumulator back to the MMA issuer (pair: the issuer lives in the leader CTA)
+    auto release_acc = [&](int acc) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR == 2)
+          mbar_arrive_cluster(&tempty_bar[acc], 0);
+        else
+          mbar_arrive(&tempty_bar[acc]);
+      }
+    };
+    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       const int n_blk = tile % p.num_n_tiles;
-      const int m_blk = tile / p.num_n_tiles;
+      const int m_blk = (tile / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
       const int r_local = wq * 32 + lane;
 
       // row -> (valid, output row index, batch index)
@@ -219,7 +291,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int rem = m_blk - img * per_img;
         const int y = (rem / p.tiles_x) * kConvTileH + r_local / kConvTileW;
         const int x = (rem % p.tiles_x) * kConvTileW + r_local % kConvTileW;
-        row_ok = (y < p.Ho) && (x < p.Wo);
+        row_ok = (y < p.Ho) && (x < p.Wo) && (img < p.conv_B);
         orow = (static_cast<long long>(img) * p.Ho + y) * p.Wo + x;
         batch = img;
       } else {
@@ -233,23 +305,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
 
-      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-        const int nw0 = n_blk * BN + c0;      // weight-row index of column 0 of this chunk
-        const int no0 = n_blk * bn_out + c0;  // output column of column 0 of this chunk
-        if (no0 >= p.n_out) break;            // warp-uniform
-        const bool full_chunk = vec_ok && (no0 + 32 <= p.n_out);
+      // accumulator chunk -> fp32 values with bias / row-bias / GEGLU / activation applied (no residual yet)
+      auto load_chunk = [&](int c0, float(&v)[32]) {
+        const int nw0 = n_blk * BN + c0;  // weight-row index of column 0 of this chunk
         uint32_t raw[32];
         tmem_ld32(t_row + c0, raw);
-        // issue the residual loads before waiting on TMEM so their latency overlaps
-        uint4 rres[4];
-        const bool vec_res = p.residual != nullptr && row_ok && full_chunk;
-        if (vec_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + orow * p.ldres + no0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rres[q] = __ldg(rp + q);
-        }
         tmem_ld_wait();
-        float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
         if (p.bias) add32(v, p.bias + nw0, nw0);
@@ -271,21 +332,103 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
         }
+      };
 
-        if (row_ok) {
-          if (vec_res) {
+      if (p.tma_epilogue) {
+        // ---------------- coalesced path: 64-column blocks staged in swizzled smem, moved by TMA
+        uint8_t* stage = sOut + half * (kBM * 64 * 2);
+        const bool issuer = (wq == 0) && (lane == 0);  // one thread per column-half group drives the TMA engine
+        const int bar_id = 1 + half;                   // named barrier of this group's 4 warps (128 threads)
+        int cx = 0, cy = 0, cimg = 0;                  // tile origin in the output tensor map
+        if (p.conv) {
+          const int per_img = p.tiles_x * p.tiles_y;
+          cimg = m_blk / per_img;
+          const int rem = m_blk - cimg * per_img;
+          cy = (rem / p.tiles_x) * kConvTileH;
+          cx = (rem % p.tiles_x) * kConvTileW;
+        }
+        bool released = false;
+        for (int cb = c_begin; cb < c_end; cb += 64) {
+          const int no0 = n_blk * bn_out + cb;  // first output column of this 64-wide block
+          if (no0 >= p.n_out) break;            // group-uniform
+          // the previous TMA store must have finished READING the staging tile before anyone overwrites it
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (p.residual) {
+            if (issuer) {
+              mbar_arrive_expect_tx(&res_bar[half], kBM * 64 * 2);
+              if (p.conv)
+                tma_load_4d(stage, &tmR, &res_bar[half], no0, cx, cy, cimg);
+              else
+                tma_load_2d(stage, &tmR, &res_bar[half], no0, m_blk * kBM);
+            }
+            mbar_wait(&res_bar[half], res_phase);
+            res_phase ^= 1;
+          }
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            float v[32];
+            load_chunk(cb + cc * 32, v);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              v[q * 8 + 0] += bf16_lo(rres[q].x);
-              v[q * 8 + 1] += bf16_hi(rres[q].x);
-              v[q * 8 + 2] += bf16_lo(rres[q].y);
-              v[q * 8 + 3] += bf16_hi(rres[q].y);
-              v[q * 8 + 4] += bf16_lo(rres[q].z);
-              v[q * 8 + 5] += bf16_hi(rres[q].z);
-              v[q * 8 + 6] += bf16_lo(rres[q].w);
-              v[q * 8 + 7] += bf16_hi(rres[q].w);
+              uint8_t* sp = stage + r_local * 128 + (((cc * 4 + q) ^ (r_local & 7)) << 4);
+              if (p.residual) {
+                uint4 u;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                             : "r"(smem_u32(sp)));
+                v[q * 8 + 0] += bf16_lo(u.x);
+                v[q * 8 + 1] += bf16_hi(u.x);
+                v[q * 8 + 2] += bf16_lo(u.y);
+                v[q * 8 + 3] += bf16_hi(u.y);
+                v[q * 8 + 4] += bf16_lo(u.z);
+                v[q * 8 + 5] += bf16_hi(u.z);
+                v[q * 8 + 6] += bf16_lo(u.w);
+                v[q * 8 + 7] += bf16_hi(u.w);
+              }
+              if (p.out_scale != 0.0f) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[q * 8 + e] *= p.out_scale;
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(sp)),
+                           "r"(pack_bf16(v[q * 8 + 0], v[q * 8 + 1])), "r"(pack_bf16(v[q * 8 + 2], v[q * 8 + 3])),
+                           "r"(pack_bf16(v[q * 8 + 4], v[q * 8 + 5])), "r"(pack_bf16(v[q * 8 + 6], v[q * 8 + 7]))
+                           : "memory");
             }
-          } else if (p.residual) {
+          }
+          if (cb + 64 >= c_end || n_blk * bn_out + cb + 64 >= p.n_out) {
+            // last block of this tile for this warp: TMEM is drained -> hand the accumulator back early
+            release_acc(acc);
+            released = true;
+          }
+          fence_proxy_async_smem();  // st.shared -> visible to the TMA (async proxy)
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (issuer) {
+            if (p.conv)
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                               &tmC),
+                           "r"(smem_u32(stage)), "r"(no0), "r"(cx), "r"(cy), "r"(cimg)
+                           : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
+                           "r"(smem_u32(stage)), "r"(no0), "r"(m_blk * kBM)
+                           : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (!released) release_acc(acc);  // this column half lies entirely beyond N
+        continue;
+      }
+
+      // ---------------- direct path (fp32 output or rows that are not 16-byte addressable): per-thread row stores
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        const int no0 = n_blk * bn_out + c0;  // output column of column 0 of this chunk
+        if (no0 >= p.n_out) break;            // warp-uniform
+        const bool full_chunk = vec_ok && (no0 + 32 <= p.n_out);
+        float v[32];
+        load_chunk(c0, v);
+        if (row_ok) {
+          if (p.residual) {
             const __nv_bfloat16* rp = p.residual + orow * p.ldres + no0;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -308,56 +451,76 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           } else {
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + no0;
-            if (full_chunk) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                uint4 u;
-                u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-                u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-                u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-                u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-                reinterpret_cast<uint4*>(op)[q] = u;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (no0 + j < p.n_out) op[j] = __float2bfloat16(v[j]);
-            }
+            for (int j = 0; j < 32; ++j)
+              if (no0 + j < p.n_out) op[j] = __float2bfloat16(v[j]);
           }
         }
       }
-      // release the accumulator back to the MMA issuer
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      release_acc(acc);
     }
+    if (p.tma_epilogue && wq == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   // ---------------------------------------------------------------------- teardown
   tc_fence_before();
-  __syncthreads();
+  if (PAIR == 2)
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
+  else
+    __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (PAIR == 2)
+      tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else
+      tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
-                       cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+template <int BN, int PAIR>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       const CUtensorMap& tmR, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, PAIR>;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
-    DS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int total = p.num_m_tiles * p.num_n_tiles;
-  const int grid = total < num_sms ? total : num_sms;
-  gemm_bf16_tcgen05<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  const int units = ((p.num_m_tiles + PAIR - 1) / PAIR) * p.num_n_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // The schedule is persistent with a static stride, so every CTA (pair) must be co-resident: a pair needs both
+  // SMs of one TPC, and not every TPC of a 148-SM part has two enabled SMs.  Ask the runtime how many clusters fit.
+  static int max_groups = 0;
+  if (max_groups == 0) {
+    int n = num_sms / PAIR;
+    if (PAIR == 2) {
+      cfg.gridDim = dim3((num_sms / PAIR) * PAIR);
+      int q = 0;
+      if (cudaOccupancyMaxActiveClusters(&q, gemm_bf16_tcgen05<BN, PAIR>, &cfg) == cudaSuccess && q > 0) n = q < n ? q : n;
+      (void)cudaGetLastError();
+    }
+    max_groups = n;
+    if (getenv("DS_DEBUG"))
+      fprintf(stderr, "[dsengine] gemm<%d,%d>: %d co-resident CTA %s of %d SMs\n", BN, PAIR, max_groups,
+              PAIR == 2 ? "pairs" : "singles", num_sms);
+  }
+  const int groups = units < max_groups ? units : max_groups;
+  cfg.gridDim = dim3(groups * PAIR);
+  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR>, tmA, tmB, tmC, tmR, p));
   DS_LAUNCH_OK("gemm_bf16_tcgen05");
   return DS_OK;
 }
@@ -370,20 +533,57 @@ static int pick_bn(int N, int epilogue) {
   return (e256 + 0.04 >= e128) ? 256 : 128;
 }
 
-static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& p, cudaStream_t stream) {
+// Output / residual tensor maps for the TMA epilogue: plain GEMM = 2-D {n_out, M}, box {64, 128};
+// conv = 4-D NHWC {Cout, Wo, Ho, B}, box {64, 16, 8, 1} (the same 8x16 pixel patch as the M tile).
+static bool make_out_map(CUtensorMap* m, const void* base, const GemmParams& p, int ld, int conv_B) {
+  if (p.conv) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(p.n_out), static_cast<uint64_t>(p.Wo), static_cast<uint64_t>(p.Ho),
+                              static_cast<uint64_t>(conv_B)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(p.Wo) * ld * 2,
+                                 static_cast<uint64_t>(p.Ho) * p.Wo * ld * 2};
+    const uint32_t box[4] = {64, kConvTileW, kConvTileH, 1};
+    return encode_tmap_bf16(m, base, 4, dims, strides, box, nullptr);
+  }
+  const uint64_t dims[2] = {static_cast<uint64_t>(p.n_out), static_cast<uint64_t>(p.M)};
+  const uint64_t strides[1] = {static_cast<uint64_t>(ld) * 2};
+  const uint32_t box[2] = {64, kBM};
+  return encode_tmap_bf16(m, base, 2, dims, strides, box, nullptr);
+}
+
+static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& p, int conv_B, cudaStream_t stream) {
   DeviceInfo dev;
   if (!get_device(&dev)) return DS_ERR_CUDA;
   const int bn = pick_bn(p.N, p.epilogue);
+  // CTA pairs (cta_group::2) whenever there are at least two M tiles to pair up; DS_GEMM_PAIR=0 forces 1-CTA tiles
+  static const int pair_env = [] {
+    const char* e = getenv("DS_GEMM_PAIR");
+    return e ? atoi(e) : 1;
+  }();
+  const int pair = (pair_env != 0 && p.num_m_tiles >= 2) ? 2 : 1;
   CUtensorMap tmB;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-    const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
+    const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn / pair)};
     if (!encode_tmap_bf16(&tmB, w, 2, dims, strides, box, nullptr)) return DS_ERR_CUDA;
   }
+  // coalesced TMA epilogue whenever the bf16 output (and residual) rows are 16-byte addressable
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  p.tma_epilogue = !p.out_fp32 && p.n_out % 8 == 0 && p.ldo % 8 == 0 && aligned16(p.out) &&
+                   (!p.residual || (p.ldres % 8 == 0 && aligned16(p.residual)));
+  CUtensorMap tmC = tmA, tmR = tmA;  // placeholders when the direct epilogue is used
+  if (p.tma_epilogue) {
+    if (!make_out_map(&tmC, p.out, p, p.ldo, conv_B)) return DS_ERR_CUDA;
+    if (p.residual && !make_out_map(&tmR, p.residual, p, p.ldres, conv_B)) return DS_ERR_CUDA;
+  }
   p.num_n_tiles = (p.N + bn - 1) / bn;
-  if (bn == 256) return launch_gemm<256>(tmA, tmB, p, dev.num_sms, stream);
-  return launch_gemm<128>(tmA, tmB, p, dev.num_sms, stream);
+  p.conv_B = conv_B;
+  if (pair == 2) {
+    if (bn == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
+    return launch_gemm<128, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
+  }
+  if (bn == 256) return launch_gemm<256, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
+  return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
 }
 
 }  // namespace ds
@@ -433,7 +633,7 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
   p.num_m_tiles = (a->M + kBM - 1) / kBM;
   p.num_k_iters = (a->K + kBK - 1) / kBK;
   p.conv = 0;
-  return run_gemm(tmA, a->w, a->ldw, p, static_cast<cudaStream_t>(stream));
+  return run_gemm(tmA, a->w, a->ldw, p, 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ds_conv3x3_nhwc(const ds_conv3x3_args* a, void* stream) {
@@ -484,5 +684,5 @@ extern "C" int ds_conv3x3_nhwc(const ds_conv3x3_args* a, void* stream) {
   p.Ho = Ho;
   p.Wo = Wo;
   p.cin_chunks = a->Cin / kBK;
-  return run_gemm(tmA, a->w, 9 * a->Cin, p, static_cast<cudaStream_t>(stream));
+  return run_gemm(tmA, a->w, 9 * a->Cin, p, a->B, static_cast<cudaStream_t>(stream));
 }

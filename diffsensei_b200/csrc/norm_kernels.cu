@@ -38,21 +38,21 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x, double* __restrict_
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   const uint4* base = x + (static_cast<size_t>(b) * HW) * cv + cvec;
   int p = p0 + prow;
-  // 4 independent 16-byte loads in flight per thread
-  for (; p + 3 * rpb < p1; p += 4 * rpb) {
-    uint4 u[4];
+  // 8 independent 16-byte loads in flight per thread
+  for (; p + 7 * rpb < p1; p += 8 * rpb) {
+    uint4 u[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = __ldg(base + static_cast<size_t>(p + k * rpb) * cv);
+    for (int k = 0; k < 8; ++k) u[k] = __ldg(base + static_cast<size_t>(p + k * rpb) * cv);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
       const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float a = bf16_lo(w[j]), c = bf16_hi(w[j]);
         s[2 * j] += a;
-        q[2 * j] += a * a;
+        q[2 * j] = fmaf(a, a, q[2 * j]);
         s[2 * j + 1] += c;
-        q[2 * j + 1] += c * c;
+        q[2 * j + 1] = fmaf(c, c, q[2 * j + 1]);
       }
     }
   }
@@ -133,10 +133,10 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__
       float a = fmaf(bf16_lo(w[j]), sc[2 * j], sf[2 * j]);
       float c = fmaf(bf16_hi(w[j]), sc[2 * j + 1], sf[2 * j + 1]);
       if (kSilu) {
-        a = silu_f(a);
-        c = silu_f(c);
+        a = silu_tanh_f(a);
+        c = silu_tanh_f(c);
       }
-      o[j] = pack_bf16(a, c);
+      o[j] = pack_bf16_alu(a, c);
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
   };
@@ -206,8 +206,8 @@ __global__ void layernorm_kernel(const uint4* __restrict__ x, uint4* __restrict_
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        o[j] = pack_bf16((v[i][2 * j] - mean) * rstd * ga[2 * j] + be[2 * j],
-                         (v[i][2 * j + 1] - mean) * rstd * ga[2 * j + 1] + be[2 * j + 1]);
+        o[j] = pack_bf16_alu((v[i][2 * j] - mean) * rstd * ga[2 * j] + be[2 * j],
+                             (v[i][2 * j + 1] - mean) * rstd * ga[2 * j + 1] + be[2 * j + 1]);
       yr[vi] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
@@ -234,10 +234,10 @@ extern "C" int ds_groupnorm_silu(const void* x, void* y, const float* gamma, con
   if (rpb < 1) rpb = 1;
   const int threads = cv * rpb;
   DS_REQUIRE(threads <= 1024, "ds_groupnorm_silu: C too large for one CTA row");
-  // pixels per CTA: aim at ~8 CTAs per SM over the whole tensor, at least 4 sweeps of the CTA's pixel rows
+  // pixels per CTA: aim at ~8 CTAs per SM over the whole tensor, a multiple of 8 sweeps of the CTA's pixel rows
   long long ppc = (static_cast<long long>(B) * HW + dev.num_sms * 8 - 1) / (dev.num_sms * 8);
-  if (ppc < 4 * rpb) ppc = 4 * rpb;
-  ppc = ((ppc + 4 * rpb - 1) / (4 * rpb)) * (4 * rpb);
+  if (ppc < 8 * rpb) ppc = 8 * rpb;
+  ppc = ((ppc + 8 * rpb - 1) / (8 * rpb)) * (8 * rpb);
   const int chunks = static_cast<int>((HW + ppc - 1) / ppc);
   double* dstats = reinterpret_cast<double*>(stats);
   DS_CUDA_OK(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * B * groups, st));
@@ -269,15 +269,22 @@ extern "C" int ds_layernorm(const void* x, void* y, const float* gamma, const fl
   const int threads = 256;
   const int blocks = (rows + 7) / 8;
   const int cv = C / 8;
-  if (cv <= 32 * 4)
-    layernorm_kernel<4><<<blocks, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), gamma, beta,
-                                                    rows, C, eps);
-  else if (cv <= 32 * 8)
-    layernorm_kernel<8><<<blocks, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), gamma, beta,
-                                                    rows, C, eps);
-  else
-    layernorm_kernel<16><<<blocks, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), gamma, beta,
-                                                     rows, C, eps);
+  const int per_lane = (cv + 31) / 32;  // 16-byte vectors each lane holds: exact-fit instantiation keeps registers low
+#define DS_LN_CASE(V)                                                                                             \
+  layernorm_kernel<V><<<blocks, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), gamma, beta, \
+                                                  rows, C, eps)
+  switch (per_lane) {
+    case 1: DS_LN_CASE(1); break;
+    case 2: DS_LN_CASE(2); break;
+    case 3: DS_LN_CASE(3); break;
+    case 4: DS_LN_CASE(4); break;
+    case 5: DS_LN_CASE(5); break;
+    case 6: DS_LN_CASE(6); break;
+    case 7:
+    case 8: DS_LN_CASE(8); break;
+    default: DS_LN_CASE(16); break;
+  }
+#undef DS_LN_CASE
   DS_LAUNCH_OK("layernorm_kernel");
   return DS_OK;
 }
