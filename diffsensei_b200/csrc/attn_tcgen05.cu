@@ -8,7 +8,7 @@
 //       warp 1   MMA issuer   : S = Q K_j^T (M128 N128 K64) into TMEM; O (+)= P_j V_j (M128 N64 K128),
 //                               V consumed MN-major straight from its [kv][d] TMA tile
 //       warp 2   TMEM allocator (256 columns: S 0..127, O 128..191)
-//       warps 4-7 softmax     : thread <-> query row.  tcgen05.ld S, running max in the log2 domain with LAZY
+//       warps 4-11 softmax    : 2 threads per query row (64 key columns each).  tcgen05.ld S, running max in the log2 domain with LAZY
 //                               rescaling (O/l are only rescaled when the row max grows by > 2^8), exp2,
 //                               P_j -> bf16 into swizzled shared memory as the next MMA's A operand.
 //                               O never leaves TMEM until the final 1/l normalisation.
@@ -72,7 +72,9 @@ struct FlashParams {
 // =================================================================================================
 // (1) flash attention
 // =================================================================================================
-__global__ void __launch_bounds__(kAttnThreads, 2)
+constexpr int kFlashThreads = 384;  // 4 control warps + 8 softmax warps (2 threads per query row)
+
+__global__ void __launch_bounds__(kFlashThreads, 2)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
   constexpr int RING = 3;
@@ -90,6 +92,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* p_full = s_full + 1;
   uint64_t* o_full = p_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* s_xchg = reinterpret_cast<float*>(tmem_slot + 2);  // [2][128] per-row exchange between the two column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kTile;
@@ -109,7 +112,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_init(&empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
@@ -189,20 +192,43 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       umma_commit(o_full);
     }
   } else if (warp >= 4) {
+    // ---------------------------------------------------------------- softmax: 8 warps, 2 threads per query row.
+    // warp -> TMEM lane quadrant (warp & 3) and key-column half ((warp-4)>>2): thread (row, half) owns columns
+    // [64*half, 64*half+64) of S, i.e. exactly one 64-wide swizzle atom of P.
     const int wq = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int row = wq * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
-    float m_ref = -INFINITY, l = 0.f;
+    const uint32_t tSh = tS + lane_base + half * 64;
+    uint8_t* atom = sP + half * kTileBytes;
+    float m_ref = -INFINITY, l = 0.f;  // m_ref is identical in both threads of a row; l is this thread's partial
 
-    // One sweep over this row of S: P = 2^(S*scale - m) -> bf16 -> swizzled smem.  Returns the row sum of P and
-    // (via t_max) the largest exponent seen, i.e. (row max of this tile) - m in the log2 domain.
+    auto bar_softmax = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    // CTA-wide OR over the 256 softmax threads (named barrier 2 with reduction)
+    auto any_softmax = [&](bool v) -> bool {
+      uint32_t r;
+      asm volatile(
+          "{\n"
+          ".reg .pred pin, pout;\n"
+          "setp.ne.u32 pin, %1, 0;\n"
+          "barrier.cta.red.or.pred pout, 2, 256, pin;\n"
+          "selp.u32 %0, 1, 0, pout;\n"
+          "}\n"
+          : "=r"(r)
+          : "r"(static_cast<uint32_t>(v))
+          : "memory");
+      return r != 0;
+    };
+
+    // One sweep over this thread's 64 columns of S: P = 2^(S*scale - m) -> bf16 -> swizzled smem.  Returns the
+    // partial row sum and (via t_max) the largest exponent seen.
     auto sweep = [&](float neg_m, int kv_valid, float& t_max) -> float {
-      const bool full_tile = kv_valid >= kTile;  // warp-uniform
+      const bool full_tile = kv_valid >= kTile;  // CTA-uniform
       float lsum = 0.f, tm = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t raw[32];
-        tmem_ld32(tS + lane_base + c * 32, raw);
+        tmem_ld32(tSh + c * 32, raw);
         tmem_ld_wait();
         uint32_t pk[16];
         if (full_tile) {
@@ -216,16 +242,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             pk[i] = pack_bf16_alu(e0, e1);
           }
         } else {
+          const int col0 = half * 64 + c * 32;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
             const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
             float e0 = 0.f, e1 = 0.f;
-            if (c * 32 + 2 * i < kv_valid) {
+            if (col0 + 2 * i < kv_valid) {
               tm = fmaxf(tm, t0);
               e0 = ex2(t0);
             }
-            if (c * 32 + 2 * i + 1 < kv_valid) {
+            if (col0 + 2 * i + 1 < kv_valid) {
               tm = fmaxf(tm, t1);
               e1 = ex2(t1);
             }
@@ -233,11 +260,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             pk[i] = pack_bf16_alu(e0, e1);
           }
         }
-        uint8_t* atom = sP + (c >> 1) * kTileBytes;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          st_shared_16(atom + sw128_off(row, (c & 1) * 4 + q), pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2],
-                       pk[q * 4 + 3]);
+          st_shared_16(atom + sw128_off(row, c * 4 + q), pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
       }
       t_max = tm;
       return lsum;
@@ -249,45 +274,53 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_after();
       float lsum, t_max;
       if (j == 0) {
-        // first tile: exact row max first (nothing to compare against yet)
+        // first tile: exact row max (each half scans its 64 columns, the two halves meet in smem)
         float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 4; c += 2) {
+        {
           uint32_t r0[32], r1[32];
-          tmem_ld32(tS + lane_base + c * 32, r0);
-          tmem_ld32(tS + lane_base + c * 32 + 32, r1);
+          tmem_ld32(tSh, r0);
+          tmem_ld32(tSh + 32, r1);
           tmem_ld_wait();
+          const int col0 = half * 64;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r0[i]));
-            if (c * 32 + 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r1[i]));
+            if (col0 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r0[i]));
+            if (col0 + 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r1[i]));
           }
         }
-        m_ref = mx * p.scale_log2;
+        s_xchg[half * kTile + row] = mx;
+        bar_softmax();
+        m_ref = fmaxf(s_xchg[row], s_xchg[kTile + row]) * p.scale_log2;
+        bar_softmax();  // s_xchg is reused below
         lsum = sweep(-m_ref, kv_valid, t_max);
       } else {
         // OPTIMISTIC single sweep against the running reference max.  Correct as long as no score of this tile
         // exceeds m_ref by more than 2^8 (P <= 256 is exact enough in bf16 and cannot overflow); otherwise the
-        // affected rows move their reference, O and l are rescaled, and the warp redoes the sweep.
+        // affected rows move their reference, O and l are rescaled, and the sweep is redone.
         lsum = sweep(-m_ref, kv_valid, t_max);
-        const bool need = t_max > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {
+        if (any_softmax(t_max > kRescaleThreshold)) {  // CTA-uniform
+          s_xchg[half * kTile + row] = t_max;
+          bar_softmax();
+          const float row_t = fmaxf(s_xchg[row], s_xchg[kTile + row]);
+          bar_softmax();
           float alpha = 1.0f;
-          if (need) {
-            alpha = ex2(-t_max);  // 2^(m_ref_old - m_ref_new)
-            m_ref += t_max;
+          if (row_t > kRescaleThreshold) {
+            alpha = ex2(-row_t);  // 2^(m_ref_old - m_ref_new)
+            m_ref += row_t;
             l *= alpha;
           }
+          if (half == 0) {  // warps 4-7 rescale their quadrant's 32 rows of O in TMEM
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {  // rescale this warp's 32 rows of O in TMEM
-            uint32_t raw[32];
-            tmem_ld32(tO + lane_base + c * 32, raw);
-            tmem_ld_wait();
+            for (int c = 0; c < 2; ++c) {
+              uint32_t raw[32];
+              tmem_ld32(tO + lane_base + c * 32, raw);
+              tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
-            tmem_st32(tO + lane_base + c * 32, raw);
+              for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+              tmem_st32(tO + lane_base + c * 32, raw);
+            }
+            tmem_st_wait();
           }
-          tmem_st_wait();
           lsum = sweep(-m_ref, kv_valid, t_max);
         }
       }
@@ -296,27 +329,26 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // ---- epilogue: O / l -> bf16 -> global
+    // ---- epilogue: O / l -> bf16 -> global; each thread of a row writes 32 of its 64 output columns
+    s_xchg[half * kTile + row] = l;
+    bar_softmax();
+    const float inv_l = 1.0f / (s_xchg[row] + s_xchg[kTile + row]);
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const float inv_l = 1.0f / l;
     const int q_row = q0 + row;
-    __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.Nq + q_row) * p.ldo + head * kHd;
+    __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.Nq + q_row) * p.ldo + head * kHd + half * 32;
+    uint32_t raw[32];
+    tmem_ld32(tO + lane_base + half * 32, raw);
+    tmem_ld_wait();
+    if (q_row < p.Nq) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t raw[32];
-      tmem_ld32(tO + lane_base + c * 32, raw);
-      tmem_ld_wait();
-      if (q_row < p.Nq) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(raw[q * 8 + 0]) * inv_l, __uint_as_float(raw[q * 8 + 1]) * inv_l);
-          u.y = pack_bf16(__uint_as_float(raw[q * 8 + 2]) * inv_l, __uint_as_float(raw[q * 8 + 3]) * inv_l);
-          u.z = pack_bf16(__uint_as_float(raw[q * 8 + 4]) * inv_l, __uint_as_float(raw[q * 8 + 5]) * inv_l);
-          u.w = pack_bf16(__uint_as_float(raw[q * 8 + 6]) * inv_l, __uint_as_float(raw[q * 8 + 7]) * inv_l);
-          reinterpret_cast<uint4*>(orow + c * 32)[q] = u;
-        }
+      for (int q = 0; q < 4; ++q) {
+        uint4 u;
+        u.x = pack_bf16(__uint_as_float(raw[q * 8 + 0]) * inv_l, __uint_as_float(raw[q * 8 + 1]) * inv_l);
+        u.y = pack_bf16(__uint_as_float(raw[q * 8 + 2]) * inv_l, __uint_as_float(raw[q * 8 + 3]) * inv_l);
+        u.z = pack_bf16(__uint_as_float(raw[q * 8 + 4]) * inv_l, __uint_as_float(raw[q * 8 + 5]) * inv_l);
+        u.w = pack_bf16(__uint_as_float(raw[q * 8 + 6]) * inv_l, __uint_as_float(raw[q * 8 + 7]) * inv_l);
+        reinterpret_cast<uint4*>(orow)[q] = u;
       }
     }
   }
@@ -329,7 +361,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-constexpr int kFlashSmemBytes = kTileBytes * (1 + 3 + 2) + 1024 + 128;
+constexpr int kFlashSmemBytes = kTileBytes * (1 + 3 + 2) + 1024 + 128 + 2 * kTile * 4;
 
 // =================================================================================================
 // (2) fused text + masked-IP cross-attention
@@ -595,7 +627,7 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
   p.v_col0 = v_col0;
   p.scale_log2 = scale * kLog2e;
   dim3 grid((Nq + kTile - 1) / kTile, heads, B);
-  flash_attn_kernel<<<grid, kAttnThreads, kFlashSmemBytes, st>>>(tmQ, tmK, tmV, p);
+  flash_attn_kernel<<<grid, kFlashThreads, kFlashSmemBytes, st>>>(tmQ, tmK, tmV, p);
   DS_LAUNCH_OK("flash_attn_kernel");
   return DS_OK;
 }

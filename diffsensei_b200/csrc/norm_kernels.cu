@@ -18,113 +18,128 @@
 namespace ds {
 
 
-// blockDim.x = cv * rpb  (cv = C/8 vectors per pixel, rpb pixels processed per sweep)
+// Work decomposition shared by both passes: the tensor is cut into ITEMS of `ipx` consecutive pixels of one sample
+// (item id = sample * items_per_sample + k); a launch has exactly one resident wave of CTAs (grid = SMs x
+// occupancy) and CTA c owns the contiguous item range [c*I/G, (c+1)*I/G) — so no tail wave, and a CTA touches at
+// most a couple of samples.  blockDim.x = cv * rpb (cv = C/8 16-byte vectors per pixel, rpb pixel rows per sweep);
+// every thread stays pinned to the same 8 channels.
+__device__ __forceinline__ void gn_item_range(int total_items, int& i0, int& i1) {
+  const long long g = gridDim.x, c = blockIdx.x;
+  i0 = static_cast<int>(c * total_items / g);
+  i1 = static_cast<int>((c + 1) * total_items / g);
+}
+
 __global__ void gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int HW, int C, int groups,
-                                int chunks_per_sample, int ppc) {
+                                int items_per_sample, int ipx, int total_items) {
   extern __shared__ double sh[];  // [2*groups]
   const int cv = C >> 3;
   const int rpb = blockDim.x / cv;
   const int cvec = threadIdx.x % cv;
   const int prow = threadIdx.x / cv;
-  const int b = blockIdx.x / chunks_per_sample;
-  const int chunk = blockIdx.x - b * chunks_per_sample;
-  const int p0 = chunk * ppc;
-  const int p1 = min(p0 + ppc, HW);
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sh[i] = 0.0;
-  __syncthreads();
+  const int cpg = C / groups;
+  int i0, i1;
+  gn_item_range(total_items, i0, i1);
+  if (i0 >= i1) return;
 
   float s[8], q[8];
+  auto reset = [&]() {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  const uint4* base = x + (static_cast<size_t>(b) * HW) * cv + cvec;
-  int p = p0 + prow;
-  // 8 independent 16-byte loads in flight per thread
-  for (; p + 7 * rpb < p1; p += 8 * rpb) {
-    uint4 u[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) u[k] = __ldg(base + static_cast<size_t>(p + k * rpb) * cv);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a = bf16_lo(w[j]), c = bf16_hi(w[j]);
-        s[2 * j] += a;
-        q[2 * j] = fmaf(a, a, q[2 * j]);
-        s[2 * j + 1] += c;
-        q[2 * j + 1] = fmaf(c, c, q[2 * j + 1]);
-      }
-    }
-  }
-  for (; p < p1; p += rpb) {
-    const uint4 u = __ldg(base + static_cast<size_t>(p) * cv);
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  };
+  auto accum = [&](const uint4& u) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float a = bf16_lo(w[j]), c = bf16_hi(w[j]);
       s[2 * j] += a;
-      q[2 * j] += a * a;
+      q[2 * j] = fmaf(a, a, q[2 * j]);
       s[2 * j + 1] += c;
-      q[2 * j + 1] += c * c;
+      q[2 * j + 1] = fmaf(c, c, q[2 * j + 1]);
     }
-  }
-  // fold this thread's 8 channels into their groups (runs of equal group id merged before the atomic)
-  const int cpg = C / groups;
-  const int c0 = cvec * 8;
-  int g_run = c0 / cpg;
-  double rs = 0.0, rq = 0.0;
+  };
+  // fold this thread's 8 channel partials into their groups (smem, fp64) and publish one atomic pair per group
+  auto flush = [&](int b) {
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    const int c0 = cvec * 8;
+    int g_run = c0 / cpg;
+    double rs = 0.0, rq = 0.0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int g = (c0 + j) / cpg;
-    if (g != g_run) {
-      atomicAdd(&sh[2 * g_run], rs);
-      atomicAdd(&sh[2 * g_run + 1], rq);
-      g_run = g;
-      rs = rq = 0.0;
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c0 + j) / cpg;
+      if (g != g_run) {
+        atomicAdd(&sh[2 * g_run], rs);
+        atomicAdd(&sh[2 * g_run + 1], rq);
+        g_run = g;
+        rs = rq = 0.0;
+      }
+      rs += static_cast<double>(s[j]);
+      rq += static_cast<double>(q[j]);
     }
-    rs += static_cast<double>(s[j]);
-    rq += static_cast<double>(q[j]);
+    atomicAdd(&sh[2 * g_run], rs);
+    atomicAdd(&sh[2 * g_run + 1], rq);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
+      atomicAdd(&stats[static_cast<size_t>(b) * 2 * groups + i], sh[i]);
+    __syncthreads();
+  };
+
+  reset();
+  int cur_b = i0 / items_per_sample;
+  for (int it = i0; it < i1; ++it) {
+    const int b = it / items_per_sample;
+    if (b != cur_b) {  // CTA-uniform
+      flush(cur_b);
+      reset();
+      cur_b = b;
+    }
+    const int p0 = (it - b * items_per_sample) * ipx;
+    const int p1 = min(p0 + ipx, HW);
+    const uint4* base = x + (static_cast<size_t>(b) * HW) * cv + cvec;
+    int p = p0 + prow;
+    for (; p + 7 * rpb < p1; p += 8 * rpb) {  // 8 independent 16-byte loads in flight per thread
+      uint4 u[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = __ldg(base + static_cast<size_t>(p + k * rpb) * cv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) accum(u[k]);
+    }
+    for (; p < p1; p += rpb) accum(__ldg(base + static_cast<size_t>(p) * cv));
   }
-  atomicAdd(&sh[2 * g_run], rs);
-  atomicAdd(&sh[2 * g_run + 1], rq);
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
-    atomicAdd(&stats[static_cast<size_t>(b) * 2 * groups + i], sh[i]);
+  flush(cur_b);
 }
 
 template <bool kSilu>
 __global__ void gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
-                                int groups, float eps, int chunks_per_sample, int ppc) {
+                                int groups, float eps, int items_per_sample, int ipx, int total_items) {
   const int cv = C >> 3;
   const int rpb = blockDim.x / cv;
   const int cvec = threadIdx.x % cv;
   const int prow = threadIdx.x / cv;
-  // reverse chunk order: the most recently streamed part of x is the most likely to still be in L2
-  const int rb = gridDim.x - 1 - blockIdx.x;
-  const int b = rb / chunks_per_sample;
-  const int chunk = rb - b * chunks_per_sample;
-  const int p0 = chunk * ppc;
-  const int p1 = min(p0 + ppc, HW);
-
   const int cpg = C / groups;
   const double inv_n = 1.0 / (static_cast<double>(HW) * cpg);
-  float sc[8], sf[8];
+  int i0, i1;
+  gn_item_range(total_items, i0, i1);
+  if (i0 >= i1) return;
+  float ga[8], be[8], sc[8], sf[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int c = cvec * 8 + j;
-    const int g = c / cpg;
-    const double mean = stats[static_cast<size_t>(b) * 2 * groups + 2 * g] * inv_n;
-    double var = stats[static_cast<size_t>(b) * 2 * groups + 2 * g + 1] * inv_n - mean * mean;
-    var = var < 0.0 ? 0.0 : var;
-    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float ga = __ldg(gamma + c), be = __ldg(beta + c);
-    sc[j] = rstd * ga;
-    sf[j] = be - static_cast<float>(mean) * rstd * ga;
+    ga[j] = __ldg(gamma + cvec * 8 + j);
+    be[j] = __ldg(beta + cvec * 8 + j);
   }
-  const size_t off = (static_cast<size_t>(b) * HW) * cv + cvec;
-  const uint4* xb = x + off;
-  uint4* yb = y + off;
+  auto load_coeffs = [&](int b) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (cvec * 8 + j) / cpg;
+      const double mean = stats[static_cast<size_t>(b) * 2 * groups + 2 * g] * inv_n;
+      double var = stats[static_cast<size_t>(b) * 2 * groups + 2 * g + 1] * inv_n - mean * mean;
+      var = var < 0.0 ? 0.0 : var;
+      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      sc[j] = rstd * ga[j];
+      sf[j] = be[j] - static_cast<float>(mean) * rstd * ga[j];
+    }
+  };
   auto norm8 = [&](const uint4& u) -> uint4 {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     uint32_t o[4];
@@ -140,15 +155,30 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__
     }
     return make_uint4(o[0], o[1], o[2], o[3]);
   };
-  int p = p0 + prow;
-  for (; p + 3 * rpb < p1; p += 4 * rpb) {
-    uint4 u[4];
+  int cur_b = -1;
+  // walk this CTA's range backwards: the stats pass streamed it forwards, so its tail is the most likely part of
+  // x to still sit in the 126 MB L2
+  for (int it = i1 - 1; it >= i0; --it) {
+    const int b = it / items_per_sample;
+    if (b != cur_b) {
+      load_coeffs(b);
+      cur_b = b;
+    }
+    const int p0 = (it - b * items_per_sample) * ipx;
+    const int p1 = min(p0 + ipx, HW);
+    const size_t off = (static_cast<size_t>(b) * HW) * cv + cvec;
+    const uint4* xb = x + off;
+    uint4* yb = y + off;
+    int p = p0 + prow;
+    for (; p + 3 * rpb < p1; p += 4 * rpb) {
+      uint4 u[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = __ldg(xb + static_cast<size_t>(p + k * rpb) * cv);
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(xb + static_cast<size_t>(p + k * rpb) * cv);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) yb[static_cast<size_t>(p + k * rpb) * cv] = norm8(u[k]);
+      for (int k = 0; k < 4; ++k) yb[static_cast<size_t>(p + k * rpb) * cv] = norm8(u[k]);
+    }
+    for (; p < p1; p += rpb) yb[static_cast<size_t>(p) * cv] = norm8(__ldg(xb + static_cast<size_t>(p) * cv));
   }
-  for (; p < p1; p += rpb) yb[static_cast<size_t>(p) * cv] = norm8(__ldg(xb + static_cast<size_t>(p) * cv));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -234,22 +264,35 @@ extern "C" int ds_groupnorm_silu(const void* x, void* y, const float* gamma, con
   if (rpb < 1) rpb = 1;
   const int threads = cv * rpb;
   DS_REQUIRE(threads <= 1024, "ds_groupnorm_silu: C too large for one CTA row");
-  // pixels per CTA: aim at ~8 CTAs per SM over the whole tensor, a multiple of 8 sweeps of the CTA's pixel rows
-  long long ppc = (static_cast<long long>(B) * HW + dev.num_sms * 8 - 1) / (dev.num_sms * 8);
-  if (ppc < 8 * rpb) ppc = 8 * rpb;
-  ppc = ((ppc + 8 * rpb - 1) / (8 * rpb)) * (8 * rpb);
-  const int chunks = static_cast<int>((HW + ppc - 1) / ppc);
+  // items of 8 sweeps of the CTA's pixel rows; one resident wave of CTAs (occupancy queried once per kernel)
+  const int ipx = 8 * rpb;
+  const int items_per_sample = (HW + ipx - 1) / ipx;
+  const long long total_items_ll = static_cast<long long>(B) * items_per_sample;
+  DS_REQUIRE(total_items_ll < (1ll << 30), "ds_groupnorm_silu: tensor too large");
+  const int total_items = static_cast<int>(total_items_ll);
+  auto wave = [&](const void* fn, size_t smem) -> int {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem) != cudaSuccess || occ < 1) {
+      (void)cudaGetLastError();
+      occ = 1;
+    }
+    const long long g = static_cast<long long>(occ) * dev.num_sms;
+    return static_cast<int>(g < total_items ? g : total_items);
+  };
   double* dstats = reinterpret_cast<double*>(stats);
   DS_CUDA_OK(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * B * groups, st));
-  gn_stats_kernel<<<B * chunks, threads, sizeof(double) * 2 * groups, st>>>(static_cast<const uint4*>(x), dstats, HW,
-                                                                            C, groups, chunks, (int)ppc);
+  const size_t sh = sizeof(double) * 2 * groups;
+  gn_stats_kernel<<<wave(reinterpret_cast<const void*>(gn_stats_kernel), sh), threads, sh, st>>>(
+      static_cast<const uint4*>(x), dstats, HW, C, groups, items_per_sample, ipx, total_items);
   DS_LAUNCH_OK("gn_stats_kernel");
   if (apply_silu)
-    gn_apply_kernel<true><<<B * chunks, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), dstats,
-                                                          gamma, beta, HW, C, groups, eps, chunks, (int)ppc);
+    gn_apply_kernel<true><<<wave(reinterpret_cast<const void*>(gn_apply_kernel<true>), 0), threads, 0, st>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(y), dstats, gamma, beta, HW, C, groups, eps,
+        items_per_sample, ipx, total_items);
   else
-    gn_apply_kernel<false><<<B * chunks, threads, 0, st>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y),
-                                                           dstats, gamma, beta, HW, C, groups, eps, chunks, (int)ppc);
+    gn_apply_kernel<false><<<wave(reinterpret_cast<const void*>(gn_apply_kernel<false>), 0), threads, 0, st>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(y), dstats, gamma, beta, HW, C, groups, eps,
+        items_per_sample, ipx, total_items);
   DS_LAUNCH_OK("gn_apply_kernel");
   return DS_OK;
 }
