@@ -22,6 +22,8 @@
 //     TMEM accumulators (O_ip re-uses the dead S columns), and 1/l_text, scale/l_ip applied in the epilogue.
 //     The additive bbox mask M in {0,-10000} (:115-169) is evaluated in registers from the 4 boxes with the
 //     reference's closed-interval / derived-(H',W') semantics (ip_mask.cuh) and never touches memory.
+#include <cstdlib>
+
 #include "ds_common.cuh"
 #include "ds_host.h"
 #include "ip_mask.cuh"
@@ -364,6 +366,286 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 constexpr int kFlashSmemBytes = kTileBytes * (1 + 3 + 2) + 1024 + 128 + 2 * kTile * 4;
 
 // =================================================================================================
+// (1b) flash attention v3 — same contract as flash_attn_kernel, restructured around the two resources that bound
+//      head_dim 64 on sm_100a: the MUFU (exp2) pipe and the 128 B/clk shared-memory port.
+//        * P never touches shared memory: it is written to TMEM (tcgen05.st, bf16x2-packed, 64 columns) and the
+//          O += P V MMA takes its A operand from TMEM (tcgen05.mma "ts" form).  Per kv tile that removes 32 KB of
+//          st.shared, the fence.proxy.async, and 32 KB of tensor-core operand reads from the smem port.
+//        * one thread per query row (4 softmax warps): the rescale decision is thread-local, warp-uniform by a vote,
+//          no CTA barrier on the per-tile path.
+//        * no per-element running max: exponentials are taken against the row's reference max m_ref; because every
+//          term is >= 0, the row sum of the tile bounds its largest term, so "sum < 2^10" proves no score exceeded
+//          m_ref by more than 10 (log2).  Otherwise (rare) the warp takes the exact-max path, moves m_ref, rescales
+//          O in TMEM and redoes the tile.
+//        * TMEM loads of S are software-pipelined one 32-column chunk ahead of the exp2 work.
+//      TMEM (256 columns, 2 CTAs/SM): S [0,128) fp32 | O [128,192) fp32 | P [192,256) bf16x2.
+// =================================================================================================
+constexpr int kFlash3Threads = 256;  // 4 control warps + 4 softmax warps
+constexpr int kFlash3Ring = 4;
+constexpr int kFlash3SmemBytes = kTileBytes * (1 + kFlash3Ring) + 1024 + 256;
+constexpr float kSumOverflow = 1024.0f;  // 2^10
+
+// Degree-3 minimax 2^f on f in [-0.5, 0.5] after Cody-Waite range reduction, all on the FMA/ALU pipes (FA4-style
+// MUFU offload).  Max rel. error 7.5e-5 — far below the bf16 rounding (2^-9) applied to P right after.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float r = x + 12582912.0f;            // 1.5 * 2^23: integer part lands in the low mantissa bits
+  const float fi = r - 12582912.0f;
+  const float f = x - fi;                     // [-0.5, 0.5]
+  float p = fmaf(f, 0.05517132f, 0.24261054f);  // minimax (Lawson) fit, max rel. err 7.5e-5
+  p = fmaf(p, f, 0.69326099f);
+  p = fmaf(p, f, 0.99992811f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(r) << 23));
+}
+
+template <int POLY>  // POLY of every 8 exponentials go to the FMA pipe instead of the MUFU
+__global__ void __launch_bounds__(kFlash3Threads, 2)
+flash_attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
+  constexpr int RING = kFlash3Ring;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sRing = sQ + kTileBytes;  // RING x 16 KiB: K_0 V_0 K_1 V_1 ...
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + RING * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* full = bars + 1;      // [RING]
+  uint64_t* empty = full + RING;  // [RING]
+  uint64_t* s_full = empty + RING;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTile;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int num_kv_tiles = (p.Nkv + kTile - 1) / kTile;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < RING; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);  // one arrival per softmax warp
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;        // columns [0,128)   fp32 scores
+  const uint32_t tO = tmem_base + 128;  // columns [128,192) fp32 output accumulator
+  const uint32_t tP = tmem_base + 192;  // columns [192,256) bf16x2 probabilities (A operand of the PV MMA)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTileBytes);
+      tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + head * kHd, q0, batch);
+      for (int idx = 0; idx < 2 * num_kv_tiles; ++idx) {  // K_0 V_0 K_1 V_1 ...
+        const int slot = idx % RING;
+        const uint32_t ph = (idx / RING) & 1;
+        const int j = idx >> 1, which = idx & 1;
+        mbar_wait(&empty[slot], ph ^ 1);
+        mbar_arrive_expect_tx(&full[slot], kTileBytes);
+        tma_load_3d(sRing + slot * kTileBytes, which == 0 ? &tmK : &tmV, &full[slot],
+                    (which == 0 ? p.k_col0 : p.v_col0) + head * kHd, j * kTile, batch);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(kTile, kTile, 0, 0);  // M128 N128, both K-major
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);    // M128 N64, A from TMEM, B (=V) MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_s = [&](int j) {  // S = Q K_j^T, then free K_j's slot and publish S
+        const int idx = 2 * j, slot = idx % RING;
+        mbar_wait(&full[slot], (idx / RING) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sRing + slot * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k)
+          umma_ss(tS, make_sw128_desc(q_addr + k * 32, 1024, 16), make_sw128_desc(k_addr + k * 32, 1024, 16),
+                  idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&empty[slot]);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < num_kv_tiles; ++j) {
+        const int idx = 2 * j + 1, slot = idx % RING;
+        mbar_wait(&full[slot], (idx / RING) & 1);  // V_j landed
+        mbar_wait(p_full, j & 1);                  // P_j is in TMEM (and S_j has been read)
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sRing + slot * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k)  // K = 16 bf16 = 8 packed TMEM columns of P per MMA
+          umma_ts(tO, tP + k * 8, make_sw128_desc(v_addr + k * 2048, 1024, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
+        umma_commit(&empty[slot]);
+        if (j + 1 < num_kv_tiles) issue_s(j + 1);  // its commit also covers PV_j: s_full(j+1) => O and P are quiescent
+      }
+      umma_commit(o_full);
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- softmax: 4 warps, thread <-> query row
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tSr = tS + lane_base, tOr = tO + lane_base, tPr = tP + lane_base;
+    float m_ref = -INFINITY, l = 0.f;
+
+    // 32 scores -> 16 packed bf16x2 probabilities; partial sums into s0/s1
+    auto chunk = [&](const uint32_t(&raw)[32], uint32_t(&pk)[16], float neg_m, int valid, float& s0, float& s1) {
+      if (valid >= 32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
+          const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
+          const float e0 = ((2 * i) % 8 < POLY) ? ex2_poly(t0) : ex2(t0);
+          const float e1 = ((2 * i + 1) % 8 < POLY) ? ex2_poly(t1) : ex2(t1);
+          s0 += e0;
+          s1 += e1;
+          pk[i] = pack_bf16_alu(e0, e1);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
+          const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
+          const float e0 = (2 * i < valid) ? ex2(t0) : 0.f;
+          const float e1 = (2 * i + 1 < valid) ? ex2(t1) : 0.f;
+          s0 += e0;
+          s1 += e1;
+          pk[i] = pack_bf16_alu(e0, e1);
+        }
+      }
+    };
+    // one pass over the row's 128 scores: P -> TMEM, returns the row sum of the tile
+    auto sweep = [&](float neg_m, int kv_valid) -> float {
+      float s0 = 0.f, s1 = 0.f;
+      uint32_t ra[32], rb[32], pk[16];
+      tmem_ld32(tSr, ra);
+      tmem_ld_wait();
+      tmem_ld32(tSr + 32, rb);
+      chunk(ra, pk, neg_m, kv_valid, s0, s1);
+      tmem_st16(tPr, pk);
+      tmem_ld_wait();
+      tmem_ld32(tSr + 64, ra);
+      chunk(rb, pk, neg_m, kv_valid - 32, s0, s1);
+      tmem_st16(tPr + 16, pk);
+      tmem_ld_wait();
+      tmem_ld32(tSr + 96, rb);
+      chunk(ra, pk, neg_m, kv_valid - 64, s0, s1);
+      tmem_st16(tPr + 32, pk);
+      tmem_ld_wait();
+      chunk(rb, pk, neg_m, kv_valid - 96, s0, s1);
+      tmem_st16(tPr + 48, pk);
+      return s0 + s1;
+    };
+    // exact maximum of the row's valid scores (raw, unscaled)
+    auto row_max = [&](int kv_valid) -> float {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tSr + c * 32, raw);
+        tmem_ld_wait();
+        if (kv_valid >= (c + 1) * 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+        }
+      }
+      return mx;
+    };
+
+    for (int j = 0; j < num_kv_tiles; ++j) {
+      const int kv_valid = p.Nkv - j * kTile;  // >= 128: whole tile valid
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      float lsum;
+      if (j == 0) {
+        m_ref = row_max(kv_valid) * p.scale_log2;
+        lsum = sweep(-m_ref, kv_valid);
+      } else {
+        lsum = sweep(-m_ref, kv_valid);
+        if (__any_sync(0xffffffffu, !(lsum < kSumOverflow))) {  // warp-uniform, rare
+          const float t_new = row_max(kv_valid) * p.scale_log2;
+          float alpha = 1.0f;
+          if (t_new > m_ref) {
+            alpha = ex2(m_ref - t_new);
+            m_ref = t_new;
+            l *= alpha;
+          }
+          tmem_st_wait();  // the aborted P stores must not be overtaken
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {  // rescale this warp's 32 rows of O (quiescent: s_full(j) covers PV_{j-1})
+            uint32_t raw[32];
+            tmem_ld32(tOr + c * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+            tmem_st32(tOr + c * 32, raw);
+          }
+          lsum = sweep(-m_ref, kv_valid);
+        }
+      }
+      l += lsum;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> bf16 -> global (one 128-byte row segment per thread)
+    const float inv_l = 1.0f / l;
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int q_row = q0 + row;
+    __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.Nq + q_row) * p.ldo + head * kHd;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tOr + c * 32, raw);
+      tmem_ld_wait();
+      if (q_row < p.Nq) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(raw[q * 8 + 0]) * inv_l, __uint_as_float(raw[q * 8 + 1]) * inv_l);
+          u.y = pack_bf16(__uint_as_float(raw[q * 8 + 2]) * inv_l, __uint_as_float(raw[q * 8 + 3]) * inv_l);
+          u.z = pack_bf16(__uint_as_float(raw[q * 8 + 4]) * inv_l, __uint_as_float(raw[q * 8 + 5]) * inv_l);
+          u.w = pack_bf16(__uint_as_float(raw[q * 8 + 6]) * inv_l, __uint_as_float(raw[q * 8 + 7]) * inv_l);
+          reinterpret_cast<uint4*>(orow + c * 32)[q] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// =================================================================================================
 // (2) fused text + masked-IP cross-attention
 // =================================================================================================
 struct CrossParams {
@@ -593,6 +875,308 @@ cross_ip_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+// =================================================================================================
+// (2b) cross_ip_attn_v2_kernel — same arithmetic as cross_ip_attn_kernel, restructured because the one-tile-per-CTA
+//      version was latency-bound (one serial load -> S -> softmax -> PV -> store chain per CTA lifetime; 4-7x off its
+//      HBM floor, profiles/r01_ncu_summary.md):
+//        * persistent: 2 CTAs per SM, CTA c owns a contiguous range of (batch, head, q-tile) items, so K|V of a
+//          (batch, head) are loaded once per ~8 tiles and the next tile's Q is prefetched through a 2-slot ring
+//          while the current tile is in its softmax;
+//        * P goes registers -> TMEM (bf16x2, aliasing the dead head of the S columns: the thread that read row r's
+//          scores is the only writer of row r's probabilities) and feeds the PV MMAs as a TMEM A operand — no
+//          st.shared / fence.proxy.async / 48 KB P staging buffer;
+//        * one thread per query row, TMEM loads software-pipelined one 16-column chunk ahead.
+//      TMEM (256 columns): S [0,192) fp32 | P [0,96) bf16x2 (alias) | O_text [96,160) (alias) | O_ip [192,256).
+// =================================================================================================
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKVt,
+                        const __grid_constant__ CUtensorMap tmKVip, const CrossParams p, int heads, int q_tiles,
+                        int total_items) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int n_keys = p.nt_pad + p.nip_pad;  // multiple of 16, <= 192
+  const int kv_bytes = n_keys * 128;        // [n_keys][64] bf16
+  const int kv_stride = (kv_bytes + 1023) & ~1023;
+  uint8_t* sQ = smem;                       // 2 x 16 KiB ring
+  uint8_t* sK = sQ + 2 * kTileBytes;
+  uint8_t* sV = sK + kv_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kv_stride);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* kv_full = bars + 4;
+  uint64_t* kv_empty = bars + 5;
+  uint64_t* s_full = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint64_t* o_empty = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = static_cast<int>(static_cast<long long>(blockIdx.x) * total_items / gridDim.x);
+  const int i1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total_items / gridDim.x);
+  const int n_items = i1 - i0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKVt);
+    tma_prefetch_desc(&tmKVip);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;          // [0, n_keys) scores
+  const uint32_t tP = tmem_base;          // [0, n_keys/2) packed probabilities (alias)
+  const uint32_t tOt = tmem_base + 96;    // [96,160) text output (alias of dead score columns)
+  const uint32_t tOi = tmem_base + 192;   // [192,256) IP output
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int cur_bh = -1, kv_loads = 0;
+      for (int n = 0; n < n_items; ++n) {
+        const int item = i0 + n;
+        const int qt = item % q_tiles, bh = item / q_tiles;
+        const int head = bh % heads, batch = bh / heads;
+        if (bh != cur_bh) {
+          if (kv_loads > 0) mbar_wait(kv_empty, (kv_loads - 1) & 1);  // every MMA on the old K|V has completed
+          mbar_arrive_expect_tx(kv_full, 2 * kv_bytes);
+          tma_load_3d(sK, &tmKVt, kv_full, head * kHd, 0, batch);
+          tma_load_3d(sK + p.nt_pad * 128, &tmKVip, kv_full, head * kHd, 0, batch);
+          tma_load_3d(sV, &tmKVt, kv_full, p.C + head * kHd, 0, batch);
+          tma_load_3d(sV + p.nt_pad * 128, &tmKVip, kv_full, p.C + head * kHd, 0, batch);
+          ++kv_loads;
+          cur_bh = bh;
+        }
+        const int slot = n & 1;
+        mbar_wait(&q_empty[slot], ((n >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[slot], kTileBytes);
+        tma_load_3d(sQ + slot * kTileBytes, &tmQ, &q_full[slot], head * kHd, qt * kTile, batch);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc_bf16(kTile, n_keys, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const int kt = p.nt_pad / 16;
+      int cur_bh = -1, kv_uses = 0;
+      for (int n = 0; n < n_items; ++n) {
+        const int item = i0 + n;
+        const int bh = item / q_tiles;
+        if (bh != cur_bh) {
+          mbar_wait(kv_full, kv_uses & 1);
+          ++kv_uses;
+          cur_bh = bh;
+        }
+        const int slot = n & 1;
+        mbar_wait(&q_full[slot], (n >> 1) & 1);
+        if (n > 0) mbar_wait(o_empty, (n - 1) & 1);  // the previous tile's outputs (aliasing S) have been read
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ + slot * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k)
+          umma_ss(tS, make_sw128_desc(q_addr + k * 32, 1024, 16), make_sw128_desc(k_addr + k * 32, 1024, 16), idesc_qk,
+                  k != 0 ? 1u : 0u);
+        umma_commit(&q_empty[slot]);
+        umma_commit(s_full);
+        mbar_wait(p_full, n & 1);
+        tc_fence_after();
+        for (int k = 0; k < n_keys / 16; ++k) {
+          const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048, 1024, 1024);
+          if (k < kt)
+            umma_ts(tOt, tP + k * 8, bdesc, idesc_pv, k != 0 ? 1u : 0u);
+          else
+            umma_ts(tOi, tP + k * 8, bdesc, idesc_pv, k != kt ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        if (n + 1 < n_items && (item + 1) / q_tiles != bh) umma_commit(kv_empty);
+      }
+    }
+  } else if (warp >= 4) {
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tSr = tS + lane_base, tPr = tP + lane_base;
+    constexpr float kS2 = 0.125f * kLog2e;
+    constexpr float kMask2 = -10000.0f * kLog2e;
+    const int chunks = n_keys / 16;
+    const int t_chunks = p.nt_pad / 16;
+    const bool uniform = (p.tokens_per_ip % 16 == 0) && (p.num_dummy % 16 == 0);
+
+    for (int n = 0; n < n_items; ++n) {
+      const int item = i0 + n;
+      const int qt = item % q_tiles, bh = item / q_tiles;
+      const int head = bh % heads, batch = bh / heads;
+      const int q_row = qt * kTile + row;
+      const uint32_t bits = ip_inside_bits(p.bbox + static_cast<size_t>(batch) * p.num_ips * 4, p.num_ips,
+                                           min(q_row, p.N - 1), p.Hd, p.Wd);
+      auto chunk_valid = [&](int c) -> int {
+        const int v = (c < t_chunks) ? p.n_text - c * 16 : p.n_ip - (c - t_chunks) * 16;
+        return v < 0 ? 0 : (v > 16 ? 16 : v);
+      };
+      auto chunk_add = [&](int c) -> float {  // only meaningful when `uniform`
+        if (c < t_chunks) return 0.0f;
+        return ip_key_open(bits, (c - t_chunks) * 16, p.tokens_per_ip, p.num_dummy) ? 0.0f : kMask2;
+      };
+      auto elem_add = [&](int c, int i) -> float {  // general path
+        if (c < t_chunks) return 0.0f;
+        return ip_key_open(bits, (c - t_chunks) * 16 + i, p.tokens_per_ip, p.num_dummy) ? 0.0f : kMask2;
+      };
+
+      mbar_wait(s_full, n & 1);
+      tc_fence_after();
+      // ---- pass 1: the two row maxima (log2 domain)
+      float m_t = -INFINITY, m_i = -INFINITY;
+      auto max_chunk = [&](int c, const uint32_t(&raw)[16]) {
+        const int nv = chunk_valid(c);
+        float mx = -INFINITY;
+        if (uniform && nv == 16) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+          mx = fmaf(mx, kS2, chunk_add(c));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (i < nv) mx = fmaxf(mx, fmaf(__uint_as_float(raw[i]), kS2, uniform ? chunk_add(c) : elem_add(c, i)));
+        }
+        if (c < t_chunks)
+          m_t = fmaxf(m_t, mx);
+        else
+          m_i = fmaxf(m_i, mx);
+      };
+      // ---- pass 2: unnormalised P = 2^(t - m) -> bf16x2 -> TMEM; row sums
+      float l_t = 0.f, l_i = 0.f;
+      auto exp_chunk = [&](int c, const uint32_t(&raw)[16]) {
+        const int nv = chunk_valid(c);
+        const float m = c < t_chunks ? m_t : m_i;
+        uint32_t pk[8];
+        float s0 = 0.f, s1 = 0.f;
+        if (uniform && nv == 16) {
+          const float off = chunk_add(c) - m;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), kS2, off));
+            const float e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), kS2, off));
+            s0 += e0;
+            s1 += e1;
+            pk[i] = pack_bf16_alu(e0, e1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float e0 = 0.f, e1 = 0.f;
+            if (2 * i < nv)
+              e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), kS2, (uniform ? chunk_add(c) : elem_add(c, 2 * i)) - m));
+            if (2 * i + 1 < nv)
+              e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), kS2, (uniform ? chunk_add(c) : elem_add(c, 2 * i + 1)) - m));
+            s0 += e0;
+            s1 += e1;
+            pk[i] = pack_bf16_alu(e0, e1);
+          }
+        }
+        if (c < t_chunks)
+          l_t += s0 + s1;
+        else
+          l_i += s0 + s1;
+        tmem_st8(tPr + c * 8, pk);  // columns [8c, 8c+8) <= the chunk just read: never ahead of an unread score
+      };
+      {
+        uint32_t ra[16], rb[16];
+        tmem_ld16(tSr, ra);
+        tmem_ld_wait();
+        for (int c = 0; c < chunks; c += 2) {
+          if (c + 1 < chunks) tmem_ld16(tSr + (c + 1) * 16, rb);
+          max_chunk(c, ra);
+          tmem_ld_wait();
+          if (c + 1 < chunks) {
+            if (c + 2 < chunks) tmem_ld16(tSr + (c + 2) * 16, ra);
+            max_chunk(c + 1, rb);
+            tmem_ld_wait();
+          }
+        }
+        tmem_ld16(tSr, ra);
+        tmem_ld_wait();
+        for (int c = 0; c < chunks; c += 2) {
+          if (c + 1 < chunks) tmem_ld16(tSr + (c + 1) * 16, rb);
+          exp_chunk(c, ra);
+          tmem_ld_wait();
+          if (c + 1 < chunks) {
+            if (c + 2 < chunks) tmem_ld16(tSr + (c + 2) * 16, ra);
+            exp_chunk(c + 1, rb);
+            tmem_ld_wait();
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+
+      // ---- epilogue: out = O_text / l_t + scale * O_ip / l_i      (blend BEFORE to_out, reference :258)
+      const float w_t = 1.0f / l_t, w_i = p.ip_scale / l_i;
+      mbar_wait(o_full, n & 1);
+      tc_fence_after();
+      __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.N + q_row) * p.C + head * kHd;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t rt[32], ri[32];
+        tmem_ld32(tOt + lane_base + c * 32, rt);
+        tmem_ld32(tOi + lane_base + c * 32, ri);
+        tmem_ld_wait();
+        if (q_row < p.N) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              o[e] = fmaf(__uint_as_float(rt[q * 8 + e]), w_t, __uint_as_float(ri[q * 8 + e]) * w_i);
+            uint4 u;
+            u.x = pack_bf16(o[0], o[1]);
+            u.y = pack_bf16(o[2], o[3]);
+            u.z = pack_bf16(o[4], o[5]);
+            u.w = pack_bf16(o[6], o[7]);
+            reinterpret_cast<uint4*>(orow + c * 32)[q] = u;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -627,8 +1211,36 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
   p.v_col0 = v_col0;
   p.scale_log2 = scale * kLog2e;
   dim3 grid((Nq + kTile - 1) / kTile, heads, B);
-  flash_attn_kernel<<<grid, kFlashThreads, kFlashSmemBytes, st>>>(tmQ, tmK, tmV, p);
-  DS_LAUNCH_OK("flash_attn_kernel");
+  // DS_FLASH=2 selects the round-1 kernel (P through shared memory, 2 threads per row) for A/B timing;
+  // DS_FLASH_POLY=n sends n of every 8 exponentials to the FMA pipe (v3 only)
+  static const int flash_ver = [] {
+    const char* e = getenv("DS_FLASH");
+    return e ? atoi(e) : 3;
+  }();
+  static const int flash_poly = [] {
+    const char* e = getenv("DS_FLASH_POLY");
+    return e ? atoi(e) : 0;
+  }();
+  if (flash_ver == 2) {
+    flash_attn_kernel<<<grid, kFlashThreads, kFlashSmemBytes, st>>>(tmQ, tmK, tmV, p);
+    DS_LAUNCH_OK("flash_attn_kernel");
+    return DS_OK;
+  }
+  static bool attr3_set = false;
+  if (!attr3_set) {
+    DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
+    DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
+    DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
+    DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
+    attr3_set = true;
+  }
+  switch (flash_poly) {
+    case 1: flash_attn_v3_kernel<1><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
+    case 2: flash_attn_v3_kernel<2><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
+    case 3: flash_attn_v3_kernel<3><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
+    default: flash_attn_v3_kernel<0><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
+  }
+  DS_LAUNCH_OK("flash_attn_v3_kernel");
   return DS_OK;
 }
 
@@ -706,6 +1318,28 @@ extern "C" int ds_attention_cross_ip(const ds_cross_ip_args* a, void* stream) {
   p.Hd = Hd;
   p.Wd = Wd;
   p.ip_scale = a->ip_scale;
+  // DS_CROSS=1 selects the round-1 one-tile-per-CTA kernel (A/B timing); default: persistent v2
+  static const int cross_ver = [] {
+    const char* e = getenv("DS_CROSS");
+    return e ? atoi(e) : 2;
+  }();
+  if (cross_ver != 1) {
+    const int q_tiles = (a->N + kTile - 1) / kTile;
+    const long long total_ll = static_cast<long long>(a->B) * a->heads * q_tiles;
+    DS_REQUIRE(total_ll < (1ll << 30), "ds_attention_cross_ip: too many tiles");
+    const int total = static_cast<int>(total_ll);
+    const int smem2 = 2 * kTileBytes + 2 * kv_bytes + 1024 + 128;
+    static int attr_smem2 = 0;
+    if (smem2 > attr_smem2) {
+      DS_CUDA_OK(cudaFuncSetAttribute(cross_ip_attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      attr_smem2 = smem2;
+    }
+    const int grid2 = total < 2 * dev.num_sms ? total : 2 * dev.num_sms;
+    cross_ip_attn_v2_kernel<<<grid2, kAttnThreads, smem2, static_cast<cudaStream_t>(stream)>>>(tmQ, tmT, tmI, p, a->heads,
+                                                                                            q_tiles, total);
+    DS_LAUNCH_OK("cross_ip_attn_v2_kernel");
+    return DS_OK;
+  }
   dim3 grid((a->N + kTile - 1) / kTile, a->heads, a->B);
   cross_ip_attn_kernel<<<grid, kAttnThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmT, tmI, p);
   DS_LAUNCH_OK("cross_ip_attn_kernel");

@@ -528,6 +528,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 static int pick_bn(int N, int epilogue) {
   if (epilogue == DS_EPI_GEGLU) return 256;
   if (N <= 128) return 128;
+  static const int bn_env = [] {  // DS_GEMM_BN=128|256 forces the tile width (A/B timing); default: heuristic below
+    const char* e = getenv("DS_GEMM_BN");
+    return e ? atoi(e) : 0;
+  }();
+  if (bn_env == 128 || bn_env == 256) return bn_env;
   // BN=256 tiles run the tensor pipe ~1.3-1.5x faster per FLOP than BN=128 ones (smem operand traffic, see GemmCfg),
   // so they win unless more than ~20 % of the last N tile would be padding (N=640 -> 3 x 256 is still better)
   const double e256 = static_cast<double>(N) / (((N + 255) / 256) * 256);

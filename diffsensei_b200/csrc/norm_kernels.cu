@@ -12,11 +12,38 @@
 // Replaces diffusers ResnetBlock2D.norm1/norm2+SiLU, Transformer2DModel.norm, conv_norm_out+conv_act
 // (reached from src/models/unet.py:251-261,281-290,316-338) and BasicTransformerBlock / Resampler LayerNorms
 // (src/models/resampler.py:14,40-41,104).
+#include <cstdlib>
+
 #include "ds_common.cuh"
 #include "ds_host.h"
 
 namespace ds {
 
+// L2 residency control for the two-pass GroupNorm: the stats pass marks x evict_last so that the apply pass
+// re-reads it from the 126 MB L2 instead of HBM (x of the largest cfg2 tensor is 84 MB); the apply pass reads x
+// evict_first (dead after this read) so the y write stream displaces x's consumed lines first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ldg_hint(const uint4* ptr, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
 
 // Work decomposition shared by both passes: the tensor is cut into ITEMS of `ipx` consecutive pixels of one sample
 // (item id = sample * items_per_sample + k); a launch has exactly one resident wave of CTAs (grid = SMs x
@@ -30,7 +57,7 @@ __device__ __forceinline__ void gn_item_range(int total_items, int& i0, int& i1)
 }
 
 __global__ void gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int HW, int C, int groups,
-                                int items_per_sample, int ipx, int total_items) {
+                                int items_per_sample, int ipx, int total_items, int l2_hints) {
   extern __shared__ double sh[];  // [2*groups]
   const int cv = C >> 3;
   const int rpb = blockDim.x / cv;
@@ -85,6 +112,7 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x, double* __restrict_
   };
 
   reset();
+  const uint64_t pol = l2_hints ? l2_policy_evict_last() : l2_policy_normal();
   int cur_b = i0 / items_per_sample;
   for (int it = i0; it < i1; ++it) {
     const int b = it / items_per_sample;
@@ -100,11 +128,11 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x, double* __restrict_
     for (; p + 7 * rpb < p1; p += 8 * rpb) {  // 8 independent 16-byte loads in flight per thread
       uint4 u[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) u[k] = __ldg(base + static_cast<size_t>(p + k * rpb) * cv);
+      for (int k = 0; k < 8; ++k) u[k] = ldg_hint(base + static_cast<size_t>(p + k * rpb) * cv, pol);
 #pragma unroll
       for (int k = 0; k < 8; ++k) accum(u[k]);
     }
-    for (; p < p1; p += rpb) accum(__ldg(base + static_cast<size_t>(p) * cv));
+    for (; p < p1; p += rpb) accum(ldg_hint(base + static_cast<size_t>(p) * cv, pol));
   }
   flush(cur_b);
 }
@@ -112,7 +140,7 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x, double* __restrict_
 template <bool kSilu>
 __global__ void gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
-                                int groups, float eps, int items_per_sample, int ipx, int total_items) {
+                                int groups, float eps, int items_per_sample, int ipx, int total_items, int l2_hints) {
   const int cv = C >> 3;
   const int rpb = blockDim.x / cv;
   const int cvec = threadIdx.x % cv;
@@ -156,6 +184,7 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__
     return make_uint4(o[0], o[1], o[2], o[3]);
   };
   int cur_b = -1;
+  const uint64_t pol = l2_hints ? l2_policy_evict_first() : l2_policy_normal();
   // walk this CTA's range backwards: the stats pass streamed it forwards, so its tail is the most likely part of
   // x to still sit in the 126 MB L2
   for (int it = i1 - 1; it >= i0; --it) {
@@ -173,11 +202,11 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__
     for (; p + 3 * rpb < p1; p += 4 * rpb) {
       uint4 u[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = __ldg(xb + static_cast<size_t>(p + k * rpb) * cv);
+      for (int k = 0; k < 4; ++k) u[k] = ldg_hint(xb + static_cast<size_t>(p + k * rpb) * cv, pol);
 #pragma unroll
       for (int k = 0; k < 4; ++k) yb[static_cast<size_t>(p + k * rpb) * cv] = norm8(u[k]);
     }
-    for (; p < p1; p += rpb) yb[static_cast<size_t>(p) * cv] = norm8(__ldg(xb + static_cast<size_t>(p) * cv));
+    for (; p < p1; p += rpb) yb[static_cast<size_t>(p) * cv] = norm8(ldg_hint(xb + static_cast<size_t>(p) * cv, pol));
   }
 }
 
@@ -279,20 +308,24 @@ extern "C" int ds_groupnorm_silu(const void* x, void* y, const float* gamma, con
     const long long g = static_cast<long long>(occ) * dev.num_sms;
     return static_cast<int>(g < total_items ? g : total_items);
   };
+  static const int l2_hints = [] {  // DS_GN_L2HINT=0 disables the evict_last / evict_first policies (A/B timing)
+    const char* e = getenv("DS_GN_L2HINT");
+    return e ? atoi(e) : 1;
+  }();
   double* dstats = reinterpret_cast<double*>(stats);
   DS_CUDA_OK(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * B * groups, st));
   const size_t sh = sizeof(double) * 2 * groups;
   gn_stats_kernel<<<wave(reinterpret_cast<const void*>(gn_stats_kernel), sh), threads, sh, st>>>(
-      static_cast<const uint4*>(x), dstats, HW, C, groups, items_per_sample, ipx, total_items);
+      static_cast<const uint4*>(x), dstats, HW, C, groups, items_per_sample, ipx, total_items, l2_hints);
   DS_LAUNCH_OK("gn_stats_kernel");
   if (apply_silu)
     gn_apply_kernel<true><<<wave(reinterpret_cast<const void*>(gn_apply_kernel<true>), 0), threads, 0, st>>>(
         static_cast<const uint4*>(x), static_cast<uint4*>(y), dstats, gamma, beta, HW, C, groups, eps,
-        items_per_sample, ipx, total_items);
+        items_per_sample, ipx, total_items, l2_hints);
   else
     gn_apply_kernel<false><<<wave(reinterpret_cast<const void*>(gn_apply_kernel<false>), 0), threads, 0, st>>>(
         static_cast<const uint4*>(x), static_cast<uint4*>(y), dstats, gamma, beta, HW, C, groups, eps,
-        items_per_sample, ipx, total_items);
+        items_per_sample, ipx, total_items, l2_hints);
   DS_LAUNCH_OK("gn_apply_kernel");
   return DS_OK;
 }

@@ -19,6 +19,8 @@ Loop structure on the GPU (one process per GPU, one stream):
 """
 from __future__ import annotations
 
+import os
+
 from types import SimpleNamespace
 from typing import List, Optional
 
@@ -120,9 +122,9 @@ class DiffSenseiPipeline:
     def make_stepper(self, latents: torch.Tensor, prompt_embeds: torch.Tensor, add_text_embeds: torch.Tensor,
                      add_time_ids: torch.Tensor, bbox: torch.Tensor, aspect_ratio: float,
                      dialog_bbox: Optional[torch.Tensor], num_inference_steps: int, guidance_scale: float,
-                     use_graph: bool = True) -> "DenoiseStepper":
+                     use_graph: bool = True, chains: Optional[int] = None) -> "DenoiseStepper":
         return DenoiseStepper(self, latents, prompt_embeds, add_text_embeds, add_time_ids, bbox, aspect_ratio,
-                              dialog_bbox, num_inference_steps, guidance_scale, use_graph)
+                              dialog_bbox, num_inference_steps, guidance_scale, use_graph, chains)
 
     @torch.no_grad()
     def denoise(self, latents: torch.Tensor, prompt_embeds: torch.Tensor, add_text_embeds: torch.Tensor,
@@ -207,7 +209,7 @@ class DenoiseStepper:
 
     @torch.no_grad()
     def __init__(self, pipe: DiffSenseiPipeline, latents, prompt_embeds, add_text_embeds, add_time_ids, bbox,
-                 aspect_ratio, dialog_bbox, num_inference_steps, guidance_scale, use_graph=True):
+                 aspect_ratio, dialog_bbox, num_inference_steps, guidance_scale, use_graph=True, chains=None):
         unet, dev = pipe.unet, pipe.unet.device
         self.unet, self.dev, self.guidance = unet, dev, float(guidance_scale)
         bs = latents.shape[0]
@@ -228,6 +230,22 @@ class DenoiseStepper:
         self.coef_cur = self.coef_table[0].clone()
         self._host_in = None
         self.graph = None
+        # Independent batch rows (the CFG halves, the panels) CAN run as `chains` concurrent kernel chains on separate
+        # streams (graph branches), meant to back-fill the idle SMs of every kernel's last wave (flops-weighted tile
+        # efficiency of one cfg2 step: 0.80, tools/shape_census.py).  MEASURED on B200 (cfg2, graph replay): 1 chain
+        # 67.6 ms/step, 2 chains 76.7, 4 chains 76.9 — the half-size launches lose more to their own tails and
+        # per-launch fixed costs than back-filling recovers (1-CTA/SM persistent GEMMs cannot co-reside).  Default
+        # therefore stays 1; DS_CHAINS / `chains=` keep the path for var-res buckets whose panels differ in size.
+        B2 = self.model_in.shape[0]
+        want = int(os.environ.get("DS_CHAINS", "1")) if chains is None else int(chains)
+        self.chains = max(1, min(want, B2))
+        self._parts, self._side = [(0, B2)], []
+        if self.chains > 1:
+            cuts = [round(k * B2 / self.chains) for k in range(self.chains + 1)]
+            self._parts = [(cuts[k], cuts[k + 1]) for k in range(self.chains) if cuts[k + 1] > cuts[k]]
+            self._cond_parts = [self.cond.rows(s, e) for s, e in self._parts]
+            self._side = [torch.cuda.Stream(device=dev) for _ in self._parts[1:]]
+            self._eps = torch.empty_like(self.model_in)
         if use_graph:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -244,7 +262,20 @@ class DenoiseStepper:
             self.model_in.copy_(min0)
 
     def _launch(self):
-        eps = self.unet.forward_nhwc(self.model_in, self.temb_cur, self.cond, self.db, self.round_bf16)   # :322-329
+        if len(self._parts) == 1:
+            eps = self.unet.forward_nhwc(self.model_in, self.temb_cur, self.cond, self.db, self.round_bf16)  # :322-329
+        else:
+            main = torch.cuda.current_stream(self.dev)
+            eps = self._eps
+            for k, (s, e) in enumerate(self._parts):
+                st = main if k == 0 else self._side[k - 1]
+                if k:
+                    st.wait_stream(main)                       # fork (inside a capture: joins the captured graph)
+                with torch.cuda.stream(st):
+                    self.unet.forward_nhwc(self.model_in[s:e], self.temb_cur[s:e], self._cond_parts[k],
+                                           None if self.db is None else self.db[s:e], self.round_bf16, out=eps[s:e])
+            for st in self._side:
+                main.wait_stream(st)                           # join before the CFG blend needs both halves
         ops.cfg_ddim_step_(eps, self.lat, self.model_in, self.coef_cur, self.guidance)   # :332-337 (+ :315 of next)
 
     @torch.no_grad()

@@ -46,6 +46,11 @@ class Conditions:
     batch: int
     key: tuple = ()
 
+    def rows(self, s: int, e: int) -> "Conditions":
+        """The conditions of batch rows [s, e) (views; every op on the path is per-sample)."""
+        return Conditions(kv_text=[t[s:e] for t in self.kv_text], kv_ip=[t[s:e] for t in self.kv_ip],
+                          bbox=self.bbox[s:e], aspect_ratio=self.aspect_ratio, batch=e - s)
+
 
 class _Resnet:
     __slots__ = ("cin", "cout", "n1", "n2", "w1", "b1", "w2", "b2", "wsc", "bsc", "temb_off")
@@ -263,8 +268,10 @@ class UNetMangaEngine:
 
     # ------------------------------------------------------------------------------------------ forward
     def forward_nhwc(self, x: torch.Tensor, temb: torch.Tensor, cond: Conditions,
-                     dialog_bbox: Optional[torch.Tensor] = None, round_bf16: bool = True) -> torch.Tensor:
-        """x: bf16 [B,H,W,4]; temb: fp32 [B, sum(Cout)] from ``time_rowbias``; returns eps bf16 [B,H,W,4]."""
+                     dialog_bbox: Optional[torch.Tensor] = None, round_bf16: bool = True,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x: bf16 [B,H,W,4]; temb: fp32 [B, sum(Cout)] from ``time_rowbias``; returns eps bf16 [B,H,W,4]
+        (written into ``out`` when given — a contiguous batch slice of a larger buffer is fine)."""
         cfg = self.cfg
         ch, depth = cfg.block_out_channels, cfg.transformer_layers_per_block
         nlev = len(ch)
@@ -301,7 +308,7 @@ class UNetMangaEngine:
                 w, b = self.up_convs[i]
                 h = ops.conv3x3(ops.upsample_nearest(h, Ho, Wo), w, b)
         h = ops.groupnorm_silu(h, self.norm_out[0], self.norm_out[1], cfg.norm_num_groups, 1e-5, True, out=h)
-        return ops.conv3x3(h, self.conv_out_w, self.conv_out_b)
+        return ops.conv3x3(h, self.conv_out_w, self.conv_out_b, out=out)
 
     def _conditions_for(self, ehs: torch.Tensor, bbox: torch.Tensor, aspect_ratio: float) -> Conditions:
         key = (ehs.data_ptr(), ehs._version, tuple(ehs.shape), bbox.data_ptr(), bbox._version, float(aspect_ratio))

@@ -55,6 +55,8 @@ static const Case cases[] = {
     {"self_2x200_h2_tail", SELF, 2, 200, 2, 0, 1.0f, 0, 0, 0, 0},
     {"self_1x1024_h2_peaky", SELF, 1, 1024, 2, 0, 4.0f, 64, 0, 0, 0},
     {"self_2x77_h1_small", SELF, 2, 77, 1, 0, 2.0f, 0, 0, 0, 0},
+    {"self_1x2048_h1_verypeaky_rescale", SELF, 1, 2048, 1, 0, 8.0f, 96, 0, 0, 0},
+    {"self_1x300_h1_peaky_tail", SELF, 1, 300, 1, 0, 6.0f, 0, 0, 0, 0},
     {"resampler_4x16_kv274_h2", RESAMPLER, 4, 16, 2, 274, 1.5f, 0, 0, 0, 0},
     {"cross_2x(12x20)_h2", CROSS, 2, 240, 2, 0, 1.0f, 0, 0, 12, 20},
     {"cross_2x(32x32)_h1", CROSS, 2, 1024, 1, 0, 2.0f, 0, 0, 32, 32},

@@ -127,6 +127,27 @@ def test_denoise_loop_matches_oracle_and_graph_equals_eager(tiny):
     assert torch.equal(graphed, eager)            # same kernels, same order: bit-identical
 
 
+def test_concurrent_chains_do_not_change_the_result(tiny):
+    """DenoiseStepper runs independent batch rows as concurrent kernel chains (graph branches on side streams);
+    every op on the path is per-sample, so 1, 2 and 4 chains must agree."""
+    ds, _oracle, engine = tiny
+    bs, h, w = 2, 16, 24
+    lat, ehs, pooled, time_ids, bbox, dialog = _inputs(ds.TINY, bs, h, w, seed=9)
+    pipe = ds.DiffSenseiPipeline(engine)
+    outs = {}
+    for chains in (1, 2, 4):
+        for use_graph in (False, True):
+            st = pipe.make_stepper(lat, ehs, pooled, time_ids, bbox, h / w, dialog, 3, 7.5, use_graph=use_graph,
+                                   chains=chains)
+            assert st.chains == chains
+            for i in range(3):
+                st.step(i)
+            outs[(chains, use_graph)] = st.latents_nchw().float().cpu()
+    base = outs[(1, False)]
+    for k, v in outs.items():
+        assert rel_l2(v, base) < 1e-3, k
+
+
 def test_pipeline_call_surface(tiny):
     ds, _oracle, engine = tiny
     from oracle.resampler import OracleResampler

@@ -3,7 +3,7 @@
   ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/kernels \
       python tools/profile_kernels.py
 Launch order inside the profiled range: gn_stats, gn_apply, gemm<256> FF1/GEGLU, gemm<128> (N=640 out-proj with
-residual), conv3x3 (8,64,64,640->640), flash_attn (B8 N4096 h10), cross_ip_attn (B8 N4096 h10), layernorm."""
+residual), gemm M8192 N1280 K1280 + residual, conv3x3 (8,64,64,640->640), flash_attn (B8 N4096 h10), cross_ip_attn (B8 N4096 h10), layernorm."""
 import os
 import sys
 
@@ -21,6 +21,7 @@ x = r(8, 128, 128, 320)
 ga, be, st = torch.ones(320, device=dev), torch.zeros(320, device=dev), torch.empty(4 * 8 * 32, device=dev)
 a1, w1, b1 = r(8192, 1280), r(10240, 1280) * 0.03, torch.zeros(10240, device=dev)
 a2, w2, b2, res2 = r(32768, 640), r(640, 640) * 0.04, torch.zeros(640, device=dev), r(32768, 640)
+a3, w3, b3, res3 = r(8192, 1280), r(1280, 1280) * 0.03, torch.zeros(1280, device=dev), r(8192, 1280)
 xc, wc, bc = r(8, 64, 64, 640), pack_conv3x3(torch.randn(640, 640, 3, 3, device=dev) * 0.013), torch.zeros(640, device=dev)
 temb = torch.randn(8, 640, device=dev)
 qkv = r(8, 4096, 1920)
@@ -33,6 +34,7 @@ def run():
     ops.groupnorm_silu(x, ga, be, 32, 1e-5, True, stats=st)
     ops.gemm(a1, w1, b1, epilogue=ops.EPI_GEGLU)
     ops.gemm(a2, w2, b2, residual=res2)
+    ops.gemm(a3, w3, b3, residual=res3)
     ops.conv3x3(xc, wc, bc, rowbias=temb, residual=xc)
     ops.attention_self(qkv, 10)
     ops.attention_cross_ip(q, kvt, kvi, bbox, 10, 1.0, 0.6, 16, 16)
