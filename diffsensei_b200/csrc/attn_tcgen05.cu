@@ -646,6 +646,538 @@ flash_attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 // =================================================================================================
+// (1c) flash attention v4 — v3 with the kv tile split into two 64-key HALVES that flow through the
+//      S-MMA -> softmax -> PV-MMA chain independently.  ncu on v3 (profiles/r01_ncu_flash_v3.md): the softmax warps
+//      spent 36 % of their time waiting for the next S (PV + S MMAs + two mbarrier hand-offs sit between "P written"
+//      and "next S readable"), so the MUFU pipe — the binding resource at head_dim 64 — idled half the time.  Here
+//      the tensor core recomputes S half 0 of tile j+1 while the softmax warps are still in half 1 of tile j, so
+//      they never run dry:
+//        MMA warp :  wait P_h0(j) -> PV_h0(j), S_h0(j+1) ;  wait P_h1(j) -> PV_h1(j), S_h1(j+1)
+//        softmax  :  wait S_h0 -> exp -> P_h0 ;  wait S_h1 -> exp -> P_h1      (one thread per query row)
+//      The reference max starts as the exact max of half 0 of tile 0; everything after is covered by the sum-bounded
+//      lazy rescale (row sum of a half < 2^10 proves no score exceeded m_ref by more than 10 in log2).
+// =================================================================================================
+template <int POLY>
+__global__ void __launch_bounds__(kFlash3Threads, 2)
+flash_attn_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
+  constexpr int RING = kFlash3Ring;
+  constexpr int kHalf = 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sRing = sQ + kTileBytes;  // RING x 16 KiB: K_0 V_0 K_1 V_1 ...
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + RING * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* full = bars + 1;          // [RING]
+  uint64_t* empty = full + RING;      // [RING]
+  uint64_t* s_full = empty + RING;    // [2]  S half h readable
+  uint64_t* p_full = s_full + 2;      // [2]  P half h written (and S half h consumed)
+  uint64_t* pv_done = p_full + 2;     // [2]  O += P_h V_h retired (only waited on by the rescale path)
+  uint64_t* o_full = pv_done + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTile;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int num_kv_tiles = (p.Nkv + kTile - 1) / kTile;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < RING; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&s_full[h], 1);
+      mbar_init(&p_full[h], 4);  // one arrival per softmax warp
+      mbar_init(&pv_done[h], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;        // columns [0,128)   fp32 scores (half h at +64h)
+  const uint32_t tO = tmem_base + 128;  // columns [128,192) fp32 output accumulator
+  const uint32_t tP = tmem_base + 192;  // columns [192,256) bf16x2 probabilities (half h at +32h)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTileBytes);
+      tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + head * kHd, q0, batch);
+      for (int idx = 0; idx < 2 * num_kv_tiles; ++idx) {  // K_0 V_0 K_1 V_1 ...
+        const int slot = idx % RING;
+        const uint32_t ph = (idx / RING) & 1;
+        const int j = idx >> 1, which = idx & 1;
+        mbar_wait(&empty[slot], ph ^ 1);
+        mbar_arrive_expect_tx(&full[slot], kTileBytes);
+        tma_load_3d(sRing + slot * kTileBytes, which == 0 ? &tmK : &tmV, &full[slot],
+                    (which == 0 ? p.k_col0 : p.v_col0) + head * kHd, j * kTile, batch);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(kTile, kHalf, 0, 0);  // M128 N64, both K-major
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);    // M128 N64, A from TMEM, B (=V) MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_s = [&](uint32_t k_addr, int h) {  // S_h = Q K[64h..64h+64)^T
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k)
+          umma_ss(tS + h * kHalf, make_sw128_desc(q_addr + k * 32, 1024, 16),
+                  make_sw128_desc(k_addr + h * (kHalf * 128) + k * 32, 1024, 16), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[h]);
+      };
+      auto issue_pv = [&](uint32_t v_addr, int h, bool first) {  // O (+)= P_h V[64h..64h+64)
+#pragma unroll
+        for (int k = 0; k < kHalf / 16; ++k)
+          umma_ts(tO, tP + h * 32 + k * 8, make_sw128_desc(v_addr + h * (kHalf * 128) + k * 2048, 1024, 1024), idesc_pv,
+                  (first && k == 0) ? 0u : 1u);
+        umma_commit(&pv_done[h]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&full[0], 0);  // K_0
+      tc_fence_after();
+      issue_s(smem_u32(sRing), 0);
+      issue_s(smem_u32(sRing), 1);
+      umma_commit(&empty[0]);
+      for (int j = 0; j < num_kv_tiles; ++j) {
+        const int vi = 2 * j + 1, vslot = vi % RING;
+        const int ki = 2 * j + 2, kslot = ki % RING;
+        const bool more = j + 1 < num_kv_tiles;
+        mbar_wait(&full[vslot], (vi / RING) & 1);        // V_j
+        if (more) mbar_wait(&full[kslot], (ki / RING) & 1);  // K_{j+1}
+        const uint32_t v_addr = smem_u32(sRing + vslot * kTileBytes);
+        const uint32_t k_addr = smem_u32(sRing + kslot * kTileBytes);
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(v_addr, 0, j == 0);
+        if (more) issue_s(k_addr, 0);
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(v_addr, 1, false);
+        umma_commit(&empty[vslot]);
+        if (more) {
+          issue_s(k_addr, 1);
+          umma_commit(&empty[kslot]);
+        }
+      }
+      umma_commit(o_full);
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- softmax: 4 warps, thread <-> query row
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tSr = tS + lane_base, tOr = tO + lane_base, tPr = tP + lane_base;
+    float m_ref = -INFINITY, l = 0.f;
+
+    // 32 scores -> 16 packed bf16x2 probabilities; partial sums into s0/s1
+    auto chunk = [&](const uint32_t(&raw)[32], uint32_t(&pk)[16], float neg_m, int valid, float& s0, float& s1) {
+      if (valid >= 32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
+          const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
+          const float e0 = ((2 * i) % 8 < POLY) ? ex2_poly(t0) : ex2(t0);
+          const float e1 = ((2 * i + 1) % 8 < POLY) ? ex2_poly(t1) : ex2(t1);
+          s0 += e0;
+          s1 += e1;
+          pk[i] = pack_bf16_alu(e0, e1);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
+          const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
+          const float e0 = (2 * i < valid) ? ex2(t0) : 0.f;
+          const float e1 = (2 * i + 1 < valid) ? ex2(t1) : 0.f;
+          s0 += e0;
+          s1 += e1;
+          pk[i] = pack_bf16_alu(e0, e1);
+        }
+      }
+    };
+
+    for (int j = 0; j < num_kv_tiles; ++j) {
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int valid = p.Nkv - j * kTile - h * kHalf;  // >= 64: whole half valid; <= 0: nothing valid
+        mbar_wait(&s_full[h], j & 1);
+        tc_fence_after();
+        const uint32_t tSh = tSr + h * kHalf, tPh = tPr + h * 32;
+        bool need_max = (j == 0) && (h == 0);
+        float lsum;
+#pragma unroll 1
+        for (;;) {
+          uint32_t ra[32], rb[32];
+          tmem_ld32(tSh, ra);
+          tmem_ld32(tSh + 32, rb);
+          tmem_ld_wait();
+          if (need_max) {  // exact maximum of this half's valid scores -> move the reference, rescale O and l
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < valid) mx = fmaxf(mx, __uint_as_float(ra[i]));
+              if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(rb[i]));
+            }
+            const float t_new = mx * p.scale_log2;
+            float alpha = 1.0f;
+            if (t_new > m_ref) {
+              alpha = ex2(m_ref - t_new);  // m_ref = -inf on the very first half: alpha = 0, l = 0 anyway
+              m_ref = t_new;
+              l *= alpha;
+            }
+            if (j | h) {  // O holds something: wait until the last issued PV retired, then scale this warp's rows
+              if (h == 0)
+                mbar_wait(&pv_done[1], (j - 1) & 1);
+              else
+                mbar_wait(&pv_done[0], j & 1);
+              tc_fence_after();
+              tmem_st_wait();  // the aborted P stores of the first attempt
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                uint32_t o[32];
+                tmem_ld32(tOr + c * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                tmem_st32(tOr + c * 32, o);
+              }
+            }
+          }
+          float s0 = 0.f, s1 = 0.f;
+          uint32_t pk[16];
+          chunk(ra, pk, -m_ref, valid, s0, s1);
+          tmem_st16(tPh, pk);
+          chunk(rb, pk, -m_ref, valid - 32, s0, s1);
+          tmem_st16(tPh + 16, pk);
+          lsum = s0 + s1;
+          if (need_max) break;  // exact reference: every term <= 1
+          need_max = __any_sync(0xffffffffu, !(lsum < kSumOverflow));  // warp-uniform, rare
+          if (!need_max) break;
+        }
+        l += lsum;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[h]);
+      }
+    }
+    // ---- epilogue: O / l -> bf16 -> global (one 128-byte row segment per thread)
+    const float inv_l = 1.0f / l;
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int q_row = q0 + row;
+    __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.Nq + q_row) * p.ldo + head * kHd;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(tOr + c * 32, raw);
+      tmem_ld_wait();
+      if (q_row < p.Nq) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(raw[q * 8 + 0]) * inv_l, __uint_as_float(raw[q * 8 + 1]) * inv_l);
+          u.y = pack_bf16(__uint_as_float(raw[q * 8 + 2]) * inv_l, __uint_as_float(raw[q * 8 + 3]) * inv_l);
+          u.z = pack_bf16(__uint_as_float(raw[q * 8 + 4]) * inv_l, __uint_as_float(raw[q * 8 + 5]) * inv_l);
+          u.w = pack_bf16(__uint_as_float(raw[q * 8 + 6]) * inv_l, __uint_as_float(raw[q * 8 + 7]) * inv_l);
+          reinterpret_cast<uint4*>(orow + c * 32)[q] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// =================================================================================================
+// (1d) flash attention v5 — two INDEPENDENT online-softmax streams per CTA.
+//      ncu on v3/v4 (profiles/r01_ncu_flash_v3.md): with one softmax warp per SM sub-partition per CTA the exp
+//      loop is a single dependent instruction stream (issue: selected 33 % / fixed-latency wait 35 %), i.e. bound
+//      by per-warp issue latency, not by the MUFU or the tensor pipe — which is also why moving exponentials to
+//      the FMA pipe made it slower.  v5 doubles the warps that are in the exp loop at any time:
+//        stream h (h = 0, 1) owns keys [64h, 64h+64) of EVERY 128-key tile, with its own warps (4 per stream, one
+//        thread per query row), its own reference max m_h, row sum l_h and TMEM accumulator O_h.  The streams
+//        never synchronise until the epilogue, where   out = (w_0 O_0 + w_1 O_1) / (w_0 l_0 + w_1 l_1),
+//        w_h = 2^(m_h - max(m_0, m_1))   (the split-KV identity).
+//      P_h is written over the head of S_h's own columns (thread-local rows; in-order MMA execution makes
+//      S_h(j+1) land after PV_h(j) has consumed it), which frees the TMEM columns for the second accumulator:
+//        TMEM (256 columns, 2 CTAs/SM): S_0|P_0 [0,64) | S_1|P_1 [64,128) | O_0 [128,192) | O_1 [192,256).
+//      Both chunks of P are built in registers before the overflow check, so the (rare) redo still finds S intact.
+// =================================================================================================
+constexpr int kFlash5Threads = 320;  // warp 0: TMA + TMEM alloc, warp 1: MMA issue, warps 2-9: two softmax streams
+constexpr int kFlash5SmemBytes = kTileBytes * (1 + kFlash3Ring) + 1024 + 256 + 2 * kTile * 2 * 4;
+
+template <int POLY>
+__global__ void __launch_bounds__(kFlash5Threads, 2)
+flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
+  constexpr int RING = kFlash3Ring;
+  constexpr int kHalf = 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sRing = sQ + kTileBytes;  // RING x 16 KiB: K_0 V_0 K_1 V_1 ...
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + RING * kTileBytes);
+  uint64_t* q_full = bars;
+  uint64_t* full = bars + 1;        // [RING]
+  uint64_t* empty = full + RING;    // [RING]
+  uint64_t* s_full = empty + RING;  // [2]  S_h readable (and PV_h of the previous tile retired)
+  uint64_t* p_full = s_full + 2;    // [2]  P_h written
+  uint64_t* o_full = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float2* s_ml = reinterpret_cast<float2*>(bars + 32);  // [2][128] (m_h, l_h) exchange for the epilogue
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTile;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int num_kv_tiles = (p.Nkv + kTile - 1) / kTile;
+
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < RING; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&s_full[h], 1);
+      mbar_init(&p_full[h], 4);  // one arrival per softmax warp of the stream
+    }
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;        // S_h (and P_h over its first 32 columns) at +64h
+  const uint32_t tO = tmem_base + 128;  // O_h at +64h
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kTileBytes);
+      tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + head * kHd, q0, batch);
+      for (int idx = 0; idx < 2 * num_kv_tiles; ++idx) {  // K_0 V_0 K_1 V_1 ...
+        const int slot = idx % RING;
+        const uint32_t ph = (idx / RING) & 1;
+        const int j = idx >> 1, which = idx & 1;
+        mbar_wait(&empty[slot], ph ^ 1);
+        mbar_arrive_expect_tx(&full[slot], kTileBytes);
+        tma_load_3d(sRing + slot * kTileBytes, which == 0 ? &tmK : &tmV, &full[slot],
+                    (which == 0 ? p.k_col0 : p.v_col0) + head * kHd, j * kTile, batch);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(kTile, kHalf, 0, 0);  // M128 N64, both K-major
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);    // M128 N64, A from TMEM, B (=V) MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_s = [&](uint32_t k_addr, int h) {  // S_h = Q K[64h..64h+64)^T
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k)
+          umma_ss(tS + h * kHalf, make_sw128_desc(q_addr + k * 32, 1024, 16),
+                  make_sw128_desc(k_addr + h * (kHalf * 128) + k * 32, 1024, 16), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[h]);
+      };
+      auto issue_pv = [&](uint32_t v_addr, int h, bool first) {  // O_h (+)= P_h V[64h..64h+64)
+#pragma unroll
+        for (int k = 0; k < kHalf / 16; ++k)
+          umma_ts(tO + h * kHd, tS + h * kHalf + k * 8, make_sw128_desc(v_addr + h * (kHalf * 128) + k * 2048, 1024, 1024),
+                  idesc_pv, (first && k == 0) ? 0u : 1u);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&full[0], 0);  // K_0
+      tc_fence_after();
+      issue_s(smem_u32(sRing), 0);
+      issue_s(smem_u32(sRing), 1);
+      umma_commit(&empty[0]);
+      for (int j = 0; j < num_kv_tiles; ++j) {
+        const int vi = 2 * j + 1, vslot = vi % RING;
+        const int ki = 2 * j + 2, kslot = ki % RING;
+        const bool more = j + 1 < num_kv_tiles;
+        mbar_wait(&full[vslot], (vi / RING) & 1);            // V_j
+        if (more) mbar_wait(&full[kslot], (ki / RING) & 1);  // K_{j+1}
+        const uint32_t v_addr = smem_u32(sRing + vslot * kTileBytes);
+        const uint32_t k_addr = smem_u32(sRing + kslot * kTileBytes);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&p_full[h], j & 1);
+          tc_fence_after();
+          issue_pv(v_addr, h, j == 0);
+          if (h == 1) umma_commit(&empty[vslot]);
+          if (more) issue_s(k_addr, h);  // executes after PV_h(j): P_h(j) is consumed before S_h(j+1) overwrites it
+          if (more && h == 1) umma_commit(&empty[kslot]);
+        }
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax: 2 streams x 4 warps, thread <-> (row, h)
+    const int h = (warp - 2) >> 2;
+    const int wq = warp & 3;  // TMEM lane quadrant this warp may touch
+    const int row = wq * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tSh = tS + lane_base + h * kHalf;  // this stream's scores; P_h goes over [tSh, tSh + 32)
+    float m_ref = -INFINITY, l = 0.f;
+
+    // 32 scores -> 16 packed bf16x2 probabilities; partial sums into s0/s1
+    auto chunk = [&](const uint32_t(&raw)[32], uint32_t(&pk)[16], float neg_m, int valid, float& s0, float& s1) {
+      if (valid >= 32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
+          const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
+          const float e0 = ((2 * i) % 8 < POLY) ? ex2_poly(t0) : ex2(t0);
+          const float e1 = ((2 * i + 1) % 8 < POLY) ? ex2_poly(t1) : ex2(t1);
+          s0 += e0;
+          s1 += e1;
+          pk[i] = pack_bf16_alu(e0, e1);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
+          const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
+          const float e0 = (2 * i < valid) ? ex2(t0) : 0.f;
+          const float e1 = (2 * i + 1 < valid) ? ex2(t1) : 0.f;
+          s0 += e0;
+          s1 += e1;
+          pk[i] = pack_bf16_alu(e0, e1);
+        }
+      }
+    };
+
+    for (int j = 0; j < num_kv_tiles; ++j) {
+      const int valid = p.Nkv - j * kTile - h * kHalf;  // >= 64: whole half valid; <= 0: nothing valid
+      mbar_wait(&s_full[h], j & 1);
+      tc_fence_after();
+      bool need_max = (j == 0);
+      float lsum;
+#pragma unroll 1
+      for (;;) {
+        uint32_t ra[32];
+        if (need_max) {  // exact maximum of this stream's valid scores -> move the reference, rescale O_h and l_h
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tmem_ld32(tSh + c * 32, ra);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(ra[i]));
+          }
+          const float t_new = mx * p.scale_log2;
+          float alpha = 1.0f;  // rows whose reference does not move are scaled by 1
+          if (t_new > m_ref) {
+            alpha = ex2(m_ref - t_new);  // first tile: m_ref = -inf -> alpha = 0 (l = 0, O_h unset)
+            m_ref = t_new;
+            l *= alpha;
+          }
+          if (j > 0) {  // warp-uniform (tcgen05.ld/st are .sync.aligned); s_full[h](j) was committed after
+                        // PV_h(j-1), so O_h is quiescent
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              tmem_ld32(tO + lane_base + h * kHd + c * 32, ra);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ra[i] = __float_as_uint(__uint_as_float(ra[i]) * alpha);
+              tmem_st32(tO + lane_base + h * kHd + c * 32, ra);
+            }
+          }
+        }
+        float s0 = 0.f, s1 = 0.f;
+        uint32_t pk0[16], pk1[16];
+        tmem_ld32(tSh, ra);
+        tmem_ld_wait();
+        chunk(ra, pk0, -m_ref, valid, s0, s1);
+        tmem_ld32(tSh + 32, ra);
+        tmem_ld_wait();
+        chunk(ra, pk1, -m_ref, valid - 32, s0, s1);
+        lsum = s0 + s1;
+        if (!need_max) need_max = __any_sync(0xffffffffu, !(lsum < kSumOverflow));  // warp-uniform, rare
+        else need_max = false;  // exact reference: every term <= 1
+        if (!need_max) {  // S_h is only overwritten once the row sum is known to be safe
+          tmem_st16(tSh, pk0);
+          tmem_st16(tSh + 16, pk1);
+          break;
+        }
+      }
+      l += lsum;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[h]);
+    }
+    // ---- epilogue: merge the two streams, normalise, store (thread (row, h) writes output columns [32h, 32h+32))
+    s_ml[h * kTile + row] = make_float2(m_ref, l);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float2 mine = make_float2(m_ref, l), other = s_ml[(h ^ 1) * kTile + row];
+    const float m = fmaxf(mine.x, other.x);
+    const float w_me = ex2(mine.x - m), w_ot = ex2(other.x - m);  // -inf - m = -inf -> 0 for an empty stream
+    const float inv = 1.0f / (mine.y * w_me + other.y * w_ot);
+    const float w0 = (h == 0 ? w_me : w_ot) * inv, w1 = (h == 0 ? w_ot : w_me) * inv;
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int q_row = q0 + row;
+    __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.Nq + q_row) * p.ldo + head * kHd + h * 32;
+    uint32_t a[32], b[32];
+    tmem_ld32(tO + lane_base + h * 32, a);           // O_0[:, 32h .. 32h+32)
+    tmem_ld32(tO + lane_base + kHd + h * 32, b);     // O_1[:, 32h .. 32h+32)
+    tmem_ld_wait();
+    if (q_row < p.Nq) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(__uint_as_float(a[q * 8 + e]), w0, __uint_as_float(b[q * 8 + e]) * w1);
+        uint4 u;
+        u.x = pack_bf16(o[0], o[1]);
+        u.y = pack_bf16(o[2], o[3]);
+        u.z = pack_bf16(o[4], o[5]);
+        u.w = pack_bf16(o[6], o[7]);
+        reinterpret_cast<uint4*>(orow)[q] = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// =================================================================================================
 // (2) fused text + masked-IP cross-attention
 // =================================================================================================
 struct CrossParams {
@@ -885,8 +1417,10 @@ cross_ip_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 //        * P goes registers -> TMEM (bf16x2, aliasing the dead head of the S columns: the thread that read row r's
 //          scores is the only writer of row r's probabilities) and feeds the PV MMAs as a TMEM A operand — no
 //          st.shared / fence.proxy.async / 48 KB P staging buffer;
-//        * one thread per query row, TMEM loads software-pipelined one 16-column chunk ahead.
-//      TMEM (256 columns): S [0,192) fp32 | P [0,96) bf16x2 (alias) | O_text [96,160) (alias) | O_ip [192,256).
+//        * the text softmax and the masked IP softmax of a row are independent: each gets its own 4 warps (one
+//          thread per row and softmax), so 8 exp-loop warps per CTA hide each other's issue latency; TMEM loads are
+//          software-pipelined one 16-column chunk ahead; one compact predicated code path per pass (the round-1 code
+//          was 75 KB of SASS per kernel and instruction-fetch bound).
 // =================================================================================================
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
@@ -894,7 +1428,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                : "memory");
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 2)
+constexpr int kCross2Threads = 320;  // warp 0: TMA + TMEM alloc, warp 1: MMA issue, warps 2-5: text keys, 6-9: IP keys
+
+template <bool UNIFORM>  // UNIFORM: tokens_per_ip and num_dummy are multiples of 16 -> one mask bit per 16-key chunk
+__global__ void __launch_bounds__(kCross2Threads, 2)
 cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKVt,
                         const __grid_constant__ CUtensorMap tmKVip, const CrossParams p, int heads, int q_tiles,
                         int total_items) {
@@ -917,18 +1454,17 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* o_full = bars + 8;
   uint64_t* o_empty = bars + 9;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* s_l = reinterpret_cast<float*>(bars + 16);  // [2][128]: row sums of the two softmaxes (epilogue exchange)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = static_cast<int>(static_cast<long long>(blockIdx.x) * total_items / gridDim.x);
   const int i1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total_items / gridDim.x);
   const int n_items = i1 - i0;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKVt);
     tma_prefetch_desc(&tmKVip);
-  }
-  if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
@@ -936,12 +1472,12 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_init(kv_full, 1);
     mbar_init(kv_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);   // one arrival per softmax warp (4 text + 4 IP)
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
+    mbar_init(o_empty, 8);
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 0) {
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
@@ -949,10 +1485,12 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;          // [0, n_keys) scores
-  const uint32_t tP = tmem_base;          // [0, n_keys/2) packed probabilities (alias)
-  const uint32_t tOt = tmem_base + 96;    // [96,160) text output (alias of dead score columns)
-  const uint32_t tOi = tmem_base + 192;   // [192,256) IP output
+  // TMEM (256 columns): S text [0, nt_pad) | S ip [nt_pad, n_keys);  P_text over [0, nt_pad/2), P_ip over
+  // [nt_pad, nt_pad + nip_pad/2) (each stream overwrites the head of its OWN score columns, thread-local rows);
+  // O_text [128,192) (dead IP score columns + free ones; needs nt_pad + nip_pad/2 <= 128), O_ip [192,256)
+  const uint32_t tS = tmem_base;
+  const uint32_t tOt = tmem_base + 128;
+  const uint32_t tOi = tmem_base + 192;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1008,144 +1546,134 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         for (int k = 0; k < n_keys / 16; ++k) {
           const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048, 1024, 1024);
           if (k < kt)
-            umma_ts(tOt, tP + k * 8, bdesc, idesc_pv, k != 0 ? 1u : 0u);
+            umma_ts(tOt, tS + k * 8, bdesc, idesc_pv, k != 0 ? 1u : 0u);
           else
-            umma_ts(tOi, tP + k * 8, bdesc, idesc_pv, k != kt ? 1u : 0u);
+            umma_ts(tOi, tS + p.nt_pad + (k - kt) * 8, bdesc, idesc_pv, k != kt ? 1u : 0u);
         }
         umma_commit(o_full);
         if (n + 1 < n_items && (item + 1) / q_tiles != bh) umma_commit(kv_empty);
       }
     }
-  } else if (warp >= 4) {
+  } else {
+    // ------------------------------------------------------------ softmax: group 0 = text keys, group 1 = IP keys
+    const int g = (warp - 2) >> 2;
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t tSr = tS + lane_base, tPr = tP + lane_base;
     constexpr float kS2 = 0.125f * kLog2e;
     constexpr float kMask2 = -10000.0f * kLog2e;
-    const int chunks = n_keys / 16;
-    const int t_chunks = p.nt_pad / 16;
-    const bool uniform = (p.tokens_per_ip % 16 == 0) && (p.num_dummy % 16 == 0);
+    const int chunks = (g == 0 ? p.nt_pad : p.nip_pad) / 16;        // 16-key chunks of this group's softmax
+    const int n_real = g == 0 ? p.n_text : p.n_ip;                  // keys that are not padding
+    const uint32_t tSg = tS + lane_base + (g == 0 ? 0 : p.nt_pad);  // this group's scores; its P goes over their head
 
     for (int n = 0; n < n_items; ++n) {
       const int item = i0 + n;
       const int qt = item % q_tiles, bh = item / q_tiles;
       const int head = bh % heads, batch = bh / heads;
       const int q_row = qt * kTile + row;
-      const uint32_t bits = ip_inside_bits(p.bbox + static_cast<size_t>(batch) * p.num_ips * 4, p.num_ips,
-                                           min(q_row, p.N - 1), p.Hd, p.Wd);
-      auto chunk_valid = [&](int c) -> int {
-        const int v = (c < t_chunks) ? p.n_text - c * 16 : p.n_ip - (c - t_chunks) * 16;
-        return v < 0 ? 0 : (v > 16 ? 16 : v);
-      };
-      auto chunk_add = [&](int c) -> float {  // only meaningful when `uniform`
-        if (c < t_chunks) return 0.0f;
-        return ip_key_open(bits, (c - t_chunks) * 16, p.tokens_per_ip, p.num_dummy) ? 0.0f : kMask2;
-      };
-      auto elem_add = [&](int c, int i) -> float {  // general path
-        if (c < t_chunks) return 0.0f;
-        return ip_key_open(bits, (c - t_chunks) * 16 + i, p.tokens_per_ip, p.num_dummy) ? 0.0f : kMask2;
+      // bit k of `open16` (UNIFORM): IP chunk k (16 keys of one character / the dummies) is visible from this row
+      uint32_t bits = 0, open16 = 0xffffffffu;
+      if (g == 1) {
+        bits = ip_inside_bits(p.bbox + static_cast<size_t>(batch) * p.num_ips * 4, p.num_ips, min(q_row, p.N - 1), p.Hd,
+                              p.Wd);
+        if (UNIFORM) {
+          open16 = 0;
+          for (int k = 0; k < chunks; ++k)
+            open16 |= static_cast<uint32_t>(ip_key_open(bits, k * 16, p.tokens_per_ip, p.num_dummy)) << k;
+        }
+      }
+      // additive log2-domain term of key i of chunk c (reference :142,162-163: M in {0, -10000}; text keys: 0)
+      auto add_of = [&](int c, int i) -> float {
+        if (g == 0) return 0.0f;
+        const bool open = UNIFORM ? ((open16 >> c) & 1u) != 0
+                                  : ip_key_open(bits, c * 16 + i, p.tokens_per_ip, p.num_dummy);
+        return open ? 0.0f : kMask2;
       };
 
       mbar_wait(s_full, n & 1);
       tc_fence_after();
-      // ---- pass 1: the two row maxima (log2 domain)
-      float m_t = -INFINITY, m_i = -INFINITY;
+      // ---- pass 1: row maximum (log2 domain)
+      float m = -INFINITY;
       auto max_chunk = [&](int c, const uint32_t(&raw)[16]) {
-        const int nv = chunk_valid(c);
+        const int nv = n_real - c * 16;
         float mx = -INFINITY;
-        if (uniform && nv == 16) {
+        if (UNIFORM) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
-          mx = fmaf(mx, kS2, chunk_add(c));
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, i < nv ? __uint_as_float(raw[i]) : -INFINITY);
+          mx = fmaf(mx, kS2, add_of(c, 0));
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (i < nv) mx = fmaxf(mx, fmaf(__uint_as_float(raw[i]), kS2, uniform ? chunk_add(c) : elem_add(c, i)));
+            mx = fmaxf(mx, i < nv ? fmaf(__uint_as_float(raw[i]), kS2, add_of(c, i)) : -INFINITY);
         }
-        if (c < t_chunks)
-          m_t = fmaxf(m_t, mx);
-        else
-          m_i = fmaxf(m_i, mx);
+        m = fmaxf(m, mx);
       };
-      // ---- pass 2: unnormalised P = 2^(t - m) -> bf16x2 -> TMEM; row sums
-      float l_t = 0.f, l_i = 0.f;
+      // ---- pass 2: unnormalised P = 2^(t - m) -> bf16x2 -> TMEM; row sum
+      float l = 0.f;
       auto exp_chunk = [&](int c, const uint32_t(&raw)[16]) {
-        const int nv = chunk_valid(c);
-        const float m = c < t_chunks ? m_t : m_i;
+        const int nv = n_real - c * 16;
+        const float off_u = add_of(c, 0) - m;  // UNIFORM: one offset per chunk
         uint32_t pk[8];
         float s0 = 0.f, s1 = 0.f;
-        if (uniform && nv == 16) {
-          const float off = chunk_add(c) - m;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), kS2, off));
-            const float e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), kS2, off));
-            s0 += e0;
-            s1 += e1;
-            pk[i] = pack_bf16_alu(e0, e1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float e0 = 0.f, e1 = 0.f;
-            if (2 * i < nv)
-              e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), kS2, (uniform ? chunk_add(c) : elem_add(c, 2 * i)) - m));
-            if (2 * i + 1 < nv)
-              e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), kS2, (uniform ? chunk_add(c) : elem_add(c, 2 * i + 1)) - m));
-            s0 += e0;
-            s1 += e1;
-            pk[i] = pack_bf16_alu(e0, e1);
-          }
+        for (int i = 0; i < 8; ++i) {
+          const float o0 = UNIFORM ? off_u : add_of(c, 2 * i) - m;
+          const float o1 = UNIFORM ? off_u : add_of(c, 2 * i + 1) - m;
+          const float e0 = 2 * i < nv ? ex2(fmaf(__uint_as_float(raw[2 * i]), kS2, o0)) : 0.f;
+          const float e1 = 2 * i + 1 < nv ? ex2(fmaf(__uint_as_float(raw[2 * i + 1]), kS2, o1)) : 0.f;
+          s0 += e0;
+          s1 += e1;
+          pk[i] = pack_bf16_alu(e0, e1);
         }
-        if (c < t_chunks)
-          l_t += s0 + s1;
-        else
-          l_i += s0 + s1;
-        tmem_st8(tPr + c * 8, pk);  // columns [8c, 8c+8) <= the chunk just read: never ahead of an unread score
+        l += s0 + s1;
+        tmem_st8(tSg + c * 8, pk);  // columns [8c, 8c+8) <= the chunk just read: never ahead of an unread score
       };
       {
         uint32_t ra[16], rb[16];
-        tmem_ld16(tSr, ra);
+        tmem_ld16(tSg, ra);
         tmem_ld_wait();
+#pragma unroll 1
         for (int c = 0; c < chunks; c += 2) {
-          if (c + 1 < chunks) tmem_ld16(tSr + (c + 1) * 16, rb);
+          if (c + 1 < chunks) tmem_ld16(tSg + (c + 1) * 16, rb);
           max_chunk(c, ra);
           tmem_ld_wait();
           if (c + 1 < chunks) {
-            if (c + 2 < chunks) tmem_ld16(tSr + (c + 2) * 16, ra);
+            if (c + 2 < chunks) tmem_ld16(tSg + (c + 2) * 16, ra);
             max_chunk(c + 1, rb);
             tmem_ld_wait();
           }
         }
-        tmem_ld16(tSr, ra);
+        tmem_ld16(tSg, ra);
         tmem_ld_wait();
+#pragma unroll 1
         for (int c = 0; c < chunks; c += 2) {
-          if (c + 1 < chunks) tmem_ld16(tSr + (c + 1) * 16, rb);
+          if (c + 1 < chunks) tmem_ld16(tSg + (c + 1) * 16, rb);
           exp_chunk(c, ra);
           tmem_ld_wait();
           if (c + 1 < chunks) {
-            if (c + 2 < chunks) tmem_ld16(tSr + (c + 2) * 16, ra);
+            if (c + 2 < chunks) tmem_ld16(tSg + (c + 2) * 16, ra);
             exp_chunk(c + 1, rb);
             tmem_ld_wait();
           }
         }
       }
+      s_l[g * kTile + row] = l;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // both row sums visible to both groups
 
-      // ---- epilogue: out = O_text / l_t + scale * O_ip / l_i      (blend BEFORE to_out, reference :258)
-      const float w_t = 1.0f / l_t, w_i = p.ip_scale / l_i;
+      // ---- epilogue: out = O_text / l_t + scale * O_ip / l_i   (blend BEFORE to_out, reference :258);
+      //      group g writes output columns [32g, 32g+32)
+      const float w_t = 1.0f / s_l[row], w_i = p.ip_scale / s_l[kTile + row];
       mbar_wait(o_full, n & 1);
       tc_fence_after();
-      __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.N + q_row) * p.C + head * kHd;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.N + q_row) * p.C + head * kHd + g * 32;
+      {
         uint32_t rt[32], ri[32];
-        tmem_ld32(tOt + lane_base + c * 32, rt);
-        tmem_ld32(tOi + lane_base + c * 32, ri);
+        tmem_ld32(tOt + lane_base + g * 32, rt);
+        tmem_ld32(tOi + lane_base + g * 32, ri);
         tmem_ld_wait();
         if (q_row < p.N) {
 #pragma unroll
@@ -1159,19 +1687,20 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             u.y = pack_bf16(o[2], o[3]);
             u.z = pack_bf16(o[4], o[5]);
             u.w = pack_bf16(o[6], o[7]);
-            reinterpret_cast<uint4*>(orow + c * 32)[q] = u;
+            reinterpret_cast<uint4*>(orow)[q] = u;
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // s_l is rewritten by the next tile
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
@@ -1215,7 +1744,7 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
   // DS_FLASH_POLY=n sends n of every 8 exponentials to the FMA pipe (v3 only)
   static const int flash_ver = [] {
     const char* e = getenv("DS_FLASH");
-    return e ? atoi(e) : 3;
+    return e ? atoi(e) : 5;
   }();
   static const int flash_poly = [] {
     const char* e = getenv("DS_FLASH_POLY");
@@ -1224,6 +1753,38 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
   if (flash_ver == 2) {
     flash_attn_kernel<<<grid, kFlashThreads, kFlashSmemBytes, st>>>(tmQ, tmK, tmV, p);
     DS_LAUNCH_OK("flash_attn_kernel");
+    return DS_OK;
+  }
+  if (flash_ver >= 5) {
+    static bool attr5_set = false;
+    if (!attr5_set) {
+      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
+      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
+      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
+      attr5_set = true;
+    }
+    switch (flash_poly) {
+      case 1: flash_attn_v5_kernel<1><<<grid, kFlash5Threads, kFlash5SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
+      case 2: flash_attn_v5_kernel<2><<<grid, kFlash5Threads, kFlash5SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
+      default: flash_attn_v5_kernel<0><<<grid, kFlash5Threads, kFlash5SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
+    }
+    DS_LAUNCH_OK("flash_attn_v5_kernel");
+    return DS_OK;
+  }
+  if (flash_ver >= 4) {
+    static bool attr4_set = false;
+    if (!attr4_set) {
+      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
+      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
+      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
+      attr4_set = true;
+    }
+    switch (flash_poly) {
+      case 1: flash_attn_v4_kernel<1><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
+      case 2: flash_attn_v4_kernel<2><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
+      default: flash_attn_v4_kernel<0><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
+    }
+    DS_LAUNCH_OK("flash_attn_v4_kernel");
     return DS_OK;
   }
   static bool attr3_set = false;
@@ -1323,20 +1884,26 @@ extern "C" int ds_attention_cross_ip(const ds_cross_ip_args* a, void* stream) {
     const char* e = getenv("DS_CROSS");
     return e ? atoi(e) : 2;
   }();
-  if (cross_ver != 1) {
+  if (cross_ver != 1 && nt_pad + nip_pad / 2 <= 128) {  // v2's TMEM layout needs P_ip to end below column 128
     const int q_tiles = (a->N + kTile - 1) / kTile;
     const long long total_ll = static_cast<long long>(a->B) * a->heads * q_tiles;
     DS_REQUIRE(total_ll < (1ll << 30), "ds_attention_cross_ip: too many tiles");
     const int total = static_cast<int>(total_ll);
-    const int smem2 = 2 * kTileBytes + 2 * kv_bytes + 1024 + 128;
+    const int smem2 = 2 * kTileBytes + 2 * kv_bytes + 1024 + 128 + 2 * kTile * 4;
     static int attr_smem2 = 0;
     if (smem2 > attr_smem2) {
-      DS_CUDA_OK(cudaFuncSetAttribute(cross_ip_attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      DS_CUDA_OK(cudaFuncSetAttribute(cross_ip_attn_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      DS_CUDA_OK(cudaFuncSetAttribute(cross_ip_attn_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
       attr_smem2 = smem2;
     }
     const int grid2 = total < 2 * dev.num_sms ? total : 2 * dev.num_sms;
-    cross_ip_attn_v2_kernel<<<grid2, kAttnThreads, smem2, static_cast<cudaStream_t>(stream)>>>(tmQ, tmT, tmI, p, a->heads,
-                                                                                            q_tiles, total);
+    const bool uniform = (a->tokens_per_ip % 16 == 0) && (a->num_dummy % 16 == 0);
+    if (uniform)
+      cross_ip_attn_v2_kernel<true><<<grid2, kCross2Threads, smem2, static_cast<cudaStream_t>(stream)>>>(
+          tmQ, tmT, tmI, p, a->heads, q_tiles, total);
+    else
+      cross_ip_attn_v2_kernel<false><<<grid2, kCross2Threads, smem2, static_cast<cudaStream_t>(stream)>>>(
+          tmQ, tmT, tmI, p, a->heads, q_tiles, total);
     DS_LAUNCH_OK("cross_ip_attn_v2_kernel");
     return DS_OK;
   }

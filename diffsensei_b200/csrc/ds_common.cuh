@@ -337,6 +337,21 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return 0.5f * x * (1.0f + erf_v);
 }
 
+// erf-GELU as x * sigmoid(2 k (x + a x^3 + b x^5)) with (k, a, b) fitted to x * Phi(x): |abs err| <= 2.6e-5 for every
+// x (the classic tanh form with b = 0 is 4.7e-4), i.e. >= 10x below the bf16 rounding of the GEGLU product it feeds.
+// 7 FP + 2 MUFU instead of the 15 FP + 2 MUFU of gelu_erf_fast: the GEGLU epilogue was the co-limiter of the FF1
+// GEMM (tensor pipe 66 %, profiles/r01_ncu_flash_v3.md).  The quintic changes sign beyond |x| ~ 11: clamp to +-10
+// (sigmoid is saturated to 1 - 3e-9 there).
+__device__ __forceinline__ float gelu_sig5(float x) {
+  const float xc = fminf(fmaxf(x, -10.0f), 10.0f);
+  const float x2 = xc * xc;
+  float p = fmaf(-4.40769046e-4f, x2, 4.64016052e-2f);
+  p = fmaf(p, x2, 1.0f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(xc * p * -2.301121339f));  // exp(-2 k u)
+  return __fdividef(x, 1.0f + e);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

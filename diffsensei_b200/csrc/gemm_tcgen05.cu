@@ -48,6 +48,11 @@ struct GemmParams {
   int epilogue, out_fp32;
   int tma_epilogue;  // 1: stage bf16 output tiles in smem and TMA-store them (residual tiles TMA-loaded)
   float out_scale;
+  // LayerNorm fusion: consumer side (A rows are un-normalised; W/bias pre-folded) and producer side (row sums out)
+  const float* ln_stats;   // [M][2] {sum, sum of squares} of A's rows, or NULL
+  const float* ln_colsum;  // [N] sum_k W'[n][k]
+  float ln_eps, ln_inv_k;
+  float* row_stats_out;    // [M][2], accumulated with atomics (zeroed by the host wrapper), or NULL
   int num_m_tiles, num_n_tiles, num_k_iters;
   // conv geometry
   int conv, stride, Ho, Wo, tiles_x, tiles_y, cin_chunks, conv_B;
@@ -62,11 +67,13 @@ template <int BN, int PAIR>
 struct GemmCfg {
   static constexpr int kBRows = BN / PAIR;  // weight rows each CTA stages
   static constexpr int kBBytes = kBRows * kBK * 2;
-  static constexpr int kStages = (196608 / (kABytes + kBBytes)) > 8 ? 8 : (196608 / (kABytes + kBBytes));
+  static constexpr int kStages = (192512 / (kABytes + kBBytes)) > 8 ? 8 : (192512 / (kABytes + kBBytes));
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kStageOutBytes = 2 * kBM * 64 * 2;  // two [128][64] bf16 epilogue staging tiles (one per column half)
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStageOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kVecBytes = 2 * 2 * BN * 4;         // double-buffered per-tile copies of bias[BN] and ln_colsum[BN]
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kStageOutBytes + kVecBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, int PAIR>
@@ -87,7 +94,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * kABytes;
   uint8_t* sOut = sB + STAGES * Cfg::kBBytes;  // 2 x [128][64] bf16, 128-B swizzled (TMA store / residual load)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + Cfg::kStageOutBytes);
+  float* sVec = reinterpret_cast<float*>(sOut + Cfg::kStageOutBytes);  // [2 tiles in flight][bias | colsum][BN]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + Cfg::kStageOutBytes + Cfg::kVecBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
@@ -261,6 +269,29 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     };
 
+    // shared-memory versions (broadcast LDS.128): v[j] += sv[j];  v[j] = rstd * (v[j] - mean * cs[j])
+    auto add32s = [&](float(&v)[32], const float* sv) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 f = *reinterpret_cast<const float4*>(sv + q * 4);
+        v[q * 4 + 0] += f.x;
+        v[q * 4 + 1] += f.y;
+        v[q * 4 + 2] += f.z;
+        v[q * 4 + 3] += f.w;
+      }
+    };
+    auto ln32s = [&](float(&v)[32], const float* cs, float mean, float rstd) {
+      const float nm = -mean * rstd;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 f = *reinterpret_cast<const float4*>(cs + q * 4);
+        v[q * 4 + 0] = fmaf(v[q * 4 + 0], rstd, nm * f.x);
+        v[q * 4 + 1] = fmaf(v[q * 4 + 1], rstd, nm * f.y);
+        v[q * 4 + 2] = fmaf(v[q * 4 + 2], rstd, nm * f.z);
+        v[q * 4 + 3] = fmaf(v[q * 4 + 3], rstd, nm * f.w);
+      }
+    };
+
     int iter = 0;
     uint32_t res_phase = 0;
     // hand the accumulator back to the MMA issuer (pair: the issuer lives in the leader CTA)
@@ -301,6 +332,44 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         batch = p.rowbias ? row / p.rows_per_batch : 0;
       }
 
+      // Per-tile column vectors -> shared memory (double-buffered by accumulator parity).  With ~200 KB of the SM's
+      // 228 KB carved out as shared memory there is next to no L1 left, so the per-chunk __ldg of bias / colsum in
+      // the chunk loops below were L2 round trips on the epilogue's critical path (profiles/r01_ncu_flash_v3.md).
+      //   vec[0..BN)    = bias[n] (+ the time-embedding row bias of this tile's image in conv mode), 0 beyond N
+      //   vec[BN..2BN)  = ln_colsum[n]
+      float* vec = sVec + (iter & 1) * 2 * BN;
+      {
+        const int et = (warp - 4) * 32 + lane;
+        const float* rb_row = nullptr;  // conv: every row of the tile belongs to one image
+        if (p.conv && p.rowbias) {
+          const int img = m_blk / (p.tiles_x * p.tiles_y);
+          if (img < p.conv_B) rb_row = p.rowbias + static_cast<long long>(img) * p.ldrb;
+        }
+        for (int i = et; i < BN; i += 256) {
+          const int nn = n_blk * BN + i;
+          float b = 0.f, c = 0.f;
+          if (nn < p.N) {
+            if (p.bias) b = __ldg(p.bias + nn);
+            if (rb_row) b += __ldg(rb_row + nn);
+            if (p.ln_stats) c = __ldg(p.ln_colsum + nn);
+          }
+          vec[i] = b;
+          vec[BN + i] = c;
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");  // the 8 epilogue warps
+      }
+      const bool gemm_rowbias = p.rowbias && !p.conv;  // GEMM mode: rows of a tile may belong to different samples
+
+      // LayerNorm-on-A: v = rstd * (acc - mean * colsum[n]) (+ folded bias); statistics of this thread's row
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (p.ln_stats && row_ok) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + orow);
+        ln_mean = st.x * p.ln_inv_k;
+        const float var = fmaxf(fmaf(st.y, p.ln_inv_k, -ln_mean * ln_mean), 0.f);
+        ln_rstd = rsqrtf(var + p.ln_eps);
+      }
+      float rs_sum = 0.f, rs_sq = 0.f;  // producer side: sums over this thread's columns of the rounded outputs
+
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
@@ -313,8 +382,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (p.bias) add32(v, p.bias + nw0, nw0);
-        if (p.rowbias && row_ok) add32(v, p.rowbias + static_cast<long long>(batch) * p.ldrb + nw0, nw0);
+        if (p.ln_stats) ln32s(v, vec + BN + c0, ln_mean, ln_rstd);
+        add32s(v, vec + c0);
+        if (gemm_rowbias && row_ok) add32(v, p.rowbias + static_cast<long long>(batch) * p.ldrb + nw0, nw0);
         if (geglu) {
           uint32_t graw[32];
           tmem_ld32(t_row + BN / 2 + c0, graw);
@@ -322,12 +392,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float g[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(graw[j]);
-          if (p.bias) add32(g, p.bias + nw0 + BN / 2, nw0 + BN / 2);
+          if (p.ln_stats) ln32s(g, vec + BN + BN / 2 + c0, ln_mean, ln_rstd);
+          add32s(g, vec + BN / 2 + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_fast(g[j]);
+          for (int j = 0; j < 32; ++j) v[j] *= gelu_sig5(g[j]);
         } else if (p.epilogue == DS_EPI_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_sig5(v[j]);
         } else if (p.epilogue == DS_EPI_SILU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
@@ -390,9 +461,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[q * 8 + e] *= p.out_scale;
               }
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(sp)),
-                           "r"(pack_bf16(v[q * 8 + 0], v[q * 8 + 1])), "r"(pack_bf16(v[q * 8 + 2], v[q * 8 + 3])),
-                           "r"(pack_bf16(v[q * 8 + 4], v[q * 8 + 5])), "r"(pack_bf16(v[q * 8 + 6], v[q * 8 + 7]))
+              const uint32_t o0 = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), o1 = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+              const uint32_t o2 = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), o3 = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              if (p.row_stats_out) {  // statistics for the next LayerNorm, from the fp32 values (the bf16 rounding
+                                      // of 1e3 row elements is unbiased: it moves mean / rstd by < 1e-4 relative)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  rs_sum += v[q * 8 + e];
+                  rs_sq = fmaf(v[q * 8 + e], v[q * 8 + e], rs_sq);
+                }
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(sp)), "r"(o0), "r"(o1), "r"(o2),
+                           "r"(o3)
                            : "memory");
             }
           }
@@ -417,6 +497,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         if (!released) release_acc(acc);  // this column half lies entirely beyond N
+        if (p.row_stats_out && row_ok) {  // columns beyond N contributed exact zeros
+          atomicAdd(p.row_stats_out + 2 * orow, rs_sum);
+          atomicAdd(p.row_stats_out + 2 * orow + 1, rs_sq);
+        }
         continue;
       }
 
@@ -577,6 +661,10 @@ static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& 
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.tma_epilogue = !p.out_fp32 && p.n_out % 8 == 0 && p.ldo % 8 == 0 && aligned16(p.out) &&
                    (!p.residual || (p.ldres % 8 == 0 && aligned16(p.residual)));
+  if (p.row_stats_out) {
+    DS_REQUIRE(p.tma_epilogue, "ds_gemm_bf16: row_stats_out needs a 16-byte addressable bf16 output");
+    DS_CUDA_OK(cudaMemsetAsync(p.row_stats_out, 0, sizeof(float) * 2 * static_cast<size_t>(p.M), stream));
+  }
   CUtensorMap tmC = tmA, tmR = tmA;  // placeholders when the direct epilogue is used
   if (p.tma_epilogue) {
     if (!make_out_map(&tmC, p.out, p, p.ldo, conv_B)) return DS_ERR_CUDA;
@@ -636,6 +724,16 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
   p.epilogue = a->epilogue;
   p.out_fp32 = a->out_fp32;
   p.out_scale = a->out_scale == 1.0f ? 0.0f : a->out_scale;
+  if (a->ln_stats) {
+    DS_REQUIRE(a->ln_colsum != nullptr, "ds_gemm_bf16: ln_stats needs ln_colsum");
+    DS_REQUIRE(a->rowbias == nullptr, "ds_gemm_bf16: ln_stats and rowbias are mutually exclusive");
+    DS_REQUIRE((reinterpret_cast<uintptr_t>(a->ln_stats) & 7) == 0, "ds_gemm_bf16: ln_stats must be 8-byte aligned");
+  }
+  p.ln_stats = a->ln_stats;
+  p.ln_colsum = a->ln_colsum;
+  p.ln_eps = a->ln_eps;
+  p.ln_inv_k = 1.0f / static_cast<float>(a->K);
+  p.row_stats_out = a->row_stats_out;
   p.num_m_tiles = (a->M + kBM - 1) / kBM;
   p.num_k_iters = (a->K + kBK - 1) / kBK;
   p.conv = 0;

@@ -211,6 +211,189 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// gn_fused_kernel — GroupNorm(+SiLU) in ONE pass over HBM: x is read once and y written once (the algorithmic
+// 4 B/element; the two-kernel path above reads x twice).
+//   * cooperative persistent grid, one CTA per SM.  Sample b is cut into gridDim.x contiguous pixel slices; CTA c
+//     owns slice c of EVERY sample and keeps it in shared memory (1-D bulk-async copies, NBUF-deep ring), so the
+//     second "pass" (normalise) reads shared memory, not HBM.
+//   * per sample: partial (sum, sum of squares) per group -> fp64 atomics in global memory -> arrival counter;
+//     a CTA normalises sample b only after all gridDim.x slices of b have arrived.  The wait is software-pipelined:
+//     the CTA accumulates the statistics of sample b+1 (already in its ring) before it waits for sample b, and the
+//     loads of samples b+2.. are in flight meanwhile, so HBM never idles on the barrier.
+//   * the spin on the arrival counter is bounded (trap), and the launch is cooperative, so a scheduling surprise
+//     is a launch error, not a hung GPU.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <bool kSilu>
+__global__ void __launch_bounds__(512, 1)
+gn_fused_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, double* __restrict__ stats,
+                unsigned int* __restrict__ arrived, const float* __restrict__ gamma, const float* __restrict__ beta,
+                int B, int HW, int C, int groups, float eps, int nbuf, int slice_stride) {
+  extern __shared__ uint8_t gsm_raw[];
+  uint8_t* gsm = gsm_raw + ((128u - (smem_u32(gsm_raw) & 127u)) & 127u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(gsm);           // [nbuf]
+  float* sh_part = reinterpret_cast<float*>(gsm + 64);          // [2*groups] CTA partials (groups <= 64)
+  float* sh_coef = sh_part + 128;                               // [2*groups] mean, rstd of the sample being applied
+  uint8_t* ring = gsm + 1152;                                   // nbuf x slice_stride bytes (128-B aligned)
+
+  const int cv = C >> 3;                 // 16-byte vectors per pixel
+  const int rpb = blockDim.x / cv;       // pixel rows per sweep
+  const int cvec = threadIdx.x % cv;
+  const int prow = threadIdx.x / cv;
+  const bool active = prow < rpb;        // blockDim.x is cv * rpb exactly, kept for clarity
+  const int cpg = C / groups;
+  // this CTA's pixel slice (same for every sample)
+  const int p0 = static_cast<int>(static_cast<long long>(blockIdx.x) * HW / gridDim.x);
+  const int p1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * HW / gridDim.x);
+  const int npx = p1 - p0;
+  const uint32_t bytes = static_cast<uint32_t>(npx) * C * 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nbuf; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue_load = [&](int b) {  // thread 0 only
+    uint64_t* bar = &full[b % nbuf];
+    if (bytes == 0) {
+      mbar_arrive(bar);
+      return;
+    }
+    mbar_arrive_expect_tx(bar, bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(x) + (static_cast<size_t>(b) * HW + p0) * C * 2;
+    uint8_t* dst = ring + static_cast<size_t>(b % nbuf) * slice_stride;
+    uint32_t off = 0;
+    while (off < bytes) {  // bulk copies of at most 64 KB
+      const uint32_t n = bytes - off < 65536u ? bytes - off : 65536u;
+      bulk_load_1d(dst + off, src + off, n, bar);
+      off += n;
+    }
+  };
+  if (threadIdx.x == 0)
+    for (int b = 0; b < nbuf && b < B; ++b) issue_load(b);
+
+  float ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ga[j] = __ldg(gamma + cvec * 8 + j);
+    be[j] = __ldg(beta + cvec * 8 + j);
+  }
+  const double inv_n = 1.0 / (static_cast<double>(HW) * cpg);
+
+  // statistics of sample b from its shared-memory slice -> global fp64 atomics -> arrival counter
+  auto do_stats = [&](int b) {
+    mbar_wait(&full[b % nbuf], (b / nbuf) & 1);
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sh_part[i] = 0.f;
+    __syncthreads();
+    const uint4* tile = reinterpret_cast<const uint4*>(ring + static_cast<size_t>(b % nbuf) * slice_stride);
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    if (active) {
+      for (int r = prow; r < npx; r += rpb) {
+        const uint4 u = tile[static_cast<size_t>(r) * cv + cvec];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = bf16_lo(w[j]), c = bf16_hi(w[j]);
+          s[2 * j] += a;
+          q[2 * j] = fmaf(a, a, q[2 * j]);
+          s[2 * j + 1] += c;
+          q[2 * j + 1] = fmaf(c, c, q[2 * j + 1]);
+        }
+      }
+      const int c0 = cvec * 8;
+      int g_run = c0 / cpg;
+      float rs = 0.f, rq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int g = (c0 + j) / cpg;
+        if (g != g_run) {
+          atomicAdd(&sh_part[2 * g_run], rs);
+          atomicAdd(&sh_part[2 * g_run + 1], rq);
+          g_run = g;
+          rs = rq = 0.f;
+        }
+        rs += s[j];
+        rq += q[j];
+      }
+      atomicAdd(&sh_part[2 * g_run], rs);
+      atomicAdd(&sh_part[2 * g_run + 1], rq);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
+      atomicAdd(&stats[static_cast<size_t>(b) * 2 * groups + i], static_cast<double>(sh_part[i]));
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(&arrived[b], 1u);
+  };
+
+  for (int b = 0; b < B; ++b) {
+    if (b == 0) do_stats(0);
+    if (b + 1 < B) do_stats(b + 1);  // its slice is already in the ring: hide sample b's barrier behind this work
+    // ---- wait until every CTA has contributed sample b's statistics
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      unsigned int v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(arrived + b) : "memory");
+        if (clock64() - t0 > 4000000000LL) __trap();
+      } while (v < gridDim.x);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < groups; i += blockDim.x) {
+      const double sum = __ldcg(&stats[static_cast<size_t>(b) * 2 * groups + 2 * i]);
+      const double sq = __ldcg(&stats[static_cast<size_t>(b) * 2 * groups + 2 * i + 1]);
+      const double mean = sum * inv_n;
+      double var = sq * inv_n - mean * mean;
+      var = var < 0.0 ? 0.0 : var;
+      sh_coef[2 * i] = static_cast<float>(mean);
+      sh_coef[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
+    // ---- normalise sample b from shared memory, write y
+    if (active) {
+      float sc[8], sf[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int g = (cvec * 8 + j) / cpg;
+        const float mean = sh_coef[2 * g], rstd = sh_coef[2 * g + 1];
+        sc[j] = rstd * ga[j];
+        sf[j] = be[j] - mean * rstd * ga[j];
+      }
+      const uint4* tile = reinterpret_cast<const uint4*>(ring + static_cast<size_t>(b % nbuf) * slice_stride);
+      uint4* yb = y + (static_cast<size_t>(b) * HW + p0) * cv + cvec;
+      for (int r = prow; r < npx; r += rpb) {
+        const uint4 u = tile[static_cast<size_t>(r) * cv + cvec];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = fmaf(bf16_lo(w[j]), sc[2 * j], sf[2 * j]);
+          float c = fmaf(bf16_hi(w[j]), sc[2 * j + 1], sf[2 * j + 1]);
+          if (kSilu) {
+            a = silu_tanh_f(a);
+            c = silu_tanh_f(c);
+          }
+          o[j] = pack_bf16_alu(a, c);
+        }
+        yb[static_cast<size_t>(r) * cv] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    // ---- recycle the ring slot: generic-proxy reads above must be ordered before the async-proxy refill
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0 && b + nbuf < B) issue_load(b + nbuf);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the whole row held in registers (two-pass mean / variance, fp32).
 // ------------------------------------------------------------------------------------------------
 template <int MAXV>
@@ -313,6 +496,57 @@ extern "C" int ds_groupnorm_silu(const void* x, void* y, const float* gamma, con
     return e ? atoi(e) : 1;
   }();
   double* dstats = reinterpret_cast<double*>(stats);
+  // ---- single-pass fused kernel when a sample's per-CTA slice fits a >= 2-deep shared-memory ring
+  static const int fused_env = [] {  // DS_GN_FUSED=0 forces the two-kernel path (A/B timing)
+    const char* e = getenv("DS_GN_FUSED");
+    return e ? atoi(e) : 1;
+  }();
+  if (fused_env && groups <= 64 && cv <= 512 && B <= 65536) {
+    const int fthreads = cv * (512 / cv);
+    const int grid = dev.num_sms;
+    const long long max_px = (static_cast<long long>(HW) + grid - 1) / grid + 1;
+    const long long slice_stride_ll = ((max_px * C * 2) + 127) / 128 * 128;
+    const int ring_budget = 200 * 1024;
+    int nbuf = static_cast<int>(ring_budget / slice_stride_ll);
+    if (nbuf > 4) nbuf = 4;
+    if (nbuf > B) nbuf = B;
+    if (nbuf >= 2 || (nbuf >= 1 && B == 1)) {
+      const int slice_stride = static_cast<int>(slice_stride_ll);
+      const size_t smem = 128 + 1152 + static_cast<size_t>(nbuf) * slice_stride;
+      const void* fn = apply_silu ? reinterpret_cast<const void*>(gn_fused_kernel<true>)
+                                  : reinterpret_cast<const void*>(gn_fused_kernel<false>);
+      static size_t attr_smem[2] = {0, 0};
+      if (smem > attr_smem[apply_silu ? 1 : 0]) {
+        DS_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        attr_smem[apply_silu ? 1 : 0] = smem;
+      }
+      // stats scratch (4*B*groups + 2*B floats): [B][2*groups] doubles, then B arrival counters
+      unsigned int* d_arrived = reinterpret_cast<unsigned int*>(dstats + static_cast<size_t>(2) * B * groups);
+      {
+        DS_CUDA_OK(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * B * groups + sizeof(unsigned int) * B, st));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(fthreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const uint4* xp = static_cast<const uint4*>(x);
+        uint4* yp = static_cast<uint4*>(y);
+        if (apply_silu)
+          DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel<true>, xp, yp, dstats, d_arrived, gamma, beta, B, HW, C,
+                                        groups, eps, nbuf, slice_stride));
+        else
+          DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel<false>, xp, yp, dstats, d_arrived, gamma, beta, B, HW, C,
+                                        groups, eps, nbuf, slice_stride));
+        DS_LAUNCH_OK("gn_fused_kernel");
+        return DS_OK;
+      }
+    }
+  }
   DS_CUDA_OK(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * B * groups, st));
   const size_t sh = sizeof(double) * 2 * groups;
   gn_stats_kernel<<<wave(reinterpret_cast<const void*>(gn_stats_kernel), sh), threads, sh, st>>>(

@@ -63,8 +63,8 @@ def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, gro
         raise DsEngineError("groupnorm_silu: gamma/beta must have C elements")
     out = torch.empty_like(x) if out is None else _req(out, bf16, "groupnorm_silu.out")
     if stats is None:
-        stats = torch.empty(4 * B * groups, dtype=f32, device=x.device)
-    elif stats.numel() < 4 * B * groups:
+        stats = torch.empty(4 * B * groups + 2 * B, dtype=f32, device=x.device)
+    elif stats.numel() < 4 * B * groups + 2 * B:
         raise DsEngineError("groupnorm_silu: stats scratch too small")
     check(lib.ds_groupnorm_silu(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
                                 B, HW, Cc, groups, eps, int(silu), _stream()), "ds_groupnorm_silu")
@@ -112,8 +112,14 @@ def ip_mask(bbox: torch.Tensor, seq_len: int, aspect_ratio: float, tokens_per_ip
 # ---------------------------------------------------------------------------------------------- GEMM / conv
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_NONE,
          residual: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
-         out: Optional[torch.Tensor] = None, out_fp32: bool = False, out_scale: float = 0.0) -> torch.Tensor:
-    """out[..., Nout] = epilogue(a[..., K] @ w[N, K]^T) on tcgen05; ``a`` may have any leading dims."""
+         out: Optional[torch.Tensor] = None, out_fp32: bool = False, out_scale: float = 0.0,
+         ln_stats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
+         row_stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[..., Nout] = epilogue(a[..., K] @ w[N, K]^T) on tcgen05; ``a`` may have any leading dims.
+
+    LayerNorm fusion (include/dsengine.h): ``ln_stats`` [2*M] fp32 {sum, sumsq} per row of ``a`` + ``ln_colsum`` [N]
+    turn the call into LayerNorm(a) @ w_orig^T for weights folded by ``weights.fold_layernorm``; ``row_stats_out``
+    [2*M] fp32 receives {sum, sumsq} of every (bf16-rounded) output row."""
     _req(a, bf16, "gemm.a")
     _req(w, bf16, "gemm.w", 2)
     K = a.shape[-1]
@@ -142,9 +148,22 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         _req(residual, bf16, "gemm.residual")
         if residual.numel() != M * n_out:
             raise DsEngineError("gemm: residual must match the output shape")
+    if ln_stats is not None:
+        _req(ln_stats, f32, "gemm.ln_stats", 1)
+        if ln_colsum is None:
+            raise DsEngineError("gemm: ln_stats needs ln_colsum")
+        _req(ln_colsum, f32, "gemm.ln_colsum", 1)
+        if ln_stats.numel() < 2 * M or ln_colsum.numel() != N:
+            raise DsEngineError("gemm: ln_stats must hold 2*M floats and ln_colsum N floats")
+    if row_stats_out is not None:
+        _req(row_stats_out, f32, "gemm.row_stats_out", 1)
+        if row_stats_out.numel() < 2 * M or out_fp32:
+            raise DsEngineError("gemm: row_stats_out must hold 2*M floats and needs a bf16 output")
     args = GemmArgs(a=a.data_ptr(), w=w.data_ptr(), out=out.data_ptr(), bias=_ptr(bias), rowbias=_ptr(rowbias),
                     residual=_ptr(residual), M=M, N=N, K=K, lda=K, ldw=K, ldo=n_out, ldres=n_out,
-                    rows_per_batch=rows_per_batch, rowbias_ld=rowbias_ld, epilogue=epilogue, out_fp32=int(out_fp32), out_scale=out_scale)
+                    rows_per_batch=rows_per_batch, rowbias_ld=rowbias_ld, epilogue=epilogue, out_fp32=int(out_fp32),
+                    out_scale=out_scale, ln_stats=_ptr(ln_stats), ln_colsum=_ptr(ln_colsum), ln_eps=float(ln_eps),
+                    row_stats_out=_ptr(row_stats_out))
     check(lib.ds_gemm_bf16(C.byref(args), _stream()), "ds_gemm_bf16")
     return out
 

@@ -26,7 +26,8 @@ import torch
 
 from . import ops
 from .config import UNetConfig
-from .weights import bf, fp, pack_conv3x3, pack_geglu, resnet_io, transformer_sites, unet_param_shapes
+from .weights import (bf, colsum_bf16, fold_layernorm, fp, pack_conv3x3, pack_geglu, resnet_io, transformer_sites,
+                      unet_param_shapes)
 
 bf16, f32 = torch.bfloat16, torch.float32
 
@@ -57,8 +58,8 @@ class _Resnet:
 
 
 class _Block:
-    __slots__ = ("n1", "n2", "n3", "wqkv", "wo1", "bo1", "wq2", "wo2", "bo2", "wkv_t", "wkv_ip", "wff1", "bff1",
-                 "wff2", "bff2", "layer")
+    __slots__ = ("n1", "n2", "n3", "wqkv", "bqkv", "cs_qkv", "wo1", "bo1", "wq2", "bq2", "cs_q2", "wo2", "bo2", "wkv_t",
+                 "wkv_ip", "wff1", "bff1", "cs_ff1", "wff2", "bff2", "layer")
 
 
 class _Transformer:
@@ -166,15 +167,23 @@ class UNetMangaEngine:
                 blk = _Block()
                 for i in (1, 2, 3):
                     setattr(blk, f"n{i}", (fp(W(f"{b}.norm{i}.weight")), fp(W(f"{b}.norm{i}.bias"))))
-                blk.wqkv = bf(torch.cat([W(f"{b}.attn1.to_q.weight"), W(f"{b}.attn1.to_k.weight"),
-                                         W(f"{b}.attn1.to_v.weight")], 0))
+                # norm1/2/3 are folded into the linears that consume them (weights.fold_layernorm); the GEMMs that
+                # produce the residual stream publish its row statistics (ops.gemm(..., row_stats_out=))
+                w, bb = fold_layernorm(torch.cat([W(f"{b}.attn1.to_q.weight"), W(f"{b}.attn1.to_k.weight"),
+                                                  W(f"{b}.attn1.to_v.weight")], 0), None, *blk.n1)
+                blk.wqkv, blk.bqkv = bf(w), fp(bb)
+                blk.cs_qkv = colsum_bf16(blk.wqkv)
                 blk.wo1, blk.bo1 = bf(W(f"{b}.attn1.to_out.0.weight")), fp(W(f"{b}.attn1.to_out.0.bias"))
-                blk.wq2 = bf(W(f"{b}.attn2.to_q.weight"))
+                w, bb = fold_layernorm(W(f"{b}.attn2.to_q.weight"), None, *blk.n2)
+                blk.wq2, blk.bq2 = bf(w), fp(bb)
+                blk.cs_q2 = colsum_bf16(blk.wq2)
                 blk.wkv_t = bf(torch.cat([W(f"{b}.attn2.to_k.weight"), W(f"{b}.attn2.to_v.weight")], 0))
                 blk.wkv_ip = bf(torch.cat([W(f"{b}.attn2.processor.to_k_ip.weight"),
                                            W(f"{b}.attn2.processor.to_v_ip.weight")], 0))
                 blk.wo2, blk.bo2 = bf(W(f"{b}.attn2.to_out.0.weight")), fp(W(f"{b}.attn2.to_out.0.bias"))
-                blk.wff1, blk.bff1 = pack_geglu(W(f"{b}.ff.net.0.proj.weight"), W(f"{b}.ff.net.0.proj.bias"))
+                w, bb = fold_layernorm(W(f"{b}.ff.net.0.proj.weight"), W(f"{b}.ff.net.0.proj.bias"), *blk.n3)
+                blk.wff1, blk.bff1 = pack_geglu(w, bb)
+                blk.cs_ff1 = colsum_bf16(blk.wff1)
                 blk.wff2, blk.bff2 = bf(W(f"{b}.ff.net.2.weight")), fp(W(f"{b}.ff.net.2.bias"))
                 blk.layer = layer
                 layer += 1
@@ -250,20 +259,27 @@ class UNetMangaEngine:
         t, cfg = self.transformers[p], self.cfg
         B, H, W, Cc = x.shape
         h = ops.groupnorm_silu(x, t.norm[0], t.norm[1], cfg.norm_num_groups, 1e-6, False)
-        h = ops.gemm(h.view(B, H * W, Cc), t.w_in, t.b_in)
+        M = B * H * W
+        # row statistics {sum, sum of squares} of the residual stream h, double-buffered: the GEMM that writes h
+        # publishes them, the next LayerNorm-folded GEMM consumes them (no stand-alone LayerNorm kernel, and h is
+        # read once instead of twice)
+        st = [torch.empty(2 * M, dtype=f32, device=x.device) for _ in range(2)]
+        cur = 0
+        h = ops.gemm(h.view(B, H * W, Cc), t.w_in, t.b_in, row_stats_out=st[cur])
         for blk in t.blocks:
-            n = ops.layernorm(h, blk.n1[0], blk.n1[1], 1e-5)
-            a = ops.attention_self(ops.gemm(n, blk.wqkv), t.heads, out=n)
-            h = ops.gemm(a, blk.wo1, blk.bo1, residual=h, out=h)
-            n = ops.layernorm(h, blk.n2[0], blk.n2[1], 1e-5, out=n)
-            q = ops.gemm(n, blk.wq2)
+            qkv = ops.gemm(h, blk.wqkv, blk.bqkv, ln_stats=st[cur], ln_colsum=blk.cs_qkv, ln_eps=1e-5)
+            a = ops.attention_self(qkv, t.heads)
+            h = ops.gemm(a, blk.wo1, blk.bo1, residual=h, out=h, row_stats_out=st[cur ^ 1])
+            cur ^= 1
+            q = ops.gemm(h, blk.wq2, blk.bq2, ln_stats=st[cur], ln_colsum=blk.cs_q2, ln_eps=1e-5, out=a)
             a = ops.attention_cross_ip(q, cond.kv_text[blk.layer], cond.kv_ip[blk.layer], cond.bbox, t.heads,
-                                       cond.aspect_ratio, self.ip_scale, cfg.num_vision_tokens, cfg.num_dummy_tokens,
-                                       out=n)
-            h = ops.gemm(a, blk.wo2, blk.bo2, residual=h, out=h)
-            n = ops.layernorm(h, blk.n3[0], blk.n3[1], 1e-5, out=n)
-            f = ops.gemm(n, blk.wff1, blk.bff1, epilogue=ops.EPI_GEGLU)
-            h = ops.gemm(f, blk.wff2, blk.bff2, residual=h, out=h)
+                                       cond.aspect_ratio, self.ip_scale, cfg.num_vision_tokens, cfg.num_dummy_tokens)
+            h = ops.gemm(a, blk.wo2, blk.bo2, residual=h, out=h, row_stats_out=st[cur ^ 1])
+            cur ^= 1
+            f = ops.gemm(h, blk.wff1, blk.bff1, epilogue=ops.EPI_GEGLU, ln_stats=st[cur], ln_colsum=blk.cs_ff1,
+                         ln_eps=1e-5)
+            h = ops.gemm(f, blk.wff2, blk.bff2, residual=h, out=h, row_stats_out=st[cur ^ 1])
+            cur ^= 1
         return ops.gemm(h, t.w_out, t.b_out, residual=x.view(B, H * W, Cc)).view(B, H, W, Cc)
 
     # ------------------------------------------------------------------------------------------ forward

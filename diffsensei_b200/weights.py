@@ -200,6 +200,23 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor, block: int = 128):
     return wp.reshape(2 * n, -1).contiguous().to(torch.bfloat16), bp.reshape(2 * n).contiguous().to(torch.float32)
 
 
+def fold_layernorm(w: torch.Tensor, b, gamma: torch.Tensor, beta: torch.Tensor):
+    """LayerNorm folded into the linear that consumes it (ds_gemm_bf16 "consumer" mode, include/dsengine.h):
+    LN(x) W^T + b = rstd * (x W'^T - mean * colsum) + b'   with  W' = W * gamma,  b' = b + W beta,
+    colsum[n] = sum_k W'[n][k] taken over the bf16-ROUNDED W' (exactly what the tensor core sums, so a constant
+    row cancels exactly).  Returns (W' fp32 — the caller rounds / packs it, b' fp32)."""
+    wf = w.detach().float()
+    w2 = wf * gamma.detach().float()[None, :]
+    b2 = wf @ beta.detach().float()
+    if b is not None:
+        b2 = b2 + b.detach().float()
+    return w2, b2
+
+
+def colsum_bf16(w_packed: torch.Tensor) -> torch.Tensor:
+    return w_packed.float().sum(dim=1).contiguous()
+
+
 def bf(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.bfloat16).contiguous()
 

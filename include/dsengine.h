@@ -42,10 +42,13 @@ uint64_t ds_launch_count(void);
  * src/models/unet.py:251-261,281-290,316-338.
  *   x, y      : [B][HW][C] bf16 (y may alias x)
  *   gamma/beta: [C] fp32
- *   stats     : scratch, 4*B*groups floats (= 2*B*groups doubles: per-(sample, group) sum and sum of
- *               squares), 8-byte aligned; zeroed, written and read by the call itself
+ *   stats     : scratch, 4*B*groups + 2*B floats (2*B*groups doubles: per-(sample, group) sum and sum of
+ *               squares, then B arrival counters), 8-byte aligned; zeroed, written and read by the call itself
  * Per-thread partial sums are fp32, every cross-thread accumulation is fp64; normalisation + affine +
- * SiLU run in fp32 with one rounding to bf16.
+ * SiLU run in fp32 with one rounding to bf16.  Whenever a sample's per-SM slice fits a >= 2-deep shared-memory
+ * ring (every ResnetBlock2D / Transformer2DModel norm of the cfg2 UNet except the 640/960-channel ones at
+ * 128x128) the op is ONE cooperative kernel that reads x once and writes y once; otherwise a statistics kernel
+ * followed by an apply kernel.
  * --------------------------------------------------------------------------------------------- */
 int ds_groupnorm_silu(const void* x, void* y, const float* gamma, const float* beta, float* stats, int B, int HW,
                       int C, int groups, float eps, int apply_silu, void* stream);
@@ -86,9 +89,18 @@ int ds_ip_mask(const float* bbox, float* mask, int B, int N, double aspect_ratio
  *   v = acc + bias[n] + rowbias[row / rows_per_batch][n]
  *   DS_EPI_GEGLU: W/bias rows are packed in blocks of 128 "value" rows followed by their 128 "gate"
  *                 rows (see diffsensei_b200.weights.pack_geglu); out[:, j] = v_val * gelu_erf(v_gate),
- *                 Nout = N/2.
+ *                 Nout = N/2.  gelu_erf(x) = x * Phi(x) is evaluated as x * sigmoid(2k(x + a x^3 + b x^5)) with
+ *                 (k, a, b) fitted to Phi: |abs err| <= 2.6e-5 for all x (the bf16 output rounding is >= 10x larger).
  *   DS_EPI_GELU / DS_EPI_SILU : v = act(v)
  *   then v += residual[row][n] (bf16) and v *= out_scale (if != 0).
+ * LayerNorm fusion (diffusers BasicTransformerBlock.norm1/2/3 -> the linears on either side of them):
+ *   consumer: with ln_stats != NULL, A holds the UN-normalised rows and the caller passes pre-folded weights
+ *             W' = W * gamma (per input feature), bias' = bias + W beta, ln_colsum[n] = sum_k W'[n][k]; then
+ *             acc is replaced by rstd[row] * (acc - mean[row] * ln_colsum[n]) before anything else, where
+ *             mean = sum/K, rstd = rsqrt(sumsq/K - mean^2 + ln_eps) from ln_stats[row] = {sum, sumsq}.
+ *             Algebraically identical to LayerNorm(A) W^T + bias.
+ *   producer: with row_stats_out != NULL the call zeroes it, then accumulates {sum, sum of squares} of every
+ *             bf16-ROUNDED output row (what the next LayerNorm reads) — bf16 outputs with 16-byte rows only.
  * Constraints: K % 8 == 0, lda % 8 == 0 (16-byte TMA strides). M, N, K tails are handled by TMA
  * zero-fill and masked stores.
  * --------------------------------------------------------------------------------------------- */
@@ -111,6 +123,10 @@ typedef struct {
   int32_t epilogue;       /* DS_EPI_*                                      */
   int32_t out_fp32;       /* 1: `out` is fp32                              */
   float out_scale;        /* 0 or 1: no scaling                            */
+  const float* ln_stats;  /* [M][2] fp32 (sum, sumsq) of A's rows, or NULL  */
+  const float* ln_colsum; /* [N] fp32; required with ln_stats               */
+  float ln_eps;
+  float* row_stats_out;   /* [M][2] fp32 or NULL (see "producer" above)     */
 } ds_gemm_args;
 
 int ds_gemm_bf16(const ds_gemm_args* args, void* stream);

@@ -83,3 +83,26 @@ def test_pipeline_check_inputs_raises_like_reference():
     with pytest.raises(ValueError, match="must have the same length as `ip_bbox`"):
         pipe.check_inputs("a", None, [object(), object()], None, [[0, 0, 1, 1]])
     pipe.check_inputs("a", None, [object()], None, [[0, 0, 1, 1]])
+
+
+def test_fold_layernorm_is_algebraically_layernorm_then_linear():
+    """weights.fold_layernorm + the ds_gemm_bf16 "consumer" epilogue formula (include/dsengine.h) restated in fp64:
+    rstd * (x W'^T - mean * colsum) + b'  ==  LayerNorm(x) W^T + b."""
+    import torch
+    from diffsensei_b200.weights import fold_layernorm
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(37, 96, generator=g, dtype=torch.float64) * 3 + 1.5
+    w = torch.randn(50, 96, generator=g, dtype=torch.float64) / 10
+    b = torch.randn(50, generator=g, dtype=torch.float64)
+    gamma = 1 + 0.2 * torch.randn(96, generator=g, dtype=torch.float64)
+    beta = 0.3 * torch.randn(96, generator=g, dtype=torch.float64)
+    want = torch.nn.functional.layer_norm(x, (96,), gamma, beta, 1e-5) @ w.T + b
+    w2, b2 = fold_layernorm(w, b, gamma, beta)
+    w2, b2 = w2.double(), b2.double()
+    s, q = x.sum(1), (x * x).sum(1)
+    mean = s / 96
+    rstd = (q / 96 - mean * mean + 1e-5).rsqrt()
+    got = rstd[:, None] * (x @ w2.T - mean[:, None] * w2.sum(1)[None, :]) + b2
+    assert (got - want).abs().max() < 1e-5      # fold_layernorm computes in fp32
+    w3, b3 = fold_layernorm(w, None, gamma, beta)
+    assert torch.allclose(b3.double(), w @ beta, atol=1e-5)

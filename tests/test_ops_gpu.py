@@ -118,6 +118,37 @@ def test_gemm_activations_and_rowbias(ops):
     assert rel_l2(ops.gemm(a.to(DEV), w.to(DEV), epilogue=ops.EPI_GELU).float(), F.gelu(F.linear(a.float(), w.float()))) < 6e-3
 
 
+@pytest.mark.parametrize("M,N,K,geglu", [(300, 200, 72, False), (1024, 1920, 640, False), (333, 1024, 128, True),
+                                          (4096, 640, 640, False)])
+def test_gemm_layernorm_fusion(ops, M, N, K, geglu):
+    """BasicTransformerBlock: h = linear(attn) + h ; y = linear2(LayerNorm(h)).  The first GEMM publishes the row
+    statistics of h, the second consumes them with LayerNorm folded into its weights (weights.fold_layernorm)."""
+    from diffsensei_b200.weights import colsum_bf16, fold_layernorm, pack_geglu
+    a0, w0 = _r(M, 96, seed=20), _r(K, 96, seed=21, scale=96 ** -0.5)
+    b0, res = torch.randn(K) * 0.3, _r(M, K, seed=22) * 2 + 0.7          # row mean != 0 on purpose
+    gamma, beta = torch.randn(K) * 0.2 + 1, torch.randn(K) * 0.1
+    w1, b1 = _r(N, K, seed=23, scale=K ** -0.5), torch.randn(N) * 0.2
+    stats = torch.full((2 * M,), 7.0, device=DEV)                          # the call must zero it first
+    h = ops.gemm(a0.to(DEV), w0.to(DEV), b0.to(DEV), residual=res.to(DEV), row_stats_out=stats)
+    hf = h.float().cpu()
+    st = stats.cpu().view(M, 2)
+    assert torch.allclose(st[:, 0], hf.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(st[:, 1], (hf * hf).sum(1), rtol=1e-4, atol=1e-2)
+    ln = F.layer_norm(hf, (K,), gamma, beta, 1e-5)
+    w2, b2 = fold_layernorm(w1.float(), b1, gamma, beta)
+    if geglu:
+        val, gate = F.linear(ln, w1.float(), b1).chunk(2, dim=-1)
+        want = val * F.gelu(gate)
+        wp, bp = pack_geglu(w2, b2)
+        got = ops.gemm(h, wp.to(DEV), bp.to(DEV), epilogue=ops.EPI_GEGLU, ln_stats=stats,
+                       ln_colsum=colsum_bf16(wp).to(DEV), ln_eps=1e-5)
+    else:
+        want = F.linear(ln, w1.float(), b1)
+        wp = w2.to(bf16)
+        got = ops.gemm(h, wp.to(DEV), b2.to(DEV), ln_stats=stats, ln_colsum=colsum_bf16(wp).to(DEV), ln_eps=1e-5)
+    assert rel_l2(got.float(), want) < 8e-3
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 16, 24, 64, 128, 1), (2, 19, 13, 128, 64, 1),
                                                    (1, 16, 32, 64, 128, 2), (2, 19, 13, 64, 64, 2),
                                                    (1, 8, 8, 320, 4, 1), (2, 32, 32, 192, 320, 1)])
