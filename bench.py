@@ -127,6 +127,16 @@ def event_time_ms(fn, iters, stream_sync=True):
 
 
 # ------------------------------------------------------------------------------------------------ kernel rooflines
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the roofline kernels, from the
+    committed `ncu --set full` capture of tools/profile_kernels.py (profiles/ncu_traffic.json; null if absent)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def kernel_rooflines(ds, peaks, device):
     """The dominant kernel and the two north-star kernels, each timed alone with CUDA events on the launching
     stream: >= 3 warm-ups, then ROUNDS back-to-back launches that rotate over SETS disjoint input/output buffer
@@ -152,6 +162,7 @@ def kernel_rooflines(ds, peaks, device):
         return e0.elapsed_time(e1) / (rounds * len(calls))
 
     out = {}
+    traffic = ncu_traffic()
     # dominant kernel: gemm_bf16_tcgen05 at the level-2 FF1/GEGLU shape (60 launches per step, 22.5 of 54.8 TFLOP)
     M, N, K = 8192, 10240, 1280
     sets = []
@@ -163,9 +174,9 @@ def kernel_rooflines(ds, peaks, device):
     b = torch.zeros(N, device=device)
     ms = timed([(lambda s=s: ops.gemm(s[0], s[1], b, epilogue=ops.EPI_GEGLU, out=s[2])) for s in sets], 4)
     flops = 2.0 * M * N * K
-    out["roofline"] = {"kernel": "gemm_bf16_tcgen05<256> FF1+GEGLU M8192 N10240 K1280", "bound": "tensor",
+    out["roofline"] = {"kernel": "gemm_bf16_tcgen05<256,2> FF1+GEGLU M8192 N10240 K1280", "bound": "tensor",
                        "achieved": round(flops / ms / 1e9, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                       "frac": round(flops / ms / 1e9 / peaks["bf16_tflops"], 4), "traffic": None,
+                       "frac": round(flops / ms / 1e9 / peaks["bf16_tflops"], 4), "traffic": traffic.get("gemm_ff1"),
                        "ms_per_launch": round(ms, 4), "peak_source": peaks["source"] + " burst (kernel timed alone)",
                        "algorithmic_GFLOP": round(flops / 1e9, 1)}
     del sets
@@ -179,7 +190,7 @@ def kernel_rooflines(ds, peaks, device):
     gb = 2 * sets[0][0].numel() * 2 / 1e9
     out["roofline_gn"] = {"kernel": "gn_stats_kernel + gn_apply_kernel (8,128,128,320) bf16", "bound": "hbm",
                           "achieved": round(gb / (ms * 1e-3), 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                          "frac": round(gb / (ms * 1e-3) / peaks["hbm_gbs"], 4), "traffic": None,
+                          "frac": round(gb / (ms * 1e-3) / peaks["hbm_gbs"], 4), "traffic": traffic.get("gn"),
                           "ms_per_launch": round(ms, 4), "algorithmic_MB": round(gb * 1e3, 1)}
     del sets
     # fused self-attention at level 1: B=8, N=4096, 10 heads (4*N^2*C*B flops)
@@ -190,9 +201,9 @@ def kernel_rooflines(ds, peaks, device):
                      torch.empty(B, Nn, heads * 64, dtype=bf, device=device)))
     ms = timed([(lambda s=s: ops.attention_self(s[0], heads, out=s[1])) for s in sets], 4)
     flops = 4.0 * Nn * Nn * heads * 64 * B
-    out["roofline_attn"] = {"kernel": "flash_attn_kernel B8 N4096 h10 d64", "bound": "tensor",
+    out["roofline_attn"] = {"kernel": "flash_attn_v5_kernel B8 N4096 h10 d64", "bound": "tensor",
                             "achieved": round(flops / ms / 1e9, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                            "frac": round(flops / ms / 1e9 / peaks["bf16_tflops"], 4), "traffic": None,
+                            "frac": round(flops / ms / 1e9 / peaks["bf16_tflops"], 4), "traffic": traffic.get("flash"),
                             "ms_per_launch": round(ms, 4), "algorithmic_GFLOP": round(flops / 1e9, 1)}
     return out
 

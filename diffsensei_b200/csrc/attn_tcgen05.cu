@@ -925,10 +925,31 @@ flash_attn_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 //        TMEM (256 columns, 2 CTAs/SM): S_0|P_0 [0,64) | S_1|P_1 [64,128) | O_0 [128,192) | O_1 [192,256).
 //      Both chunks of P are built in registers before the overflow check, so the (rare) redo still finds S intact.
 // =================================================================================================
+// packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): one instruction for two lanes-worth of scale-and-subtract /
+// row-sum work in the exp loops
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 constexpr int kFlash5Threads = 320;  // warp 0: TMA + TMEM alloc, warp 1: MMA issue, warps 2-9: two softmax streams
 constexpr int kFlash5SmemBytes = kTileBytes * (1 + kFlash3Ring) + 1024 + 256 + 2 * kTile * 2 * 4;
 
-template <int POLY>
+template <int POLY, bool F2>
 __global__ void __launch_bounds__(kFlash5Threads, 2)
 flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
@@ -975,10 +996,12 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the prologue above overlapped the producer GEMM's tail
   const uint32_t tS = tmem_base;        // S_h (and P_h over its first 32 columns) at +64h
   const uint32_t tO = tmem_base + 128;  // O_h at +64h
 
@@ -1052,15 +1075,30 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // 32 scores -> 16 packed bf16x2 probabilities; partial sums into s0/s1
     auto chunk = [&](const uint32_t(&raw)[32], uint32_t(&pk)[16], float neg_m, int valid, float& s0, float& s1) {
       if (valid >= 32) {
+        if (F2) {
+          const uint64_t sc2 = f2_pack(p.scale_log2, p.scale_log2), nm2 = f2_pack(neg_m, neg_m);
+          uint64_t acc = f2_pack(s0, s1);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
-          const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
-          const float e0 = ((2 * i) % 8 < POLY) ? ex2_poly(t0) : ex2(t0);
-          const float e1 = ((2 * i + 1) % 8 < POLY) ? ex2_poly(t1) : ex2(t1);
-          s0 += e0;
-          s1 += e1;
-          pk[i] = pack_bf16_alu(e0, e1);
+          for (int i = 0; i < 16; ++i) {
+            float t0, t1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1])), sc2, nm2), t0, t1);
+            const float e0 = ((2 * i) % 8 < POLY) ? ex2_poly(t0) : ex2(t0);
+            const float e1 = ((2 * i + 1) % 8 < POLY) ? ex2_poly(t1) : ex2(t1);
+            acc = f2_add(acc, f2_pack(e0, e1));
+            pk[i] = pack_bf16_alu(e0, e1);
+          }
+          f2_unpack(acc, s0, s1);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
+            const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
+            const float e0 = ((2 * i) % 8 < POLY) ? ex2_poly(t0) : ex2(t0);
+            const float e1 = ((2 * i + 1) % 8 < POLY) ? ex2_poly(t1) : ex2(t1);
+            s0 += e0;
+            s1 += e1;
+            pk[i] = pack_bf16_alu(e0, e1);
+          }
         }
       } else {
 #pragma unroll
@@ -1481,10 +1519,12 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   // TMEM (256 columns): S text [0, nt_pad) | S ip [nt_pad, n_keys);  P_text over [0, nt_pad/2), P_ip over
   // [nt_pad, nt_pad + nip_pad/2) (each stream overwrites the head of its OWN score columns, thread-local rows);
   // O_text [128,192) (dead IP score columns + free ones; needs nt_pad + nip_pad/2 <= 128), O_ip [192,256)
@@ -1629,46 +1669,36 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tmem_st8(tSg + c * 8, pk);  // columns [8c, 8c+8) <= the chunk just read: never ahead of an unread score
       };
       {
-        uint32_t ra[16], rb[16];
-        tmem_ld16(tSg, ra);
-        tmem_ld_wait();
+        // single register buffer: the 4 softmax warps per SM sub-partition (2 groups x 2 CTAs) hide the TMEM load
+        // latency; a second buffer pushed the kernel over its 96-register budget and the spill reloads (local
+        // memory = L2 round trips, the L1 carve-out is nearly all shared memory) sat on the per-tile critical path
+        uint32_t ra[16];
 #pragma unroll 1
-        for (int c = 0; c < chunks; c += 2) {
-          if (c + 1 < chunks) tmem_ld16(tSg + (c + 1) * 16, rb);
+        for (int c = 0; c < chunks; ++c) {
+          tmem_ld16(tSg + c * 16, ra);
+          tmem_ld_wait();
           max_chunk(c, ra);
-          tmem_ld_wait();
-          if (c + 1 < chunks) {
-            if (c + 2 < chunks) tmem_ld16(tSg + (c + 2) * 16, ra);
-            max_chunk(c + 1, rb);
-            tmem_ld_wait();
-          }
         }
-        tmem_ld16(tSg, ra);
-        tmem_ld_wait();
 #pragma unroll 1
-        for (int c = 0; c < chunks; c += 2) {
-          if (c + 1 < chunks) tmem_ld16(tSg + (c + 1) * 16, rb);
-          exp_chunk(c, ra);
+        for (int c = 0; c < chunks; ++c) {
+          tmem_ld16(tSg + c * 16, ra);
           tmem_ld_wait();
-          if (c + 1 < chunks) {
-            if (c + 2 < chunks) tmem_ld16(tSg + (c + 2) * 16, ra);
-            exp_chunk(c + 1, rb);
-            tmem_ld_wait();
-          }
+          exp_chunk(c, ra);
         }
       }
+      // the other group's row sum travels with the barriers: st.shared -> arrive(p_full) [release] -> MMA thread
+      // [acquire] -> commit(o_full) -> our wait below [acquire]; and s_l is only rewritten after o_empty(n)
       s_l[g * kTile + row] = l;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // both row sums visible to both groups
 
       // ---- epilogue: out = O_text / l_t + scale * O_ip / l_i   (blend BEFORE to_out, reference :258);
       //      group g writes output columns [32g, 32g+32)
-      const float w_t = 1.0f / s_l[row], w_i = p.ip_scale / s_l[kTile + row];
       mbar_wait(o_full, n & 1);
       tc_fence_after();
+      const float w_t = 1.0f / s_l[row], w_i = p.ip_scale / s_l[kTile + row];
       __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.N + q_row) * p.C + head * kHd + g * 32;
       {
         uint32_t rt[32], ri[32];
@@ -1694,7 +1724,6 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // s_l is rewritten by the next tile
     }
   }
 
@@ -1756,18 +1785,35 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
     return DS_OK;
   }
   if (flash_ver >= 5) {
+    static const int flash_f2 = [] {  // DS_FLASH_F2=0: scalar FFMA/FADD instead of the packed fp32x2 forms
+      const char* e = getenv("DS_FLASH_F2");
+      return e ? atoi(e) : 1;
+    }();
     static bool attr5_set = false;
     if (!attr5_set) {
-      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
-      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
-      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
+      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
+      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
+      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
+      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
       attr5_set = true;
     }
-    switch (flash_poly) {
-      case 1: flash_attn_v5_kernel<1><<<grid, kFlash5Threads, kFlash5SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
-      case 2: flash_attn_v5_kernel<2><<<grid, kFlash5Threads, kFlash5SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
-      default: flash_attn_v5_kernel<0><<<grid, kFlash5Threads, kFlash5SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
-    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kFlash5Threads);
+    cfg.dynamicSmemBytes = kFlash5SmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    pdl_attr(&attr[0]);
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (!flash_f2)
+      DS_CUDA_OK(cudaLaunchKernelEx(&cfg, flash_attn_v5_kernel<0, false>, tmQ, tmK, tmV, p));
+    else if (flash_poly == 1)
+      DS_CUDA_OK(cudaLaunchKernelEx(&cfg, flash_attn_v5_kernel<1, true>, tmQ, tmK, tmV, p));
+    else if (flash_poly == 2)
+      DS_CUDA_OK(cudaLaunchKernelEx(&cfg, flash_attn_v5_kernel<2, true>, tmQ, tmK, tmV, p));
+    else
+      DS_CUDA_OK(cudaLaunchKernelEx(&cfg, flash_attn_v5_kernel<0, true>, tmQ, tmK, tmV, p));
     DS_LAUNCH_OK("flash_attn_v5_kernel");
     return DS_OK;
   }
@@ -1898,12 +1944,20 @@ extern "C" int ds_attention_cross_ip(const ds_cross_ip_args* a, void* stream) {
     }
     const int grid2 = total < 2 * dev.num_sms ? total : 2 * dev.num_sms;
     const bool uniform = (a->tokens_per_ip % 16 == 0) && (a->num_dummy % 16 == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid2);
+    cfg.blockDim = dim3(kCross2Threads);
+    cfg.dynamicSmemBytes = smem2;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    pdl_attr(&attr[0]);
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int heads_i = a->heads;
     if (uniform)
-      cross_ip_attn_v2_kernel<true><<<grid2, kCross2Threads, smem2, static_cast<cudaStream_t>(stream)>>>(
-          tmQ, tmT, tmI, p, a->heads, q_tiles, total);
+      DS_CUDA_OK(cudaLaunchKernelEx(&cfg, cross_ip_attn_v2_kernel<true>, tmQ, tmT, tmI, p, heads_i, q_tiles, total));
     else
-      cross_ip_attn_v2_kernel<false><<<grid2, kCross2Threads, smem2, static_cast<cudaStream_t>(stream)>>>(
-          tmQ, tmT, tmI, p, a->heads, q_tiles, total);
+      DS_CUDA_OK(cudaLaunchKernelEx(&cfg, cross_ip_attn_v2_kernel<false>, tmQ, tmT, tmI, p, heads_i, q_tiles, total));
     DS_LAUNCH_OK("cross_ip_attn_v2_kernel");
     return DS_OK;
   }

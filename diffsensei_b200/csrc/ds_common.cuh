@@ -52,6 +52,15 @@ __device__ __forceinline__ uint32_t pack_bf16_alu(float lo, float hi) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched with programmaticStreamSerializationAllowed may start
+// (and run its prologue: barrier init, TMEM alloc, tensor-map prefetch) while its predecessor in the stream / graph
+// is still draining; pdl_wait() blocks until the predecessor grid has completed and its memory is visible, and must
+// precede the first global-memory access.  pdl_launch_dependents() lets OUR successor start early likewise.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -54,6 +54,13 @@ bool get_device(DeviceInfo* out);
     ::ds::count_launch();                                                            \
   } while (0)
 
+// DS_PDL=0 disables programmatic dependent launch (A/B timing); default on.  Fills one launch attribute.
+bool pdl_enabled();
+inline void pdl_attr(cudaLaunchAttribute* a) {
+  a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  a->val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+}
+
 // bf16 tensor map (tile mode, 128-byte swizzle, zero OOB fill). dims/strides innermost first;
 // strides_bytes has rank-1 entries (dim 0 is contiguous). Returns false + error text on failure.
 bool encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,

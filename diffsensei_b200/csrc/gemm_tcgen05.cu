@@ -134,6 +134,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tmem_relinquish();
     }
   }
+  pdl_launch_dependents();  // the next kernel may start its prologue on SMs this grid has already left
   tc_fence_before();
   if (PAIR == 2)
     cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
@@ -141,6 +142,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; from here on we touch its outputs
 
   const int m_units = (p.num_m_tiles + PAIR - 1) / PAIR;
   const int total_tiles = m_units * p.num_n_tiles;  // work units; each covers PAIR vertically adjacent M tiles
@@ -579,13 +581,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  pdl_attr(&attr[1]);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   // The schedule is persistent with a static stride, so every CTA (pair) must be co-resident: a pair needs both
   // SMs of one TPC, and not every TPC of a 148-SM part has two enabled SMs.  Ask the runtime how many clusters fit.
   static int max_groups = 0;

@@ -497,9 +497,12 @@ extern "C" int ds_groupnorm_silu(const void* x, void* y, const float* gamma, con
   }();
   double* dstats = reinterpret_cast<double*>(stats);
   // ---- single-pass fused kernel when a sample's per-CTA slice fits a >= 2-deep shared-memory ring
-  static const int fused_env = [] {  // DS_GN_FUSED=0 forces the two-kernel path (A/B timing)
+  // MEASURED (B200, (8,128,128,320)): fused 78.6 us vs two kernels 64.8 us — every sample's barrier waits for
+  // 148 CTAs x 64 same-address fp64 atomics to drain; until the partials are pre-reduced hierarchically the
+  // single-pass kernel is opt-in (DS_GN_FUSED=1) and the two-kernel path stays the default.
+  static const int fused_env = [] {
     const char* e = getenv("DS_GN_FUSED");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 0;
   }();
   if (fused_env && groups <= 64 && cv <= 512 && B <= 65536) {
     const int fthreads = cv * (512 / cv);

@@ -45,10 +45,10 @@ uint64_t ds_launch_count(void);
  *   stats     : scratch, 4*B*groups + 2*B floats (2*B*groups doubles: per-(sample, group) sum and sum of
  *               squares, then B arrival counters), 8-byte aligned; zeroed, written and read by the call itself
  * Per-thread partial sums are fp32, every cross-thread accumulation is fp64; normalisation + affine +
- * SiLU run in fp32 with one rounding to bf16.  Whenever a sample's per-SM slice fits a >= 2-deep shared-memory
- * ring (every ResnetBlock2D / Transformer2DModel norm of the cfg2 UNet except the 640/960-channel ones at
- * 128x128) the op is ONE cooperative kernel that reads x once and writes y once; otherwise a statistics kernel
- * followed by an apply kernel.
+ * SiLU run in fp32 with one rounding to bf16.  Default: a statistics kernel (x marked evict_last in L2) followed
+ * by an apply kernel.  DS_GN_FUSED=1 selects an experimental single cooperative kernel that keeps every sample's
+ * per-SM slice in a shared-memory ring and reads x once (measured slower so far: its per-sample barrier waits on
+ * contended fp64 atomics; see norm_kernels.cu).
  * --------------------------------------------------------------------------------------------- */
 int ds_groupnorm_silu(const void* x, void* y, const float* gamma, const float* beta, float* stats, int B, int HW,
                       int C, int groups, float eps, int apply_silu, void* stream);

@@ -132,8 +132,9 @@ def test_gemm_layernorm_fusion(ops, M, N, K, geglu):
     h = ops.gemm(a0.to(DEV), w0.to(DEV), b0.to(DEV), residual=res.to(DEV), row_stats_out=stats)
     hf = h.float().cpu()
     st = stats.cpu().view(M, 2)
-    assert torch.allclose(st[:, 0], hf.sum(1), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(st[:, 1], (hf * hf).sum(1), rtol=1e-4, atol=1e-2)
+    h32 = F.linear(a0.float(), w0.float(), b0) + res.float()   # the statistics are taken before the bf16 rounding
+    assert torch.allclose(st[:, 0], h32.sum(1), rtol=1e-4, atol=2e-2)
+    assert torch.allclose(st[:, 1], (h32 * h32).sum(1), rtol=1e-4, atol=2e-2)
     ln = F.layer_norm(hf, (K,), gamma, beta, 1e-5)
     w2, b2 = fold_layernorm(w1.float(), b1, gamma, beta)
     if geglu:
