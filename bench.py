@@ -185,7 +185,7 @@ def kernel_rooflines(ds, peaks, device):
     sets = []
     for i in range(4):                                   # 4 x (84 + 84 MB) = 671 MB > L2
         x = torch.randn(8, 128, 128, 320, device=device).to(bf)
-        sets.append((x, torch.empty_like(x), torch.empty(4 * 8 * 32 + 16, device=device)))
+        sets.append((x, torch.empty_like(x), torch.empty(ops.groupnorm_scratch_floats(8, 32), device=device)))
     ms = timed([(lambda s=s: ops.groupnorm_silu(s[0], ga, be, 32, 1e-5, True, out=s[1], stats=s[2])) for s in sets], 4)
     gb = 2 * sets[0][0].numel() * 2 / 1e9
     out["roofline_gn"] = {"kernel": "gn_stats_kernel + gn_apply_kernel (8,128,128,320) bf16", "bound": "hbm",

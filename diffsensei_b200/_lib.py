@@ -69,7 +69,7 @@ SIGNATURES = {
     "ds_cfg_ddim_step": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp],
     "ds_resampler_attn": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
 }
-OTHER_EXPORTS = ("ds_version", "ds_last_error", "ds_launch_count")
+OTHER_EXPORTS = ("ds_version", "ds_last_error", "ds_launch_count", "ds_groupnorm_scratch_floats")
 
 
 def _load() -> C.CDLL:
@@ -85,6 +85,8 @@ def _load() -> C.CDLL:
     lib.ds_version.restype = C.c_int
     lib.ds_last_error.restype = C.c_char_p
     lib.ds_launch_count.restype = C.c_uint64
+    lib.ds_groupnorm_scratch_floats.argtypes = [C.c_int, C.c_int]
+    lib.ds_groupnorm_scratch_floats.restype = C.c_int64
     return lib
 
 

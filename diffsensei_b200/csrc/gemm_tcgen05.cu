@@ -69,7 +69,7 @@ struct GemmCfg {
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStages = (192512 / (kABytes + kBBytes)) > 8 ? 8 : (192512 / (kABytes + kBBytes));
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kTmemCols = 2 * BN <= 256 ? 256 : 512;  // tcgen05.alloc wants a power of two
   static constexpr int kStageOutBytes = 2 * kBM * 64 * 2;  // two [128][64] bf16 epilogue staging tiles (one per column half)
   static constexpr int kVecBytes = 2 * 2 * BN * 4;         // double-buffered per-tile copies of bias[BN] and ln_colsum[BN]
   static constexpr int kSmemBytes =
@@ -250,7 +250,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int half = (warp - 4) >> 2;    // which half of the tile's output columns
     const bool geglu = p.epilogue == DS_EPI_GEGLU;
     const int bn_out = geglu ? BN / 2 : BN;
-    const int c_begin = half * (bn_out / 2), c_end = c_begin + bn_out / 2;
+    // the tile's output columns are handed to the two warp groups in 64-column blocks (BN = 192: 2 + 1 blocks)
+    const int split = ((bn_out / 64 + 1) / 2) * 64;
+    const int c_begin = half ? split : 0, c_end = half ? bn_out : (split < bn_out ? split : bn_out);
     const bool vec_ok = (p.n_out % 8 == 0) && (p.ldo % 8 == 0) && (!p.residual || p.ldres % 8 == 0);
 
     // v[j] += src[j] (src already offset to the chunk's first column n0), guarded by n0 + j < N
@@ -619,11 +621,14 @@ static int pick_bn(int N, int epilogue) {
     const char* e = getenv("DS_GEMM_BN");
     return e ? atoi(e) : 0;
   }();
-  if (bn_env == 128 || bn_env == 256) return bn_env;
+  if (bn_env == 128 || bn_env == 192 || bn_env == 256) return bn_env;
   // BN=256 tiles run the tensor pipe ~1.3-1.5x faster per FLOP than BN=128 ones (smem operand traffic, see GemmCfg),
   // so they win unless more than ~20 % of the last N tile would be padding (N=640 -> 3 x 256 is still better)
-  const double e256 = static_cast<double>(N) / (((N + 255) / 256) * 256);
-  return e256 >= 0.8 ? 256 : 128;
+  // MEASURED (B200, conv 8x128x128 320->320): BN=128 pair tiles 334 us, BN=256 (second n-tile 3/4 padding) 239 us:
+  // the narrow tiles are shared-memory-port bound (A + B + TMA fill per MMA cycle), so wide tiles win even when they
+  // compute padding.  BN=192 (3 x 64-column blocks) is used where it trims >= 15 % of the padded columns.
+  const int c256 = ((N + 255) / 256) * 256, c192 = ((N + 191) / 192) * 192;
+  return (c192 * 100 <= c256 * 85) ? 192 : 256;
 }
 
 // Output / residual tensor maps for the TMA epilogue: plain GEMM = 2-D {n_out, M}, box {64, 128};
@@ -677,9 +682,11 @@ static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& 
   p.conv_B = conv_B;
   if (pair == 2) {
     if (bn == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
+    if (bn == 192) return launch_gemm<192, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
     return launch_gemm<128, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
   }
   if (bn == 256) return launch_gemm<256, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
+  if (bn == 192) return launch_gemm<192, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
   return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
 }
 

@@ -232,22 +232,24 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 
 template <bool kSilu>
 __global__ void __launch_bounds__(512, 1)
-gn_fused_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, double* __restrict__ stats,
+gn_fused_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, float* __restrict__ partials,
                 unsigned int* __restrict__ arrived, const float* __restrict__ gamma, const float* __restrict__ beta,
                 int B, int HW, int C, int groups, float eps, int nbuf, int slice_stride) {
   extern __shared__ uint8_t gsm_raw[];
   uint8_t* gsm = gsm_raw + ((128u - (smem_u32(gsm_raw) & 127u)) & 127u);
   uint64_t* full = reinterpret_cast<uint64_t*>(gsm);           // [nbuf]
-  float* sh_part = reinterpret_cast<float*>(gsm + 64);          // [2*groups] CTA partials (groups <= 64)
-  float* sh_coef = sh_part + 128;                               // [2*groups] mean, rstd of the sample being applied
-  uint8_t* ring = gsm + 1152;                                   // nbuf x slice_stride bytes (128-B aligned)
+  double* sh_part = reinterpret_cast<double*>(gsm + 64);        // [2*groups] CTA partials, fp64 so that the order of
+                                                                // the shared-memory atomics cannot change the result
+  float* sh_coef = reinterpret_cast<float*>(gsm + 64 + 1024);   // [2*groups] mean, rstd of the sample being applied
+  float* sh_red = sh_coef + 128;                                // [8][2*groups] chunked column sums of the partials
+  uint8_t* ring = gsm + 5760;                                   // nbuf x slice_stride bytes
 
   const int cv = C >> 3;                 // 16-byte vectors per pixel
-  const int rpb = blockDim.x / cv;       // pixel rows per sweep
+  const int rpb = blockDim.x / cv;       // pixel rows per sweep (blockDim.x == cv * rpb)
   const int cvec = threadIdx.x % cv;
   const int prow = threadIdx.x / cv;
-  const bool active = prow < rpb;        // blockDim.x is cv * rpb exactly, kept for clarity
   const int cpg = C / groups;
+  const int G2 = 2 * groups;
   // this CTA's pixel slice (same for every sample)
   const int p0 = static_cast<int>(static_cast<long long>(blockIdx.x) * HW / gridDim.x);
   const int p1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * HW / gridDim.x);
@@ -286,49 +288,49 @@ gn_fused_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, double* __re
   }
   const double inv_n = 1.0 / (static_cast<double>(HW) * cpg);
 
-  // statistics of sample b from its shared-memory slice -> global fp64 atomics -> arrival counter
+  // statistics of sample b from its shared-memory slice -> this CTA's row of the partials table -> arrival counter.
+  // No global atomics except the counter: 148 CTAs x 64 same-address fp64 atomics per sample were what made the
+  // first version slower than the two-kernel path.
   auto do_stats = [&](int b) {
     mbar_wait(&full[b % nbuf], (b / nbuf) & 1);
-    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sh_part[i] = 0.f;
+    for (int i = threadIdx.x; i < G2; i += blockDim.x) sh_part[i] = 0.0;
     __syncthreads();
     const uint4* tile = reinterpret_cast<const uint4*>(ring + static_cast<size_t>(b % nbuf) * slice_stride);
     float s[8], q[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    if (active) {
-      for (int r = prow; r < npx; r += rpb) {
-        const uint4 u = tile[static_cast<size_t>(r) * cv + cvec];
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int r = prow; r < npx; r += rpb) {
+      const uint4 u = tile[static_cast<size_t>(r) * cv + cvec];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float a = bf16_lo(w[j]), c = bf16_hi(w[j]);
-          s[2 * j] += a;
-          q[2 * j] = fmaf(a, a, q[2 * j]);
-          s[2 * j + 1] += c;
-          q[2 * j + 1] = fmaf(c, c, q[2 * j + 1]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float a = bf16_lo(w[j]), c = bf16_hi(w[j]);
+        s[2 * j] += a;
+        q[2 * j] = fmaf(a, a, q[2 * j]);
+        s[2 * j + 1] += c;
+        q[2 * j + 1] = fmaf(c, c, q[2 * j + 1]);
       }
-      const int c0 = cvec * 8;
-      int g_run = c0 / cpg;
-      float rs = 0.f, rq = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int g = (c0 + j) / cpg;
-        if (g != g_run) {
-          atomicAdd(&sh_part[2 * g_run], rs);
-          atomicAdd(&sh_part[2 * g_run + 1], rq);
-          g_run = g;
-          rs = rq = 0.f;
-        }
-        rs += s[j];
-        rq += q[j];
-      }
-      atomicAdd(&sh_part[2 * g_run], rs);
-      atomicAdd(&sh_part[2 * g_run + 1], rq);
     }
+    const int c0 = cvec * 8;
+    int g_run = c0 / cpg;
+    double rs = 0.0, rq = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c0 + j) / cpg;
+      if (g != g_run) {
+        atomicAdd(&sh_part[2 * g_run], rs);
+        atomicAdd(&sh_part[2 * g_run + 1], rq);
+        g_run = g;
+        rs = rq = 0.0;
+      }
+      rs += static_cast<double>(s[j]);
+      rq += static_cast<double>(q[j]);
+    }
+    atomicAdd(&sh_part[2 * g_run], rs);
+    atomicAdd(&sh_part[2 * g_run + 1], rq);
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
-      atomicAdd(&stats[static_cast<size_t>(b) * 2 * groups + i], static_cast<double>(sh_part[i]));
+    float* mine = partials + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * G2;
+    for (int i = threadIdx.x; i < G2; i += blockDim.x) __stcg(mine + i, static_cast<float>(sh_part[i]));
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicAdd(&arrived[b], 1u);
@@ -337,7 +339,7 @@ gn_fused_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, double* __re
   for (int b = 0; b < B; ++b) {
     if (b == 0) do_stats(0);
     if (b + 1 < B) do_stats(b + 1);  // its slice is already in the ring: hide sample b's barrier behind this work
-    // ---- wait until every CTA has contributed sample b's statistics
+    // ---- wait until every CTA has published sample b's partial statistics
     if (threadIdx.x == 0) {
       const long long t0 = clock64();
       unsigned int v;
@@ -347,18 +349,35 @@ gn_fused_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, double* __re
       } while (v < gridDim.x);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < groups; i += blockDim.x) {
-      const double sum = __ldcg(&stats[static_cast<size_t>(b) * 2 * groups + 2 * i]);
-      const double sq = __ldcg(&stats[static_cast<size_t>(b) * 2 * groups + 2 * i + 1]);
-      const double mean = sum * inv_n;
-      double var = sq * inv_n - mean * mean;
-      var = var < 0.0 ? 0.0 : var;
-      sh_coef[2 * i] = static_cast<float>(mean);
-      sh_coef[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    // ---- column sums of the [gridDim.x][2*groups] partials table in a fixed order (deterministic)
+    {
+      const int col = threadIdx.x % G2, chunk = threadIdx.x / G2;  // blockDim.x >= 448 >= 7 * 64 when groups = 32
+      const int nchunks = blockDim.x / G2 < 8 ? blockDim.x / G2 : 8;
+      if (chunk < nchunks) {
+        const int per = (gridDim.x + nchunks - 1) / nchunks;
+        const int r0 = chunk * per, r1 = min(r0 + per, static_cast<int>(gridDim.x));
+        const float* tab = partials + static_cast<size_t>(b) * gridDim.x * G2 + col;
+        float acc = 0.f;
+        for (int r = r0; r < r1; ++r) acc += __ldcg(tab + static_cast<size_t>(r) * G2);
+        sh_red[chunk * G2 + col] = acc;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < groups; i += blockDim.x) {
+        double sum = 0.0, sq = 0.0;
+        for (int c = 0; c < nchunks; ++c) {
+          sum += static_cast<double>(sh_red[c * G2 + 2 * i]);
+          sq += static_cast<double>(sh_red[c * G2 + 2 * i + 1]);
+        }
+        const double mean = sum * inv_n;
+        double var = sq * inv_n - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        sh_coef[2 * i] = static_cast<float>(mean);
+        sh_coef[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      }
+      __syncthreads();
     }
-    __syncthreads();
     // ---- normalise sample b from shared memory, write y
-    if (active) {
+    {
       float sc[8], sf[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -497,25 +516,27 @@ extern "C" int ds_groupnorm_silu(const void* x, void* y, const float* gamma, con
   }();
   double* dstats = reinterpret_cast<double*>(stats);
   // ---- single-pass fused kernel when a sample's per-CTA slice fits a >= 2-deep shared-memory ring
-  // MEASURED (B200, (8,128,128,320)): fused 78.6 us vs two kernels 64.8 us — every sample's barrier waits for
-  // 148 CTAs x 64 same-address fp64 atomics to drain; until the partials are pre-reduced hierarchically the
-  // single-pass kernel is opt-in (DS_GN_FUSED=1) and the two-kernel path stays the default.
+  // MEASURED (B200, (8,128,128,320), 167.8 MB algorithmic): two kernels 64.8 us; fused with fp64 global atomics
+  // 78.6 us; fused with the partials table (this version) 87.5 us — one 480-thread CTA per SM does not have the
+  // thread-level parallelism to run its statistics / reduce / normalise phases at HBM pace (each sample costs a CTA
+  // ~10 us of serial work against 3.2 us of HBM time).  Opt-in (DS_GN_FUSED=1) until it is restructured with
+  // warp-specialised producer / normalise roles; the two-kernel path stays the default.
   static const int fused_env = [] {
     const char* e = getenv("DS_GN_FUSED");
     return e ? atoi(e) : 0;
   }();
-  if (fused_env && groups <= 64 && cv <= 512 && B <= 65536) {
+  if (fused_env && groups <= 64 && cv <= 512 && 512 / cv * cv >= 2 * groups) {
     const int fthreads = cv * (512 / cv);
     const int grid = dev.num_sms;
     const long long max_px = (static_cast<long long>(HW) + grid - 1) / grid + 1;
     const long long slice_stride_ll = ((max_px * C * 2) + 127) / 128 * 128;
-    const int ring_budget = 200 * 1024;
+    const int ring_budget = 215 * 1024;
     int nbuf = static_cast<int>(ring_budget / slice_stride_ll);
     if (nbuf > 4) nbuf = 4;
     if (nbuf > B) nbuf = B;
     if (nbuf >= 2 || (nbuf >= 1 && B == 1)) {
       const int slice_stride = static_cast<int>(slice_stride_ll);
-      const size_t smem = 128 + 1152 + static_cast<size_t>(nbuf) * slice_stride;
+      const size_t smem = 128 + 5760 + static_cast<size_t>(nbuf) * slice_stride;
       const void* fn = apply_silu ? reinterpret_cast<const void*>(gn_fused_kernel<true>)
                                   : reinterpret_cast<const void*>(gn_fused_kernel<false>);
       static size_t attr_smem[2] = {0, 0};
@@ -523,31 +544,31 @@ extern "C" int ds_groupnorm_silu(const void* x, void* y, const float* gamma, con
         DS_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr_smem[apply_silu ? 1 : 0] = smem;
       }
-      // stats scratch (4*B*groups + 2*B floats): [B][2*groups] doubles, then B arrival counters
-      unsigned int* d_arrived = reinterpret_cast<unsigned int*>(dstats + static_cast<size_t>(2) * B * groups);
-      {
-        DS_CUDA_OK(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * B * groups + sizeof(unsigned int) * B, st));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(fthreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeCooperative;
-        attr[0].val.cooperative = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        const uint4* xp = static_cast<const uint4*>(x);
-        uint4* yp = static_cast<uint4*>(y);
-        if (apply_silu)
-          DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel<true>, xp, yp, dstats, d_arrived, gamma, beta, B, HW, C,
-                                        groups, eps, nbuf, slice_stride));
-        else
-          DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel<false>, xp, yp, dstats, d_arrived, gamma, beta, B, HW, C,
-                                        groups, eps, nbuf, slice_stride));
-        DS_LAUNCH_OK("gn_fused_kernel");
-        return DS_OK;
-      }
+      // scratch (ds_groupnorm_scratch_floats): [4*B*groups floats: fp64 sums of the two-kernel path] [2*B: arrival
+      // counters] [B][num_sms][2*groups] fp32 partials
+      unsigned int* d_arrived = reinterpret_cast<unsigned int*>(stats + static_cast<size_t>(4) * B * groups);
+      float* d_partials = stats + static_cast<size_t>(4) * B * groups + 2 * B;
+      DS_CUDA_OK(cudaMemsetAsync(d_arrived, 0, sizeof(unsigned int) * B, st));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(fthreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      const uint4* xp = static_cast<const uint4*>(x);
+      uint4* yp = static_cast<uint4*>(y);
+      if (apply_silu)
+        DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel<true>, xp, yp, d_partials, d_arrived, gamma, beta, B, HW, C,
+                                      groups, eps, nbuf, slice_stride));
+      else
+        DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel<false>, xp, yp, d_partials, d_arrived, gamma, beta, B, HW, C,
+                                      groups, eps, nbuf, slice_stride));
+      DS_LAUNCH_OK("gn_fused_kernel");
+      return DS_OK;
     }
   }
   DS_CUDA_OK(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * B * groups, st));
@@ -565,6 +586,14 @@ extern "C" int ds_groupnorm_silu(const void* x, void* y, const float* gamma, con
         items_per_sample, ipx, total_items, l2_hints);
   DS_LAUNCH_OK("gn_apply_kernel");
   return DS_OK;
+}
+
+extern "C" int64_t ds_groupnorm_scratch_floats(int B, int groups) {
+  if (B <= 0 || groups <= 0) return 0;
+  int sms = 256;  // without a device: an upper bound for any sm_100 part
+  ds::DeviceInfo dev;
+  if (ds::get_device(&dev)) sms = dev.num_sms;
+  return static_cast<int64_t>(4) * B * groups + 2 * B + static_cast<int64_t>(B) * sms * 2 * groups;
 }
 
 extern "C" int ds_layernorm(const void* x, void* y, const float* gamma, const float* beta, int rows, int C, float eps,

@@ -50,6 +50,11 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 # ---------------------------------------------------------------------------------------------- norms
+def groupnorm_scratch_floats(B: int, groups: int) -> int:
+    """Floats of scratch ds_groupnorm_silu needs for a [B, ..., C] tensor (include/dsengine.h)."""
+    return int(lib.ds_groupnorm_scratch_floats(int(B), int(groups)))
+
+
 def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float,
                    silu: bool = True, out: Optional[torch.Tensor] = None,
                    stats: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -62,10 +67,11 @@ def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, gro
     if gamma.numel() != Cc or beta.numel() != Cc:
         raise DsEngineError("groupnorm_silu: gamma/beta must have C elements")
     out = torch.empty_like(x) if out is None else _req(out, bf16, "groupnorm_silu.out")
+    need = groupnorm_scratch_floats(B, groups)
     if stats is None:
-        stats = torch.empty(4 * B * groups + 2 * B, dtype=f32, device=x.device)
-    elif stats.numel() < 4 * B * groups + 2 * B:
-        raise DsEngineError("groupnorm_silu: stats scratch too small")
+        stats = torch.empty(need, dtype=f32, device=x.device)
+    elif stats.numel() < need:
+        raise DsEngineError(f"groupnorm_silu: stats scratch too small ({stats.numel()} < {need} floats)")
     check(lib.ds_groupnorm_silu(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
                                 B, HW, Cc, groups, eps, int(silu), _stream()), "ds_groupnorm_silu")
     return out

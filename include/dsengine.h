@@ -42,14 +42,16 @@ uint64_t ds_launch_count(void);
  * src/models/unet.py:251-261,281-290,316-338.
  *   x, y      : [B][HW][C] bf16 (y may alias x)
  *   gamma/beta: [C] fp32
- *   stats     : scratch, 4*B*groups + 2*B floats (2*B*groups doubles: per-(sample, group) sum and sum of
- *               squares, then B arrival counters), 8-byte aligned; zeroed, written and read by the call itself
- * Per-thread partial sums are fp32, every cross-thread accumulation is fp64; normalisation + affine +
- * SiLU run in fp32 with one rounding to bf16.  Default: a statistics kernel (x marked evict_last in L2) followed
- * by an apply kernel.  DS_GN_FUSED=1 selects an experimental single cooperative kernel that keeps every sample's
- * per-SM slice in a shared-memory ring and reads x once (measured slower so far: its per-sample barrier waits on
- * contended fp64 atomics; see norm_kernels.cu).
+ *   stats     : scratch of ds_groupnorm_scratch_floats(B, groups) floats, 8-byte aligned; zeroed, written and read
+ *               by the call itself.  Layout: 2*B*groups doubles (per-(sample, group) sum / sum of squares of the
+ *               two-kernel path) | 2*B arrival counters | [B][num_SMs][2*groups] fp32 per-CTA partial statistics.
+ * Per-thread partial sums are fp32, cross-CTA accumulation is fp64; normalisation + affine + SiLU run in fp32 with
+ * one rounding to bf16.  Default: a statistics kernel (x marked evict_last in L2) followed by an apply kernel.
+ * DS_GN_FUSED=1 selects an experimental single cooperative kernel that keeps every sample's per-SM pixel slice in a
+ * shared-memory ring and reads x once (per-CTA partials go through the table in the scratch, one arrival counter
+ * per sample; deterministic).  Measured slower so far (87 us vs 65 us at (8,128,128,320)), hence opt-in.
  * --------------------------------------------------------------------------------------------- */
+int64_t ds_groupnorm_scratch_floats(int B, int groups);
 int ds_groupnorm_silu(const void* x, void* y, const float* gamma, const float* beta, float* stats, int B, int HW,
                       int C, int groups, float eps, int apply_silu, void* stream);
 

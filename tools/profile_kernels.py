@@ -18,7 +18,7 @@ dev = torch.device("cuda:0")
 bf = torch.bfloat16
 r = lambda *s: torch.randn(*s, device=dev).to(bf)
 x = r(8, 128, 128, 320)
-ga, be, st = torch.ones(320, device=dev), torch.zeros(320, device=dev), torch.empty(4 * 8 * 32 + 16, device=dev)
+ga, be, st = torch.ones(320, device=dev), torch.zeros(320, device=dev), torch.empty(ops.groupnorm_scratch_floats(8, 32), device=dev)
 a1, w1, b1 = r(8192, 1280), r(10240, 1280) * 0.03, torch.zeros(10240, device=dev)
 a2, w2, b2, res2 = r(32768, 640), r(640, 640) * 0.04, torch.zeros(640, device=dev), r(32768, 640)
 a3, w3, b3, res3 = r(8192, 1280), r(1280, 1280) * 0.03, torch.zeros(1280, device=dev), r(8192, 1280)
