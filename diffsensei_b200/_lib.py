@@ -25,7 +25,7 @@ class GemmArgs(C.Structure):
                 ("rows_per_batch", C.c_int32), ("rowbias_ld", C.c_int32), ("epilogue", C.c_int32), ("out_fp32", C.c_int32),
                 ("out_scale", C.c_float),
                 ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float),
-                ("row_stats_out", C.c_void_p)]
+                ("row_stats_out", C.c_void_p), ("zero_rows", C.c_void_p), ("row_stats_zeroed", C.c_int32)]
 
 
 class Conv3x3Args(C.Structure):

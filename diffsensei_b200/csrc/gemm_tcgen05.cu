@@ -53,6 +53,7 @@ struct GemmParams {
   const float* ln_colsum;  // [N] sum_k W'[n][k]
   float ln_eps, ln_inv_k;
   float* row_stats_out;    // [M][2], accumulated with atomics (zeroed by the host wrapper), or NULL
+  float* zero_rows;        // [M][2] buffer whose rows this launch resets to 0 (the statistics buffer two hops ahead)
   int num_m_tiles, num_n_tiles, num_k_iters;
   // conv geometry
   int conv, stride, Ho, Wo, tiles_x, tiles_y, cin_chunks, conv_B;
@@ -372,7 +373,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const float var = fmaxf(fmaf(st.y, p.ln_inv_k, -ln_mean * ln_mean), 0.f);
         ln_rstd = rsqrtf(var + p.ln_eps);
       }
-      float rs_sum = 0.f, rs_sq = 0.f;  // producer side: sums over this thread's columns of the rounded outputs
+      float rs_sum = 0.f, rs_sq = 0.f;  // producer side: sums over this thread's columns of the outputs
+      if (p.zero_rows && n_blk == 0 && half == 0 && row_ok)
+        *reinterpret_cast<float2*>(p.zero_rows + 2 * orow) = make_float2(0.f, 0.f);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -648,7 +651,8 @@ static bool make_out_map(CUtensorMap* m, const void* base, const GemmParams& p, 
   return encode_tmap_bf16(m, base, 2, dims, strides, box, nullptr);
 }
 
-static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& p, int conv_B, cudaStream_t stream) {
+static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& p, int conv_B, cudaStream_t stream,
+                    bool row_stats_zeroed = false) {
   DeviceInfo dev;
   if (!get_device(&dev)) return DS_ERR_CUDA;
   const int bn = pick_bn(p.N, p.epilogue);
@@ -671,7 +675,8 @@ static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& 
                    (!p.residual || (p.ldres % 8 == 0 && aligned16(p.residual)));
   if (p.row_stats_out) {
     DS_REQUIRE(p.tma_epilogue, "ds_gemm_bf16: row_stats_out needs a 16-byte addressable bf16 output");
-    DS_CUDA_OK(cudaMemsetAsync(p.row_stats_out, 0, sizeof(float) * 2 * static_cast<size_t>(p.M), stream));
+    if (!row_stats_zeroed)
+      DS_CUDA_OK(cudaMemsetAsync(p.row_stats_out, 0, sizeof(float) * 2 * static_cast<size_t>(p.M), stream));
   }
   CUtensorMap tmC = tmA, tmR = tmA;  // placeholders when the direct epilogue is used
   if (p.tma_epilogue) {
@@ -744,10 +749,15 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
   p.ln_eps = a->ln_eps;
   p.ln_inv_k = 1.0f / static_cast<float>(a->K);
   p.row_stats_out = a->row_stats_out;
+  p.zero_rows = a->zero_rows;
+  if (a->zero_rows)
+    DS_REQUIRE((reinterpret_cast<uintptr_t>(a->zero_rows) & 7) == 0 && a->zero_rows != a->row_stats_out &&
+                   a->zero_rows != a->ln_stats,
+               "ds_gemm_bf16: zero_rows must be 8-byte aligned and distinct from ln_stats / row_stats_out");
   p.num_m_tiles = (a->M + kBM - 1) / kBM;
   p.num_k_iters = (a->K + kBK - 1) / kBK;
   p.conv = 0;
-  return run_gemm(tmA, a->w, a->ldw, p, 0, static_cast<cudaStream_t>(stream));
+  return run_gemm(tmA, a->w, a->ldw, p, 0, static_cast<cudaStream_t>(stream), a->row_stats_zeroed != 0);
 }
 
 extern "C" int ds_conv3x3_nhwc(const ds_conv3x3_args* a, void* stream) {

@@ -12,7 +12,10 @@ namespace ds {
 // Replaces UNet2DConditionModel.conv_in (src/models/unet.py:206).
 // ------------------------------------------------------------------------------------------------
 __global__ void conv_in_kernel(const uint2* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                               uint4* __restrict__ out, int H, int W, int Cout, int pix_per_cta) {
+                               uint4* __restrict__ out, int H, int W, int Cout, int grp_per_cta) {
+  // Work item = 4 consecutive output pixels of one row x 8 output channels: every weight read from shared memory
+  // feeds 4 FMAs (the one-pixel version re-read all 36 x 8 weights per output vector and was bound by the
+  // shared-memory port: 403 us for 84 MB of output).
   extern __shared__ float sw[];  // [36][Cout] then bias [Cout]
   float* sb = sw + 36 * Cout;
   for (int i = threadIdx.x; i < 36 * Cout; i += blockDim.x) {
@@ -24,44 +27,64 @@ __global__ void conv_in_kernel(const uint2* __restrict__ x, const float* __restr
   const int cv = Cout >> 3;
   const int b = blockIdx.y;
   const int HW = H * W;
-  const int p_begin = blockIdx.x * pix_per_cta;
-  const int p_end = min(p_begin + pix_per_cta, HW);
-  for (int idx = threadIdx.x; idx < (p_end - p_begin) * cv; idx += blockDim.x) {
-    const int pix = p_begin + idx / cv;
+  const int gpr = (W + 3) >> 2;            // 4-pixel groups per row
+  const int n_grp = H * gpr;
+  const int g_begin = blockIdx.x * grp_per_cta;
+  const int g_end = min(g_begin + grp_per_cta, n_grp);
+  const uint2* xb = x + static_cast<size_t>(b) * HW;
+  for (int idx = threadIdx.x; idx < (g_end - g_begin) * cv; idx += blockDim.x) {
+    const int grp = g_begin + idx / cv;
     const int cvec = idx % cv;
-    const int y = pix / W, xx = pix - y * W;
-    float acc[8];
+    const int y = grp / gpr, x0 = (grp - y * gpr) * 4;
+    float acc[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sb[cvec * 8 + j];
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[px][j] = sb[cvec * 8 + j];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int iy = y + r - 1;
       if (iy < 0 || iy >= H) continue;
+      float in[6][4];  // input columns x0-1 .. x0+4 of row iy (zero outside the image)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const int ix = x0 + c - 1;
+        uint2 u = make_uint2(0u, 0u);
+        if (ix >= 0 && ix < W) u = __ldg(xb + iy * W + ix);
+        in[c][0] = bf16_lo(u.x);
+        in[c][1] = bf16_hi(u.x);
+        in[c][2] = bf16_lo(u.y);
+        in[c][3] = bf16_hi(u.y);
+      }
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
-        const int ix = xx + s - 1;
-        if (ix < 0 || ix >= W) continue;
-        const uint2 u = __ldg(x + (static_cast<size_t>(b) * HW + iy * W + ix));
-        const float in[4] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y)};
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
           const float* wk = sw + ((r * 3 + s) * 4 + ci) * Cout + cvec * 8;
           const float4 w0 = *reinterpret_cast<const float4*>(wk);
           const float4 w1 = *reinterpret_cast<const float4*>(wk + 4);
-          acc[0] = fmaf(in[ci], w0.x, acc[0]);
-          acc[1] = fmaf(in[ci], w0.y, acc[1]);
-          acc[2] = fmaf(in[ci], w0.z, acc[2]);
-          acc[3] = fmaf(in[ci], w0.w, acc[3]);
-          acc[4] = fmaf(in[ci], w1.x, acc[4]);
-          acc[5] = fmaf(in[ci], w1.y, acc[5]);
-          acc[6] = fmaf(in[ci], w1.z, acc[6]);
-          acc[7] = fmaf(in[ci], w1.w, acc[7]);
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const float v = in[px + s][ci];
+            acc[px][0] = fmaf(v, w0.x, acc[px][0]);
+            acc[px][1] = fmaf(v, w0.y, acc[px][1]);
+            acc[px][2] = fmaf(v, w0.z, acc[px][2]);
+            acc[px][3] = fmaf(v, w0.w, acc[px][3]);
+            acc[px][4] = fmaf(v, w1.x, acc[px][4]);
+            acc[px][5] = fmaf(v, w1.y, acc[px][5]);
+            acc[px][6] = fmaf(v, w1.z, acc[px][6]);
+            acc[px][7] = fmaf(v, w1.w, acc[px][7]);
+          }
         }
       }
     }
-    out[(static_cast<size_t>(b) * HW + pix) * cv + cvec] =
-        make_uint4(pack_bf16(acc[0], acc[1]), pack_bf16(acc[2], acc[3]), pack_bf16(acc[4], acc[5]),
-                   pack_bf16(acc[6], acc[7]));
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      if (x0 + px < W)
+        out[(static_cast<size_t>(b) * HW + y * W + x0 + px) * cv + cvec] =
+            make_uint4(pack_bf16(acc[px][0], acc[px][1]), pack_bf16(acc[px][2], acc[px][3]),
+                       pack_bf16(acc[px][4], acc[px][5]), pack_bf16(acc[px][6], acc[px][7]));
+    }
   }
 }
 
@@ -187,12 +210,12 @@ extern "C" int ds_conv_in_3x3(const void* x, const float* w, const float* bias, 
     DS_CUDA_OK(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
-  const int HW = H * W;
-  int ppc = (B * HW + dev.num_sms * 2 - 1) / (dev.num_sms * 2);  // ~2 CTAs per SM: amortise the weight staging
-  if (ppc < 32) ppc = 32;
-  dim3 grid((HW + ppc - 1) / ppc, B);
+  const int n_grp = H * ((W + 3) / 4);  // 4-pixel groups per image
+  int gpc = (B * n_grp + dev.num_sms * 4 - 1) / (dev.num_sms * 4);  // ~4 CTAs per SM: amortise the weight staging
+  if (gpc < 8) gpc = 8;
+  dim3 grid((n_grp + gpc - 1) / gpc, B);
   conv_in_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint2*>(x), w, bias, static_cast<uint4*>(out), H, W, Cout, ppc);
+      static_cast<const uint2*>(x), w, bias, static_cast<uint4*>(out), H, W, Cout, gpc);
   DS_LAUNCH_OK("conv_in_kernel");
   return DS_OK;
 }

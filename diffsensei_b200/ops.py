@@ -120,7 +120,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          residual: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
          out: Optional[torch.Tensor] = None, out_fp32: bool = False, out_scale: float = 0.0,
          ln_stats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
-         row_stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         row_stats_out: Optional[torch.Tensor] = None, zero_rows: Optional[torch.Tensor] = None,
+         row_stats_zeroed: bool = False) -> torch.Tensor:
     """out[..., Nout] = epilogue(a[..., K] @ w[N, K]^T) on tcgen05; ``a`` may have any leading dims.
 
     LayerNorm fusion (include/dsengine.h): ``ln_stats`` [2*M] fp32 {sum, sumsq} per row of ``a`` + ``ln_colsum`` [N]
@@ -161,6 +162,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         _req(ln_colsum, f32, "gemm.ln_colsum", 1)
         if ln_stats.numel() < 2 * M or ln_colsum.numel() != N:
             raise DsEngineError("gemm: ln_stats must hold 2*M floats and ln_colsum N floats")
+    if zero_rows is not None:
+        _req(zero_rows, f32, "gemm.zero_rows", 1)
+        if zero_rows.numel() < 2 * M:
+            raise DsEngineError("gemm: zero_rows must hold 2*M floats")
     if row_stats_out is not None:
         _req(row_stats_out, f32, "gemm.row_stats_out", 1)
         if row_stats_out.numel() < 2 * M or out_fp32:
@@ -169,7 +174,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
                     residual=_ptr(residual), M=M, N=N, K=K, lda=K, ldw=K, ldo=n_out, ldres=n_out,
                     rows_per_batch=rows_per_batch, rowbias_ld=rowbias_ld, epilogue=epilogue, out_fp32=int(out_fp32),
                     out_scale=out_scale, ln_stats=_ptr(ln_stats), ln_colsum=_ptr(ln_colsum), ln_eps=float(ln_eps),
-                    row_stats_out=_ptr(row_stats_out))
+                    row_stats_out=_ptr(row_stats_out), zero_rows=_ptr(zero_rows),
+                    row_stats_zeroed=int(bool(row_stats_zeroed)))
     check(lib.ds_gemm_bf16(C.byref(args), _stream()), "ds_gemm_bf16")
     return out
 

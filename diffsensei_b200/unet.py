@@ -260,26 +260,34 @@ class UNetMangaEngine:
         B, H, W, Cc = x.shape
         h = ops.groupnorm_silu(x, t.norm[0], t.norm[1], cfg.norm_num_groups, 1e-6, False)
         M = B * H * W
-        # row statistics {sum, sum of squares} of the residual stream h, double-buffered: the GEMM that writes h
-        # publishes them, the next LayerNorm-folded GEMM consumes them (no stand-alone LayerNorm kernel, and h is
-        # read once instead of twice)
-        st = [torch.empty(2 * M, dtype=f32, device=x.device) for _ in range(2)]
-        cur = 0
-        h = ops.gemm(h.view(B, H * W, Cc), t.w_in, t.b_in, row_stats_out=st[cur])
+        # Row statistics {sum, sum of squares} of the residual stream h: the GEMM that writes h publishes them
+        # (producer k -> buffer k % 3), the next LayerNorm-folded GEMM consumes them and clears buffer (k + 2) % 3 for
+        # the producer two hops ahead — no stand-alone LayerNorm kernel, h is read once instead of twice, and after the
+        # first two producers of a transformer (which memset their buffer) no memset node either.
+        st = [torch.empty(2 * M, dtype=f32, device=x.device) for _ in range(3)]
+        k = 0
+
+        def produce(*a, **kw):
+            nonlocal k
+            out = ops.gemm(*a, row_stats_out=st[k % 3], row_stats_zeroed=k >= 2, **kw)
+            k += 1
+            return out
+
+        def consume(a, w, bias, cs, **kw):      # reads the statistics of the latest producer (k - 1)
+            return ops.gemm(a, w, bias, ln_stats=st[(k - 1) % 3], ln_colsum=cs, ln_eps=1e-5,
+                            zero_rows=st[(k + 1) % 3], **kw)
+
+        h = produce(h.view(B, H * W, Cc), t.w_in, t.b_in)
         for blk in t.blocks:
-            qkv = ops.gemm(h, blk.wqkv, blk.bqkv, ln_stats=st[cur], ln_colsum=blk.cs_qkv, ln_eps=1e-5)
+            qkv = consume(h, blk.wqkv, blk.bqkv, blk.cs_qkv)
             a = ops.attention_self(qkv, t.heads)
-            h = ops.gemm(a, blk.wo1, blk.bo1, residual=h, out=h, row_stats_out=st[cur ^ 1])
-            cur ^= 1
-            q = ops.gemm(h, blk.wq2, blk.bq2, ln_stats=st[cur], ln_colsum=blk.cs_q2, ln_eps=1e-5, out=a)
+            h = produce(a, blk.wo1, blk.bo1, residual=h, out=h)
+            q = consume(h, blk.wq2, blk.bq2, blk.cs_q2, out=a)
             a = ops.attention_cross_ip(q, cond.kv_text[blk.layer], cond.kv_ip[blk.layer], cond.bbox, t.heads,
                                        cond.aspect_ratio, self.ip_scale, cfg.num_vision_tokens, cfg.num_dummy_tokens)
-            h = ops.gemm(a, blk.wo2, blk.bo2, residual=h, out=h, row_stats_out=st[cur ^ 1])
-            cur ^= 1
-            f = ops.gemm(h, blk.wff1, blk.bff1, epilogue=ops.EPI_GEGLU, ln_stats=st[cur], ln_colsum=blk.cs_ff1,
-                         ln_eps=1e-5)
-            h = ops.gemm(f, blk.wff2, blk.bff2, residual=h, out=h, row_stats_out=st[cur ^ 1])
-            cur ^= 1
+            h = produce(a, blk.wo2, blk.bo2, residual=h, out=h)
+            f = consume(h, blk.wff1, blk.bff1, blk.cs_ff1, epilogue=ops.EPI_GEGLU)
+            h = produce(f, blk.wff2, blk.bff2, residual=h, out=h)
         return ops.gemm(h, t.w_out, t.b_out, residual=x.view(B, H * W, Cc)).view(B, H, W, Cc)
 
     # ------------------------------------------------------------------------------------------ forward

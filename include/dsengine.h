@@ -101,8 +101,11 @@ int ds_ip_mask(const float* bbox, float* mask, int B, int N, double aspect_ratio
  *             acc is replaced by rstd[row] * (acc - mean[row] * ln_colsum[n]) before anything else, where
  *             mean = sum/K, rstd = rsqrt(sumsq/K - mean^2 + ln_eps) from ln_stats[row] = {sum, sumsq}.
  *             Algebraically identical to LayerNorm(A) W^T + bias.
- *   producer: with row_stats_out != NULL the call zeroes it, then accumulates {sum, sum of squares} of every
- *             bf16-ROUNDED output row (what the next LayerNorm reads) — bf16 outputs with 16-byte rows only.
+ *   producer: with row_stats_out != NULL the call zeroes it (unless row_stats_zeroed), then accumulates {sum, sum
+ *             of squares} of every output row (fp32 values, before the bf16 rounding) — bf16 outputs with
+ *             16-byte rows only.  zero_rows != NULL: the call also resets that [M][2] buffer (the first n-tile of
+ *             every m-tile does it), which lets a chain of GEMMs rotate three statistics buffers without any
+ *             memset node: the consumer of buffer k clears buffer k+2.
  * Constraints: K % 8 == 0, lda % 8 == 0 (16-byte TMA strides). M, N, K tails are handled by TMA
  * zero-fill and masked stores.
  * --------------------------------------------------------------------------------------------- */
@@ -129,6 +132,8 @@ typedef struct {
   const float* ln_colsum; /* [N] fp32; required with ln_stats               */
   float ln_eps;
   float* row_stats_out;   /* [M][2] fp32 or NULL (see "producer" above)     */
+  float* zero_rows;       /* [M][2] fp32 or NULL: rows reset to 0 by this call */
+  int32_t row_stats_zeroed; /* 1: row_stats_out is already 0, skip the memset  */
 } ds_gemm_args;
 
 int ds_gemm_bf16(const ds_gemm_args* args, void* stream);

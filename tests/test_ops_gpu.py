@@ -148,6 +148,14 @@ def test_gemm_layernorm_fusion(ops, M, N, K, geglu):
         wp = w2.to(bf16)
         got = ops.gemm(h, wp.to(DEV), b2.to(DEV), ln_stats=stats, ln_colsum=colsum_bf16(wp).to(DEV), ln_eps=1e-5)
     assert rel_l2(got.float(), want) < 8e-3
+    # buffer rotation without memsets: the consumer clears a third buffer, a later producer accumulates into it
+    third = torch.full((2 * M,), 7.0, device=DEV)
+    if not geglu:
+        again = ops.gemm(h, wp.to(DEV), b2.to(DEV), ln_stats=stats, ln_colsum=colsum_bf16(wp).to(DEV), ln_eps=1e-5,
+                         zero_rows=third)
+        assert torch.equal(again, got) and torch.count_nonzero(third).item() == 0
+        ops.gemm(a0.to(DEV), w0.to(DEV), b0.to(DEV), residual=res.to(DEV), row_stats_out=third, row_stats_zeroed=True)
+        assert torch.allclose(third, stats, rtol=1e-5, atol=1e-3)
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 16, 24, 64, 128, 1), (2, 19, 13, 128, 64, 1),
