@@ -55,6 +55,10 @@ struct GemmParams {
   float* row_stats_out;    // [M][2], accumulated with atomics (zeroed by the host wrapper), or NULL
   float* zero_rows;        // [M][2] buffer whose rows this launch resets to 0 (the statistics buffer two hops ahead)
   int num_m_tiles, num_n_tiles, num_k_iters;
+  // tail split: work items [0, tail_start) are whole 128*PAIR x BN units; each of the remaining units (the partial last
+  // wave of the persistent schedule) is cut into tail_f column slices of BN / tail_f so that it spreads over
+  // tail_f x as many CTA pairs instead of leaving most SMs idle for a whole unit time.  tail_f = 1: off.
+  int tail_start, tail_f, total_items;
   // conv geometry
   int conv, stride, Ho, Wo, tiles_x, tiles_y, cin_chunks, conv_B;
 };
@@ -81,7 +85,7 @@ template <int BN, int PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                  const GemmParams p) {
+                  const __grid_constant__ CUtensorMap tmBt, const GemmParams p) {
   using Cfg = GemmCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::kStages;
   const uint32_t cta_rank = (PAIR == 2) ? cluster_ctarank() : 0u;  // rank inside the CTA pair; 0 = leader
@@ -145,8 +149,20 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel's tail; from here on we touch its outputs
 
-  const int m_units = (p.num_m_tiles + PAIR - 1) / PAIR;
-  const int total_tiles = m_units * p.num_n_tiles;  // work units; each covers PAIR vertically adjacent M tiles
+  const int total_tiles = p.total_items;  // work items: whole units, then the column slices of the tail units
+  // item -> (unit, first weight row n_org of its columns, its width bn_cur)
+  auto decode = [&](int item, int& unit, int& n_org, int& bn_cur) {
+    if (item < p.tail_start) {
+      unit = item;
+      bn_cur = BN;
+      n_org = (unit % p.num_n_tiles) * BN;
+    } else {
+      const int s = item - p.tail_start;
+      unit = p.tail_start + s / p.tail_f;
+      bn_cur = BN / p.tail_f;
+      n_org = (unit % p.num_n_tiles) * BN + (s % p.tail_f) * bn_cur;
+    }
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -154,8 +170,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
-        const int n_blk = tile % p.num_n_tiles;
-        const int m_blk = (tile / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
+        int unit, n_org, bn_cur;
+        decode(tile, unit, n_org, bn_cur);
+        const int m_blk = (unit / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
+        const bool slice = bn_cur != BN;
+        const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(bn_cur / PAIR) * (kBK * 2);
         int img = 0, x0 = 0, y0 = 0;
         if (p.conv) {
           const int per_img = p.tiles_x * p.tiles_y;
@@ -164,13 +183,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           y0 = (rem / p.tiles_x) * kConvTileH;
           x0 = (rem % p.tiles_x) * kConvTileW;
         }
-        const int b_row0 = n_blk * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
+        const int b_row0 = n_org + static_cast<int>(cta_rank) * (bn_cur / PAIR);
+        const CUtensorMap* mapB = slice ? &tmBt : &tmB;
         for (int kb = 0; kb < p.num_k_iters; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (PAIR == 1) {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           } else if (leader) {
-            mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);  // both CTAs' bytes land on this barrier
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);  // both CTAs' bytes land on this barrier
           } else {
             mbar_arrive_cluster(&full_bar[stage], 0);
           }
@@ -191,9 +211,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_load_2d(sA + stage * kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM);
           }
           if (PAIR == 2)
-            tma_load_2d_pair(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, b_row0);
+            tma_load_2d_pair(sB + stage * Cfg::kBBytes, mapB, &full_bar[stage], kb * kBK, b_row0);
           else
-            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, b_row0);
+            tma_load_2d(sB + stage * Cfg::kBBytes, mapB, &full_bar[stage], kb * kBK, b_row0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -204,11 +224,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && leader) {  // in a pair only the leader CTA issues (for both SMs' tensor cores)
-      constexpr uint32_t idesc = make_idesc_bf16(kBM * PAIR, BN, 0, 0);
+      constexpr uint32_t idesc_full = make_idesc_bf16(kBM * PAIR, BN, 0, 0);
+      const uint32_t idesc_slice = make_idesc_bf16(kBM * PAIR, BN / p.tail_f, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step, ++iter) {
+        const uint32_t idesc = tile < p.tail_start ? idesc_full : idesc_slice;
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -250,10 +272,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int wq = warp & 3;             // TMEM lane quadrant this warp may access
     const int half = (warp - 4) >> 2;    // which half of the tile's output columns
     const bool geglu = p.epilogue == DS_EPI_GEGLU;
-    const int bn_out = geglu ? BN / 2 : BN;
-    // the tile's output columns are handed to the two warp groups in 64-column blocks (BN = 192: 2 + 1 blocks)
-    const int split = ((bn_out / 64 + 1) / 2) * 64;
-    const int c_begin = half ? split : 0, c_end = half ? bn_out : (split < bn_out ? split : bn_out);
     const bool vec_ok = (p.n_out % 8 == 0) && (p.ldo % 8 == 0) && (!p.residual || p.ldres % 8 == 0);
 
     // v[j] += src[j] (src already offset to the chunk's first column n0), guarded by n0 + j < N
@@ -313,9 +331,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int tile = unit0; tile < total_tiles; tile += unit_step, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      const int n_blk = tile % p.num_n_tiles;
-      const int m_blk = (tile / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
+      int unit, n_org, bn_cur;
+      decode(tile, unit, n_org, bn_cur);
+      const int m_blk = (unit / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
       const int r_local = wq * 32 + lane;
+      const int bn_out = geglu ? bn_cur / 2 : bn_cur;          // output columns of this item (GEGLU items are never sliced)
+      const int no_org = geglu ? n_org / 2 : n_org;            // first output column
+      // the item's output columns are handed to the two warp groups in 64-column blocks (192: 2 + 1, 64: 1 + 0)
+      const int split = ((bn_out / 64 + 1) / 2) * 64;
+      const int c_begin = half ? split : 0, c_end = half ? bn_out : (split < bn_out ? split : bn_out);
 
       // row -> (valid, output row index, batch index)
       bool row_ok;
@@ -350,8 +374,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int img = m_blk / (p.tiles_x * p.tiles_y);
           if (img < p.conv_B) rb_row = p.rowbias + static_cast<long long>(img) * p.ldrb;
         }
-        for (int i = et; i < BN; i += 256) {
-          const int nn = n_blk * BN + i;
+        for (int i = et; i < bn_cur; i += 256) {
+          const int nn = n_org + i;
           float b = 0.f, c = 0.f;
           if (nn < p.N) {
             if (p.bias) b = __ldg(p.bias + nn);
@@ -374,7 +398,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ln_rstd = rsqrtf(var + p.ln_eps);
       }
       float rs_sum = 0.f, rs_sq = 0.f;  // producer side: sums over this thread's columns of the outputs
-      if (p.zero_rows && n_blk == 0 && half == 0 && row_ok)
+      if (p.zero_rows && n_org == 0 && half == 0 && row_ok)
         *reinterpret_cast<float2*>(p.zero_rows + 2 * orow) = make_float2(0.f, 0.f);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -383,7 +407,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       // accumulator chunk -> fp32 values with bias / row-bias / GEGLU / activation applied (no residual yet)
       auto load_chunk = [&](int c0, float(&v)[32]) {
-        const int nw0 = n_blk * BN + c0;  // weight-row index of column 0 of this chunk
+        const int nw0 = n_org + c0;  // weight-row index of column 0 of this chunk
         uint32_t raw[32];
         tmem_ld32(t_row + c0, raw);
         tmem_ld_wait();
@@ -427,7 +451,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         bool released = false;
         for (int cb = c_begin; cb < c_end; cb += 64) {
-          const int no0 = n_blk * bn_out + cb;  // first output column of this 64-wide block
+          const int no0 = no_org + cb;  // first output column of this 64-wide block
           if (no0 >= p.n_out) break;            // group-uniform
           // the previous TMA store must have finished READING the staging tile before anyone overwrites it
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -483,7 +507,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                            : "memory");
             }
           }
-          if (cb + 64 >= c_end || n_blk * bn_out + cb + 64 >= p.n_out) {
+          if (cb + 64 >= c_end || no_org + cb + 64 >= p.n_out) {
             // last block of this tile for this warp: TMEM is drained -> hand the accumulator back early
             release_acc(acc);
             released = true;
@@ -513,7 +537,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       // ---------------- direct path (fp32 output or rows that are not 16-byte addressable): per-thread row stores
       for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-        const int no0 = n_blk * bn_out + c0;  // output column of column 0 of this chunk
+        const int no0 = no_org + c0;  // output column of column 0 of this chunk
         if (no0 >= p.n_out) break;            // warp-uniform
         const bool full_chunk = vec_ok && (no0 + 32 <= p.n_out);
         float v[32];
@@ -573,7 +597,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 template <int BN, int PAIR>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                       const CUtensorMap& tmR, const GemmParams& p, int num_sms, cudaStream_t stream) {
+                       const CUtensorMap& tmR, const CUtensorMap& tmBt, const GemmParams& p_in, int num_sms,
+                       cudaStream_t stream) {
+  GemmParams p = p_in;
   using Cfg = GemmCfg<BN, PAIR>;
   static bool attr_set = false;  // benign race: idempotent
   if (!attr_set) {
@@ -611,8 +637,27 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
               PAIR == 2 ? "pairs" : "singles", num_sms);
   }
   const int groups = units < max_groups ? units : max_groups;
+  // tail split (see GemmParams): only for the 256-wide tiles, never for GEGLU (value | gate halves live in one tile)
+  // MEASURED (B200): neutral — FF2 91.1 vs 91.9 us, conv 1280 192.4 vs 192.1 us, step 60.2 vs 60.4 ms: a 64-column
+  // slice moves the whole A tile for a quarter of the math and is shared-memory-port bound at ~1/4 efficiency, so 48
+  // slices take as long as the 12 whole units they replace.  Opt-in (DS_GEMM_TAIL=1), covered by the native tests.
+  static const int tail_env = [] {
+    const char* e = getenv("DS_GEMM_TAIL");
+    return e ? atoi(e) : 0;
+  }();
+  p.tail_start = units;
+  p.tail_f = 1;
+  p.total_items = units;
+  if (tail_env && BN == 256 && p.epilogue != DS_EPI_GEGLU && units > groups) {
+    const int full = (units / groups) * groups, left = units - full;
+    if (left > 0 && left * 4 <= groups) {
+      p.tail_start = full;
+      p.tail_f = 4;
+      p.total_items = full + left * 4;
+    }
+  }
   cfg.gridDim = dim3(groups * PAIR);
-  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR>, tmA, tmB, tmC, tmR, p));
+  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR>, tmA, tmB, tmC, tmR, tmBt, p));
   DS_LAUNCH_OK("gemm_bf16_tcgen05");
   return DS_OK;
 }
@@ -662,12 +707,14 @@ static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& 
     return e ? atoi(e) : 1;
   }();
   const int pair = (pair_env != 0 && p.num_m_tiles >= 2) ? 2 : 1;
-  CUtensorMap tmB;
+  CUtensorMap tmB, tmBt;  // tmBt: the 64-column slices of the tail split (box rows = 64 / pair)
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
     const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn / pair)};
     if (!encode_tmap_bf16(&tmB, w, 2, dims, strides, box, nullptr)) return DS_ERR_CUDA;
+    const uint32_t box_t[2] = {kBK, static_cast<uint32_t>(64 / pair)};
+    if (!encode_tmap_bf16(&tmBt, w, 2, dims, strides, box_t, nullptr)) return DS_ERR_CUDA;
   }
   // coalesced TMA epilogue whenever the bf16 output (and residual) rows are 16-byte addressable
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -686,13 +733,13 @@ static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& 
   p.num_n_tiles = (p.N + bn - 1) / bn;
   p.conv_B = conv_B;
   if (pair == 2) {
-    if (bn == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
-    if (bn == 192) return launch_gemm<192, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
-    return launch_gemm<128, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
+    if (bn == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, tmBt, p, dev.num_sms, stream);
+    if (bn == 192) return launch_gemm<192, 2>(tmA, tmB, tmC, tmR, tmBt, p, dev.num_sms, stream);
+    return launch_gemm<128, 2>(tmA, tmB, tmC, tmR, tmBt, p, dev.num_sms, stream);
   }
-  if (bn == 256) return launch_gemm<256, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
-  if (bn == 192) return launch_gemm<192, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
-  return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream);
+  if (bn == 256) return launch_gemm<256, 1>(tmA, tmB, tmC, tmR, tmBt, p, dev.num_sms, stream);
+  if (bn == 192) return launch_gemm<192, 1>(tmA, tmB, tmC, tmR, tmBt, p, dev.num_sms, stream);
+  return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, tmBt, p, dev.num_sms, stream);
 }
 
 }  // namespace ds
