@@ -387,7 +387,7 @@ def run_reference(args):
                              "sample": r["sample"], "host_gflops": round(r["gflops_per_sec"], 1)},
             "e2e": {"value": round(r["steps_per_sec"], 6), "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -499,13 +499,32 @@ def run_ours(args):
         if "roofline" not in line:
             line["roofline"] = None
         line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's original stdout (see `main`)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # Libraries write to fd 1 behind Python's back (NCCL prints "NCCL version ..." there on the first collective):
+    # keep the original stdout for the JSON line only and send everything else to stderr.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

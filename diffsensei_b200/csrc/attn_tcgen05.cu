@@ -366,23 +366,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 constexpr int kFlashSmemBytes = kTileBytes * (1 + 3 + 2) + 1024 + 128 + 2 * kTile * 4;
 
 // =================================================================================================
-// (1b) flash attention v3 — same contract as flash_attn_kernel, restructured around the two resources that bound
-//      head_dim 64 on sm_100a: the MUFU (exp2) pipe and the 128 B/clk shared-memory port.
-//        * P never touches shared memory: it is written to TMEM (tcgen05.st, bf16x2-packed, 64 columns) and the
-//          O += P V MMA takes its A operand from TMEM (tcgen05.mma "ts" form).  Per kv tile that removes 32 KB of
-//          st.shared, the fence.proxy.async, and 32 KB of tensor-core operand reads from the smem port.
-//        * one thread per query row (4 softmax warps): the rescale decision is thread-local, warp-uniform by a vote,
-//          no CTA barrier on the per-tile path.
-//        * no per-element running max: exponentials are taken against the row's reference max m_ref; because every
-//          term is >= 0, the row sum of the tile bounds its largest term, so "sum < 2^10" proves no score exceeded
-//          m_ref by more than 10 (log2).  Otherwise (rare) the warp takes the exact-max path, moves m_ref, rescales
-//          O in TMEM and redoes the tile.
-//        * TMEM loads of S are software-pipelined one 32-column chunk ahead of the exp2 work.
-//      TMEM (256 columns, 2 CTAs/SM): S [0,128) fp32 | O [128,192) fp32 | P [192,256) bf16x2.
+// Shared by the TMEM-P flash kernels.  History of the self-attention kernel at B8 N4096 h10 (all measured on B200,
+// sources in git history, analysis in profiles/r01_ncu_flash_v3.md):
+//   v2 (below: P through shared memory, 2 threads per row)                                    634 us
+//   v3 (P in TMEM via tcgen05.st + ts-form PV MMA, 1 thread per row, sum-bounded lazy rescale) 562 us
+//   v4 (v3 + the kv tile pipelined through the MMA warp in two 64-key halves)                  559 us
+//   v5 (two independent online-softmax streams per CTA)                                        436 us
 // =================================================================================================
-constexpr int kFlash3Threads = 256;  // 4 control warps + 4 softmax warps
 constexpr int kFlash3Ring = 4;
-constexpr int kFlash3SmemBytes = kTileBytes * (1 + kFlash3Ring) + 1024 + 256;
 constexpr float kSumOverflow = 1024.0f;  // 2^10
 
 // Degree-3 minimax 2^f on f in [-0.5, 0.5] after Cody-Waite range reduction, all on the FMA/ALU pipes (FA4-style
@@ -396,518 +387,6 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 0.69326099f);
   p = fmaf(p, f, 0.99992811f);
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(r) << 23));
-}
-
-template <int POLY>  // POLY of every 8 exponentials go to the FMA pipe instead of the MUFU
-__global__ void __launch_bounds__(kFlash3Threads, 2)
-flash_attn_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
-  constexpr int RING = kFlash3Ring;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
-  uint8_t* sRing = sQ + kTileBytes;  // RING x 16 KiB: K_0 V_0 K_1 V_1 ...
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + RING * kTileBytes);
-  uint64_t* q_full = bars;
-  uint64_t* full = bars + 1;      // [RING]
-  uint64_t* empty = full + RING;  // [RING]
-  uint64_t* s_full = empty + RING;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTile;
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int num_kv_tiles = (p.Nkv + kTile - 1) / kTile;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < RING; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);  // one arrival per softmax warp
-    mbar_init(o_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, 256);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;        // columns [0,128)   fp32 scores
-  const uint32_t tO = tmem_base + 128;  // columns [128,192) fp32 output accumulator
-  const uint32_t tP = tmem_base + 192;  // columns [192,256) bf16x2 probabilities (A operand of the PV MMA)
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
-      tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + head * kHd, q0, batch);
-      for (int idx = 0; idx < 2 * num_kv_tiles; ++idx) {  // K_0 V_0 K_1 V_1 ...
-        const int slot = idx % RING;
-        const uint32_t ph = (idx / RING) & 1;
-        const int j = idx >> 1, which = idx & 1;
-        mbar_wait(&empty[slot], ph ^ 1);
-        mbar_arrive_expect_tx(&full[slot], kTileBytes);
-        tma_load_3d(sRing + slot * kTileBytes, which == 0 ? &tmK : &tmV, &full[slot],
-                    (which == 0 ? p.k_col0 : p.v_col0) + head * kHd, j * kTile, batch);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(kTile, kTile, 0, 0);  // M128 N128, both K-major
-      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);    // M128 N64, A from TMEM, B (=V) MN-major
-      const uint32_t q_addr = smem_u32(sQ);
-      auto issue_s = [&](int j) {  // S = Q K_j^T, then free K_j's slot and publish S
-        const int idx = 2 * j, slot = idx % RING;
-        mbar_wait(&full[slot], (idx / RING) & 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sRing + slot * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kHd / 16; ++k)
-          umma_ss(tS, make_sw128_desc(q_addr + k * 32, 1024, 16), make_sw128_desc(k_addr + k * 32, 1024, 16),
-                  idesc_qk, k != 0 ? 1u : 0u);
-        umma_commit(&empty[slot]);
-        umma_commit(s_full);
-      };
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < num_kv_tiles; ++j) {
-        const int idx = 2 * j + 1, slot = idx % RING;
-        mbar_wait(&full[slot], (idx / RING) & 1);  // V_j landed
-        mbar_wait(p_full, j & 1);                  // P_j is in TMEM (and S_j has been read)
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(sRing + slot * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kTile / 16; ++k)  // K = 16 bf16 = 8 packed TMEM columns of P per MMA
-          umma_ts(tO, tP + k * 8, make_sw128_desc(v_addr + k * 2048, 1024, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
-        umma_commit(&empty[slot]);
-        if (j + 1 < num_kv_tiles) issue_s(j + 1);  // its commit also covers PV_j: s_full(j+1) => O and P are quiescent
-      }
-      umma_commit(o_full);
-    }
-  } else if (warp >= 4) {
-    // ---------------------------------------------------------------- softmax: 4 warps, thread <-> query row
-    const int wq = warp & 3;
-    const int row = wq * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t tSr = tS + lane_base, tOr = tO + lane_base, tPr = tP + lane_base;
-    float m_ref = -INFINITY, l = 0.f;
-
-    // 32 scores -> 16 packed bf16x2 probabilities; partial sums into s0/s1
-    auto chunk = [&](const uint32_t(&raw)[32], uint32_t(&pk)[16], float neg_m, int valid, float& s0, float& s1) {
-      if (valid >= 32) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
-          const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
-          const float e0 = ((2 * i) % 8 < POLY) ? ex2_poly(t0) : ex2(t0);
-          const float e1 = ((2 * i + 1) % 8 < POLY) ? ex2_poly(t1) : ex2(t1);
-          s0 += e0;
-          s1 += e1;
-          pk[i] = pack_bf16_alu(e0, e1);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
-          const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
-          const float e0 = (2 * i < valid) ? ex2(t0) : 0.f;
-          const float e1 = (2 * i + 1 < valid) ? ex2(t1) : 0.f;
-          s0 += e0;
-          s1 += e1;
-          pk[i] = pack_bf16_alu(e0, e1);
-        }
-      }
-    };
-    // one pass over the row's 128 scores: P -> TMEM, returns the row sum of the tile
-    auto sweep = [&](float neg_m, int kv_valid) -> float {
-      float s0 = 0.f, s1 = 0.f;
-      uint32_t ra[32], rb[32], pk[16];
-      tmem_ld32(tSr, ra);
-      tmem_ld_wait();
-      tmem_ld32(tSr + 32, rb);
-      chunk(ra, pk, neg_m, kv_valid, s0, s1);
-      tmem_st16(tPr, pk);
-      tmem_ld_wait();
-      tmem_ld32(tSr + 64, ra);
-      chunk(rb, pk, neg_m, kv_valid - 32, s0, s1);
-      tmem_st16(tPr + 16, pk);
-      tmem_ld_wait();
-      tmem_ld32(tSr + 96, rb);
-      chunk(ra, pk, neg_m, kv_valid - 64, s0, s1);
-      tmem_st16(tPr + 32, pk);
-      tmem_ld_wait();
-      chunk(rb, pk, neg_m, kv_valid - 96, s0, s1);
-      tmem_st16(tPr + 48, pk);
-      return s0 + s1;
-    };
-    // exact maximum of the row's valid scores (raw, unscaled)
-    auto row_max = [&](int kv_valid) -> float {
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tSr + c * 32, raw);
-        tmem_ld_wait();
-        if (kv_valid >= (c + 1) * 32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(raw[i]));
-        }
-      }
-      return mx;
-    };
-
-    for (int j = 0; j < num_kv_tiles; ++j) {
-      const int kv_valid = p.Nkv - j * kTile;  // >= 128: whole tile valid
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      float lsum;
-      if (j == 0) {
-        m_ref = row_max(kv_valid) * p.scale_log2;
-        lsum = sweep(-m_ref, kv_valid);
-      } else {
-        lsum = sweep(-m_ref, kv_valid);
-        if (__any_sync(0xffffffffu, !(lsum < kSumOverflow))) {  // warp-uniform, rare
-          const float t_new = row_max(kv_valid) * p.scale_log2;
-          float alpha = 1.0f;
-          if (t_new > m_ref) {
-            alpha = ex2(m_ref - t_new);
-            m_ref = t_new;
-            l *= alpha;
-          }
-          tmem_st_wait();  // the aborted P stores must not be overtaken
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {  // rescale this warp's 32 rows of O (quiescent: s_full(j) covers PV_{j-1})
-            uint32_t raw[32];
-            tmem_ld32(tOr + c * 32, raw);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
-            tmem_st32(tOr + c * 32, raw);
-          }
-          lsum = sweep(-m_ref, kv_valid);
-        }
-      }
-      l += lsum;
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-    // ---- epilogue: O / l -> bf16 -> global (one 128-byte row segment per thread)
-    const float inv_l = 1.0f / l;
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const int q_row = q0 + row;
-    __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.Nq + q_row) * p.ldo + head * kHd;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t raw[32];
-      tmem_ld32(tOr + c * 32, raw);
-      tmem_ld_wait();
-      if (q_row < p.Nq) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(raw[q * 8 + 0]) * inv_l, __uint_as_float(raw[q * 8 + 1]) * inv_l);
-          u.y = pack_bf16(__uint_as_float(raw[q * 8 + 2]) * inv_l, __uint_as_float(raw[q * 8 + 3]) * inv_l);
-          u.z = pack_bf16(__uint_as_float(raw[q * 8 + 4]) * inv_l, __uint_as_float(raw[q * 8 + 5]) * inv_l);
-          u.w = pack_bf16(__uint_as_float(raw[q * 8 + 6]) * inv_l, __uint_as_float(raw[q * 8 + 7]) * inv_l);
-          reinterpret_cast<uint4*>(orow + c * 32)[q] = u;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
-
-// =================================================================================================
-// (1c) flash attention v4 — v3 with the kv tile split into two 64-key HALVES that flow through the
-//      S-MMA -> softmax -> PV-MMA chain independently.  ncu on v3 (profiles/r01_ncu_flash_v3.md): the softmax warps
-//      spent 36 % of their time waiting for the next S (PV + S MMAs + two mbarrier hand-offs sit between "P written"
-//      and "next S readable"), so the MUFU pipe — the binding resource at head_dim 64 — idled half the time.  Here
-//      the tensor core recomputes S half 0 of tile j+1 while the softmax warps are still in half 1 of tile j, so
-//      they never run dry:
-//        MMA warp :  wait P_h0(j) -> PV_h0(j), S_h0(j+1) ;  wait P_h1(j) -> PV_h1(j), S_h1(j+1)
-//        softmax  :  wait S_h0 -> exp -> P_h0 ;  wait S_h1 -> exp -> P_h1      (one thread per query row)
-//      The reference max starts as the exact max of half 0 of tile 0; everything after is covered by the sum-bounded
-//      lazy rescale (row sum of a half < 2^10 proves no score exceeded m_ref by more than 10 in log2).
-// =================================================================================================
-template <int POLY>
-__global__ void __launch_bounds__(kFlash3Threads, 2)
-flash_attn_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
-  constexpr int RING = kFlash3Ring;
-  constexpr int kHalf = 64;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
-  uint8_t* sRing = sQ + kTileBytes;  // RING x 16 KiB: K_0 V_0 K_1 V_1 ...
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + RING * kTileBytes);
-  uint64_t* q_full = bars;
-  uint64_t* full = bars + 1;          // [RING]
-  uint64_t* empty = full + RING;      // [RING]
-  uint64_t* s_full = empty + RING;    // [2]  S half h readable
-  uint64_t* p_full = s_full + 2;      // [2]  P half h written (and S half h consumed)
-  uint64_t* pv_done = p_full + 2;     // [2]  O += P_h V_h retired (only waited on by the rescale path)
-  uint64_t* o_full = pv_done + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTile;
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int num_kv_tiles = (p.Nkv + kTile - 1) / kTile;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < RING; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    for (int h = 0; h < 2; ++h) {
-      mbar_init(&s_full[h], 1);
-      mbar_init(&p_full[h], 4);  // one arrival per softmax warp
-      mbar_init(&pv_done[h], 1);
-    }
-    mbar_init(o_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, 256);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;        // columns [0,128)   fp32 scores (half h at +64h)
-  const uint32_t tO = tmem_base + 128;  // columns [128,192) fp32 output accumulator
-  const uint32_t tP = tmem_base + 192;  // columns [192,256) bf16x2 probabilities (half h at +32h)
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
-      tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + head * kHd, q0, batch);
-      for (int idx = 0; idx < 2 * num_kv_tiles; ++idx) {  // K_0 V_0 K_1 V_1 ...
-        const int slot = idx % RING;
-        const uint32_t ph = (idx / RING) & 1;
-        const int j = idx >> 1, which = idx & 1;
-        mbar_wait(&empty[slot], ph ^ 1);
-        mbar_arrive_expect_tx(&full[slot], kTileBytes);
-        tma_load_3d(sRing + slot * kTileBytes, which == 0 ? &tmK : &tmV, &full[slot],
-                    (which == 0 ? p.k_col0 : p.v_col0) + head * kHd, j * kTile, batch);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(kTile, kHalf, 0, 0);  // M128 N64, both K-major
-      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);    // M128 N64, A from TMEM, B (=V) MN-major
-      const uint32_t q_addr = smem_u32(sQ);
-      auto issue_s = [&](uint32_t k_addr, int h) {  // S_h = Q K[64h..64h+64)^T
-#pragma unroll
-        for (int k = 0; k < kHd / 16; ++k)
-          umma_ss(tS + h * kHalf, make_sw128_desc(q_addr + k * 32, 1024, 16),
-                  make_sw128_desc(k_addr + h * (kHalf * 128) + k * 32, 1024, 16), idesc_qk, k != 0 ? 1u : 0u);
-        umma_commit(&s_full[h]);
-      };
-      auto issue_pv = [&](uint32_t v_addr, int h, bool first) {  // O (+)= P_h V[64h..64h+64)
-#pragma unroll
-        for (int k = 0; k < kHalf / 16; ++k)
-          umma_ts(tO, tP + h * 32 + k * 8, make_sw128_desc(v_addr + h * (kHalf * 128) + k * 2048, 1024, 1024), idesc_pv,
-                  (first && k == 0) ? 0u : 1u);
-        umma_commit(&pv_done[h]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&full[0], 0);  // K_0
-      tc_fence_after();
-      issue_s(smem_u32(sRing), 0);
-      issue_s(smem_u32(sRing), 1);
-      umma_commit(&empty[0]);
-      for (int j = 0; j < num_kv_tiles; ++j) {
-        const int vi = 2 * j + 1, vslot = vi % RING;
-        const int ki = 2 * j + 2, kslot = ki % RING;
-        const bool more = j + 1 < num_kv_tiles;
-        mbar_wait(&full[vslot], (vi / RING) & 1);        // V_j
-        if (more) mbar_wait(&full[kslot], (ki / RING) & 1);  // K_{j+1}
-        const uint32_t v_addr = smem_u32(sRing + vslot * kTileBytes);
-        const uint32_t k_addr = smem_u32(sRing + kslot * kTileBytes);
-        mbar_wait(&p_full[0], j & 1);
-        tc_fence_after();
-        issue_pv(v_addr, 0, j == 0);
-        if (more) issue_s(k_addr, 0);
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
-        issue_pv(v_addr, 1, false);
-        umma_commit(&empty[vslot]);
-        if (more) {
-          issue_s(k_addr, 1);
-          umma_commit(&empty[kslot]);
-        }
-      }
-      umma_commit(o_full);
-    }
-  } else if (warp >= 4) {
-    // ---------------------------------------------------------------- softmax: 4 warps, thread <-> query row
-    const int wq = warp & 3;
-    const int row = wq * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t tSr = tS + lane_base, tOr = tO + lane_base, tPr = tP + lane_base;
-    float m_ref = -INFINITY, l = 0.f;
-
-    // 32 scores -> 16 packed bf16x2 probabilities; partial sums into s0/s1
-    auto chunk = [&](const uint32_t(&raw)[32], uint32_t(&pk)[16], float neg_m, int valid, float& s0, float& s1) {
-      if (valid >= 32) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
-          const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
-          const float e0 = ((2 * i) % 8 < POLY) ? ex2_poly(t0) : ex2(t0);
-          const float e1 = ((2 * i + 1) % 8 < POLY) ? ex2_poly(t1) : ex2(t1);
-          s0 += e0;
-          s1 += e1;
-          pk[i] = pack_bf16_alu(e0, e1);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
-          const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
-          const float e0 = (2 * i < valid) ? ex2(t0) : 0.f;
-          const float e1 = (2 * i + 1 < valid) ? ex2(t1) : 0.f;
-          s0 += e0;
-          s1 += e1;
-          pk[i] = pack_bf16_alu(e0, e1);
-        }
-      }
-    };
-
-    for (int j = 0; j < num_kv_tiles; ++j) {
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int valid = p.Nkv - j * kTile - h * kHalf;  // >= 64: whole half valid; <= 0: nothing valid
-        mbar_wait(&s_full[h], j & 1);
-        tc_fence_after();
-        const uint32_t tSh = tSr + h * kHalf, tPh = tPr + h * 32;
-        bool need_max = (j == 0) && (h == 0);
-        float lsum;
-#pragma unroll 1
-        for (;;) {
-          uint32_t ra[32], rb[32];
-          tmem_ld32(tSh, ra);
-          tmem_ld32(tSh + 32, rb);
-          tmem_ld_wait();
-          if (need_max) {  // exact maximum of this half's valid scores -> move the reference, rescale O and l
-            float mx = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (i < valid) mx = fmaxf(mx, __uint_as_float(ra[i]));
-              if (32 + i < valid) mx = fmaxf(mx, __uint_as_float(rb[i]));
-            }
-            const float t_new = mx * p.scale_log2;
-            float alpha = 1.0f;
-            if (t_new > m_ref) {
-              alpha = ex2(m_ref - t_new);  // m_ref = -inf on the very first half: alpha = 0, l = 0 anyway
-              m_ref = t_new;
-              l *= alpha;
-            }
-            if (j | h) {  // O holds something: wait until the last issued PV retired, then scale this warp's rows
-              if (h == 0)
-                mbar_wait(&pv_done[1], (j - 1) & 1);
-              else
-                mbar_wait(&pv_done[0], j & 1);
-              tc_fence_after();
-              tmem_st_wait();  // the aborted P stores of the first attempt
-#pragma unroll
-              for (int c = 0; c < 2; ++c) {
-                uint32_t o[32];
-                tmem_ld32(tOr + c * 32, o);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                tmem_st32(tOr + c * 32, o);
-              }
-            }
-          }
-          float s0 = 0.f, s1 = 0.f;
-          uint32_t pk[16];
-          chunk(ra, pk, -m_ref, valid, s0, s1);
-          tmem_st16(tPh, pk);
-          chunk(rb, pk, -m_ref, valid - 32, s0, s1);
-          tmem_st16(tPh + 16, pk);
-          lsum = s0 + s1;
-          if (need_max) break;  // exact reference: every term <= 1
-          need_max = __any_sync(0xffffffffu, !(lsum < kSumOverflow));  // warp-uniform, rare
-          if (!need_max) break;
-        }
-        l += lsum;
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[h]);
-      }
-    }
-    // ---- epilogue: O / l -> bf16 -> global (one 128-byte row segment per thread)
-    const float inv_l = 1.0f / l;
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const int q_row = q0 + row;
-    __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.Nq + q_row) * p.ldo + head * kHd;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t raw[32];
-      tmem_ld32(tOr + c * 32, raw);
-      tmem_ld_wait();
-      if (q_row < p.Nq) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(raw[q * 8 + 0]) * inv_l, __uint_as_float(raw[q * 8 + 1]) * inv_l);
-          u.y = pack_bf16(__uint_as_float(raw[q * 8 + 2]) * inv_l, __uint_as_float(raw[q * 8 + 3]) * inv_l);
-          u.z = pack_bf16(__uint_as_float(raw[q * 8 + 4]) * inv_l, __uint_as_float(raw[q * 8 + 5]) * inv_l);
-          u.w = pack_bf16(__uint_as_float(raw[q * 8 + 6]) * inv_l, __uint_as_float(raw[q * 8 + 7]) * inv_l);
-          reinterpret_cast<uint4*>(orow + c * 32)[q] = u;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
 }
 
 // =================================================================================================
@@ -1770,7 +1249,7 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
   p.scale_log2 = scale * kLog2e;
   dim3 grid((Nq + kTile - 1) / kTile, heads, B);
   // DS_FLASH=2 selects the round-1 kernel (P through shared memory, 2 threads per row) for A/B timing;
-  // DS_FLASH_POLY=n sends n of every 8 exponentials to the FMA pipe (v3 only)
+  // DS_FLASH_POLY=n sends n of every 8 exponentials to the FMA pipe (v5)
   static const int flash_ver = [] {
     const char* e = getenv("DS_FLASH");
     return e ? atoi(e) : 5;
@@ -1784,7 +1263,7 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
     DS_LAUNCH_OK("flash_attn_kernel");
     return DS_OK;
   }
-  if (flash_ver >= 5) {
+  if (flash_ver >= 5 || flash_ver <= 0) {
     static const int flash_f2 = [] {  // DS_FLASH_F2=0: scalar FFMA/FADD instead of the packed fp32x2 forms
       const char* e = getenv("DS_FLASH_F2");
       return e ? atoi(e) : 1;
@@ -1817,38 +1296,8 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
     DS_LAUNCH_OK("flash_attn_v5_kernel");
     return DS_OK;
   }
-  if (flash_ver >= 4) {
-    static bool attr4_set = false;
-    if (!attr4_set) {
-      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
-      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
-      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v4_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
-      attr4_set = true;
-    }
-    switch (flash_poly) {
-      case 1: flash_attn_v4_kernel<1><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
-      case 2: flash_attn_v4_kernel<2><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
-      default: flash_attn_v4_kernel<0><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
-    }
-    DS_LAUNCH_OK("flash_attn_v4_kernel");
-    return DS_OK;
-  }
-  static bool attr3_set = false;
-  if (!attr3_set) {
-    DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
-    DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
-    DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
-    DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash3SmemBytes));
-    attr3_set = true;
-  }
-  switch (flash_poly) {
-    case 1: flash_attn_v3_kernel<1><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
-    case 2: flash_attn_v3_kernel<2><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
-    case 3: flash_attn_v3_kernel<3><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
-    default: flash_attn_v3_kernel<0><<<grid, kFlash3Threads, kFlash3SmemBytes, st>>>(tmQ, tmK, tmV, p); break;
-  }
-  DS_LAUNCH_OK("flash_attn_v3_kernel");
-  return DS_OK;
+  set_error("ds_attention: DS_FLASH=%d is not built (2 = shared-memory-P kernel, 5 = default)", flash_ver);
+  return DS_ERR_INVALID;
 }
 
 }  // namespace ds

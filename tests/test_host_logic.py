@@ -1,4 +1,6 @@
 """Host-side logic that needs no GPU: weight naming / packing, schedule, pipeline argument handling."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -106,3 +108,29 @@ def test_fold_layernorm_is_algebraically_layernorm_then_linear():
     assert (got - want).abs().max() < 1e-5      # fold_layernorm computes in fp32
     w3, b3 = fold_layernorm(w, None, gamma, beta)
     assert torch.allclose(b3.double(), w @ beta, atol=1e-5)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line_on_stdout():
+    """bench.py --impl reference (tiny plumbing mode): stdout carries ONE JSON line with the contract's keys; library
+    chatter (NCCL prints its version on fd 1) is kept off stdout by bench.main's fd juggling."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    env = dict(os.environ, DS_BENCH_TINY="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_host_thread_probe_returns_a_usable_count():
+    import bench
+    n = bench.pick_host_threads()
+    assert 1 <= n <= (os.cpu_count() or 1)
