@@ -25,14 +25,16 @@ class GemmArgs(C.Structure):
                 ("rows_per_batch", C.c_int32), ("rowbias_ld", C.c_int32), ("epilogue", C.c_int32), ("out_fp32", C.c_int32),
                 ("out_scale", C.c_float),
                 ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float),
-                ("row_stats_out", C.c_void_p), ("zero_rows", C.c_void_p), ("row_stats_zeroed", C.c_int32)]
+                ("row_stats_out", C.c_void_p), ("zero_rows", C.c_void_p), ("row_stats_zeroed", C.c_int32),
+                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64)]
 
 
 class Conv3x3Args(C.Structure):
     _fields_ = [("x", C.c_void_p), ("w", C.c_void_p), ("out", C.c_void_p), ("bias", C.c_void_p),
                 ("rowbias", C.c_void_p), ("residual", C.c_void_p),
                 ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
-                ("stride", C.c_int32), ("rowbias_ld", C.c_int32), ("out_fp32", C.c_int32), ("out_scale", C.c_float)]
+                ("stride", C.c_int32), ("rowbias_ld", C.c_int32), ("out_fp32", C.c_int32), ("out_scale", C.c_float),
+                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64)]
 
 
 class CrossIpArgs(C.Structure):
@@ -69,7 +71,8 @@ SIGNATURES = {
     "ds_cfg_ddim_step": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp],
     "ds_resampler_attn": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
 }
-OTHER_EXPORTS = ("ds_version", "ds_last_error", "ds_launch_count", "ds_groupnorm_scratch_floats")
+OTHER_EXPORTS = ("ds_version", "ds_last_error", "ds_launch_count", "ds_groupnorm_scratch_floats",
+                 "ds_gemm_splitk_ws_bytes")
 
 
 def _load() -> C.CDLL:
@@ -87,6 +90,8 @@ def _load() -> C.CDLL:
     lib.ds_launch_count.restype = C.c_uint64
     lib.ds_groupnorm_scratch_floats.argtypes = [C.c_int, C.c_int]
     lib.ds_groupnorm_scratch_floats.restype = C.c_int64
+    lib.ds_gemm_splitk_ws_bytes.argtypes = []
+    lib.ds_gemm_splitk_ws_bytes.restype = C.c_int64
     return lib
 
 

@@ -55,10 +55,13 @@ struct GemmParams {
   float* row_stats_out;    // [M][2], accumulated with atomics (zeroed by the host wrapper), or NULL
   float* zero_rows;        // [M][2] buffer whose rows this launch resets to 0 (the statistics buffer two hops ahead)
   int num_m_tiles, num_n_tiles, num_k_iters;
-  // tail split: work items [0, tail_start) are whole 128*PAIR x BN units; each of the remaining units (the partial last
-  // wave of the persistent schedule) is cut into tail_f column slices of BN / tail_f so that it spreads over
-  // tail_f x as many CTA pairs instead of leaving most SMs idle for a whole unit time.  tail_f = 1: off.
-  int tail_start, tail_f, total_items;
+  // split-K tail: work items [0, tail_start) are whole 128*PAIR x BN units.  Each of the remaining `left` units (the
+  // partial last wave of the persistent schedule) is cut along K into tail_parts slices that run on different CTA
+  // pairs; every slice adds its fp32 accumulator into the unit's tile of `ws` (vector red.global.add), and the slice
+  // that arrives last (per-unit, per-CTA-rank counter) runs the normal epilogue from `ws` instead of TMEM, clearing
+  // the tile and the counter behind it.  tail_parts = 1: off.
+  int tail_start, tail_parts, total_items;
+  float* ws;  // [256 uint32 counters][left][PAIR * 128][BN] fp32, all zero between launches
   // conv geometry
   int conv, stride, Ho, Wo, tiles_x, tiles_y, cin_chunks, conv_B;
 };
@@ -85,7 +88,7 @@ template <int BN, int PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                  const __grid_constant__ CUtensorMap tmBt, const GemmParams p) {
+                  const GemmParams p) {
   using Cfg = GemmCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::kStages;
   const uint32_t cta_rank = (PAIR == 2) ? cluster_ctarank() : 0u;  // rank inside the CTA pair; 0 = leader
@@ -149,18 +152,21 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel's tail; from here on we touch its outputs
 
-  const int total_tiles = p.total_items;  // work items: whole units, then the column slices of the tail units
-  // item -> (unit, first weight row n_org of its columns, its width bn_cur)
-  auto decode = [&](int item, int& unit, int& n_org, int& bn_cur) {
+  const int total_tiles = p.total_items;  // work items: whole units, then the K-slices of the tail units
+  // item -> (unit, k-block range [k0, k1), index of the unit among the tail units or -1)
+  auto decode = [&](int item, int& unit, int& k0, int& k1, int& tail_idx) {
     if (item < p.tail_start) {
       unit = item;
-      bn_cur = BN;
-      n_org = (unit % p.num_n_tiles) * BN;
+      k0 = 0;
+      k1 = p.num_k_iters;
+      tail_idx = -1;
     } else {
       const int s = item - p.tail_start;
-      unit = p.tail_start + s / p.tail_f;
-      bn_cur = BN / p.tail_f;
-      n_org = (unit % p.num_n_tiles) * BN + (s % p.tail_f) * bn_cur;
+      tail_idx = s / p.tail_parts;
+      const int part = s - tail_idx * p.tail_parts;
+      unit = p.tail_start + tail_idx;
+      k0 = part * p.num_k_iters / p.tail_parts;
+      k1 = (part + 1) * p.num_k_iters / p.tail_parts;
     }
   };
 
@@ -170,11 +176,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
-        int unit, n_org, bn_cur;
-        decode(tile, unit, n_org, bn_cur);
+        int unit, k0, k1, tail_idx;
+        decode(tile, unit, k0, k1, tail_idx);
+        const int n_blk = unit % p.num_n_tiles;
         const int m_blk = (unit / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
-        const bool slice = bn_cur != BN;
-        const uint32_t stage_bytes = kABytes + static_cast<uint32_t>(bn_cur / PAIR) * (kBK * 2);
         int img = 0, x0 = 0, y0 = 0;
         if (p.conv) {
           const int per_img = p.tiles_x * p.tiles_y;
@@ -183,14 +188,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           y0 = (rem / p.tiles_x) * kConvTileH;
           x0 = (rem % p.tiles_x) * kConvTileW;
         }
-        const int b_row0 = n_org + static_cast<int>(cta_rank) * (bn_cur / PAIR);
-        const CUtensorMap* mapB = slice ? &tmBt : &tmB;
-        for (int kb = 0; kb < p.num_k_iters; ++kb) {
+        const int b_row0 = n_blk * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
+        for (int kb = k0; kb < k1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (PAIR == 1) {
-            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           } else if (leader) {
-            mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);  // both CTAs' bytes land on this barrier
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);  // both CTAs' bytes land on this barrier
           } else {
             mbar_arrive_cluster(&full_bar[stage], 0);
           }
@@ -211,9 +215,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_load_2d(sA + stage * kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM);
           }
           if (PAIR == 2)
-            tma_load_2d_pair(sB + stage * Cfg::kBBytes, mapB, &full_bar[stage], kb * kBK, b_row0);
+            tma_load_2d_pair(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, b_row0);
           else
-            tma_load_2d(sB + stage * Cfg::kBBytes, mapB, &full_bar[stage], kb * kBK, b_row0);
+            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, b_row0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -224,19 +228,19 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && leader) {  // in a pair only the leader CTA issues (for both SMs' tensor cores)
-      constexpr uint32_t idesc_full = make_idesc_bf16(kBM * PAIR, BN, 0, 0);
-      const uint32_t idesc_slice = make_idesc_bf16(kBM * PAIR, BN / p.tail_f, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(kBM * PAIR, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
       for (int tile = unit0; tile < total_tiles; tile += unit_step, ++iter) {
-        const uint32_t idesc = tile < p.tail_start ? idesc_full : idesc_slice;
+        int unit, k0, k1, tail_idx;
+        decode(tile, unit, k0, k1, tail_idx);
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_k_iters; ++kb) {
+        for (int kb = k0; kb < k1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * kABytes);
@@ -246,9 +250,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t adesc = make_sw128_desc(a_addr + k * 32, 1024, 16);
             const uint64_t bdesc = make_sw128_desc(b_addr + k * 32, 1024, 16);
             if (PAIR == 2)
-              umma_ss_pair(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_ss_pair(d_tmem, adesc, bdesc, idesc, (kb != k0 || k != 0) ? 1u : 0u);
             else
-              umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_ss(d_tmem, adesc, bdesc, idesc, (kb != k0 || k != 0) ? 1u : 0u);
           }
           // stage reusable (in both CTAs) once these MMAs have read it
           if (PAIR == 2)
@@ -331,11 +335,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int tile = unit0; tile < total_tiles; tile += unit_step, ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      int unit, n_org, bn_cur;
-      decode(tile, unit, n_org, bn_cur);
+      int unit, k0, k1, tail_idx;
+      decode(tile, unit, k0, k1, tail_idx);
+      const int n_org = (unit % p.num_n_tiles) * BN;           // first weight row of the tile's columns
+      constexpr int bn_cur = BN;
       const int m_blk = (unit / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
       const int r_local = wq * 32 + lane;
-      const int bn_out = geglu ? bn_cur / 2 : bn_cur;          // output columns of this item (GEGLU items are never sliced)
+      const int bn_out = geglu ? bn_cur / 2 : bn_cur;          // output columns of this item
       const int no_org = geglu ? n_org / 2 : n_org;            // first output column
       // the item's output columns are handed to the two warp groups in 64-column blocks (192: 2 + 1, 64: 1 + 0)
       const int split = ((bn_out / 64 + 1) / 2) * 64;
@@ -405,14 +411,61 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
 
+      // ---- split-K tail: add this K-slice's accumulator into the unit's workspace tile; only the last slice to
+      // arrive goes on to the epilogue proper, reading the sums back from the workspace
+      const bool from_ws = tail_idx >= 0;
+      float* ws_row = nullptr;
+      if (from_ws) {
+        ws_row = p.ws + 256 +
+                 (static_cast<size_t>(tail_idx) * (PAIR * kBM) + cta_rank * kBM + r_local) * static_cast<size_t>(BN);
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(t_row + c0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ws_row + c0 + q * 4),
+                         "f"(__uint_as_float(raw[q * 4 + 0])), "f"(__uint_as_float(raw[q * 4 + 1])),
+                         "f"(__uint_as_float(raw[q * 4 + 2])), "f"(__uint_as_float(raw[q * 4 + 3]))
+                         : "memory");
+        }
+        release_acc(acc);
+        __threadfence();  // this thread's reductions are performed before the arrival below becomes visible
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        volatile uint32_t* s_flag = tmem_slot + 2;
+        if (warp == 4 && lane == 0) {
+          unsigned int* cnt = reinterpret_cast<unsigned int*>(p.ws) + tail_idx * 2 + cta_rank;
+          const unsigned int old = atomicAdd(cnt, 1u);
+          const bool last = old == static_cast<unsigned int>(p.tail_parts - 1);
+          if (last) *cnt = 0u;  // every slice has arrived: leave the counter clean for the next launch
+          *s_flag = last ? 1u : 0u;
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (*s_flag == 0u) continue;  // CTA-uniform
+        __threadfence();
+      }
+
       // accumulator chunk -> fp32 values with bias / row-bias / GEGLU / activation applied (no residual yet)
       auto load_chunk = [&](int c0, float(&v)[32]) {
         const int nw0 = n_org + c0;  // weight-row index of column 0 of this chunk
-        uint32_t raw[32];
-        tmem_ld32(t_row + c0, raw);
-        tmem_ld_wait();
+        if (from_ws) {  // sums of all K-slices; clear behind us so the workspace is zero again for the next launch
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          for (int q = 0; q < 8; ++q) {
+            float4* wp = reinterpret_cast<float4*>(ws_row + c0) + q;
+            const float4 f = __ldcg(wp);
+            v[q * 4 + 0] = f.x;
+            v[q * 4 + 1] = f.y;
+            v[q * 4 + 2] = f.z;
+            v[q * 4 + 3] = f.w;
+            __stcg(wp, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+        } else {
+          uint32_t raw[32];
+          tmem_ld32(t_row + c0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        }
         if (p.ln_stats) ln32s(v, vec + BN + c0, ln_mean, ln_rstd);
         add32s(v, vec + c0);
         if (gemm_rowbias && row_ok) add32(v, p.rowbias + static_cast<long long>(batch) * p.ldrb + nw0, nw0);
@@ -449,7 +502,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           cy = (rem / p.tiles_x) * kConvTileH;
           cx = (rem % p.tiles_x) * kConvTileW;
         }
-        bool released = false;
+        bool released = from_ws;  // a split-K item handed its accumulator back right after the reduction
         for (int cb = c_begin; cb < c_end; cb += 64) {
           const int no0 = no_org + cb;  // first output column of this 64-wide block
           if (no0 >= p.n_out) break;            // group-uniform
@@ -507,7 +560,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                            : "memory");
             }
           }
-          if (cb + 64 >= c_end || no_org + cb + 64 >= p.n_out) {
+          if (!released && (cb + 64 >= c_end || no_org + cb + 64 >= p.n_out)) {
             // last block of this tile for this warp: TMEM is drained -> hand the accumulator back early
             release_acc(acc);
             released = true;
@@ -597,8 +650,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 template <int BN, int PAIR>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                       const CUtensorMap& tmR, const CUtensorMap& tmBt, const GemmParams& p_in, int num_sms,
-                       cudaStream_t stream) {
+                       const CUtensorMap& tmR, const GemmParams& p_in, int num_sms, cudaStream_t stream,
+                       void* splitk_ws, long long splitk_ws_bytes) {
   GemmParams p = p_in;
   using Cfg = GemmCfg<BN, PAIR>;
   static bool attr_set = false;  // benign race: idempotent
@@ -637,27 +690,39 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
               PAIR == 2 ? "pairs" : "singles", num_sms);
   }
   const int groups = units < max_groups ? units : max_groups;
-  // tail split (see GemmParams): only for the 256-wide tiles, never for GEGLU (value | gate halves live in one tile)
-  // MEASURED (B200): neutral — FF2 91.1 vs 91.9 us, conv 1280 192.4 vs 192.1 us, step 60.2 vs 60.4 ms: a 64-column
-  // slice moves the whole A tile for a quarter of the math and is shared-memory-port bound at ~1/4 efficiency, so 48
-  // slices take as long as the 12 whole units they replace.  Opt-in (DS_GEMM_TAIL=1), covered by the native tests.
-  static const int tail_env = [] {
-    const char* e = getenv("DS_GEMM_TAIL");
-    return e ? atoi(e) : 0;
+  // split-K tail (see GemmParams): the units of the partial last wave are cut along K so that every CTA pair gets
+  // a slice.  Needs the bf16 TMA epilogue, no GEGLU (its accumulator pairs value | gate columns) and a caller-provided
+  // zeroed workspace.  MEASURED (B200): the fp32 reductions through L2 (256 KB of red.global.add.v4 per slice pair)
+  // and the second epilogue pass cost ~15-20 us per launch, so it only pays when one unit's main loop is much longer
+  // than that: conv 1280->1280 (K = 11520, 180 k-blocks) 196.0 -> 174.4 us, but FF2 (K = 5120) 89.3 -> 95.3 us,
+  // qkv 63.2 -> 82.1 us and the whole step 59.4 -> 64.2 ms when applied everywhere.  Hence the k-block threshold
+  // (DS_GEMM_SPLITK = minimum k-blocks per unit, default 128; 0 disables).
+  static const int splitk_env = [] {
+    const char* e = getenv("DS_GEMM_SPLITK");
+    return e ? atoi(e) : 128;
   }();
   p.tail_start = units;
-  p.tail_f = 1;
+  p.tail_parts = 1;
   p.total_items = units;
-  if (tail_env && BN == 256 && p.epilogue != DS_EPI_GEGLU && units > groups) {
+  p.ws = nullptr;
+  if (splitk_env > 0 && p.num_k_iters >= splitk_env && splitk_ws && p.tma_epilogue && p.epilogue != DS_EPI_GEGLU &&
+      units > groups) {
     const int full = (units / groups) * groups, left = units - full;
-    if (left > 0 && left * 4 <= groups) {
-      p.tail_start = full;
-      p.tail_f = 4;
-      p.total_items = full + left * 4;
+    if (left > 0 && left <= 128) {
+      int parts = groups / left;
+      if (parts > 8) parts = 8;
+      if (parts > p.num_k_iters / 2) parts = p.num_k_iters / 2;
+      const long long need = 1024 + static_cast<long long>(left) * PAIR * kBM * BN * 4;
+      if (parts >= 2 && need <= splitk_ws_bytes && (reinterpret_cast<uintptr_t>(splitk_ws) & 15) == 0) {
+        p.tail_start = full;
+        p.tail_parts = parts;
+        p.total_items = full + left * parts;
+        p.ws = static_cast<float*>(splitk_ws);
+      }
     }
   }
   cfg.gridDim = dim3(groups * PAIR);
-  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR>, tmA, tmB, tmC, tmR, tmBt, p));
+  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR>, tmA, tmB, tmC, tmR, p));
   DS_LAUNCH_OK("gemm_bf16_tcgen05");
   return DS_OK;
 }
@@ -697,7 +762,7 @@ static bool make_out_map(CUtensorMap* m, const void* base, const GemmParams& p, 
 }
 
 static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& p, int conv_B, cudaStream_t stream,
-                    bool row_stats_zeroed = false) {
+                    bool row_stats_zeroed, void* splitk_ws, long long splitk_ws_bytes) {
   DeviceInfo dev;
   if (!get_device(&dev)) return DS_ERR_CUDA;
   const int bn = pick_bn(p.N, p.epilogue);
@@ -707,14 +772,12 @@ static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& 
     return e ? atoi(e) : 1;
   }();
   const int pair = (pair_env != 0 && p.num_m_tiles >= 2) ? 2 : 1;
-  CUtensorMap tmB, tmBt;  // tmBt: the 64-column slices of the tail split (box rows = 64 / pair)
+  CUtensorMap tmB;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
     const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn / pair)};
     if (!encode_tmap_bf16(&tmB, w, 2, dims, strides, box, nullptr)) return DS_ERR_CUDA;
-    const uint32_t box_t[2] = {kBK, static_cast<uint32_t>(64 / pair)};
-    if (!encode_tmap_bf16(&tmBt, w, 2, dims, strides, box_t, nullptr)) return DS_ERR_CUDA;
   }
   // coalesced TMA epilogue whenever the bf16 output (and residual) rows are 16-byte addressable
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -733,13 +796,13 @@ static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& 
   p.num_n_tiles = (p.N + bn - 1) / bn;
   p.conv_B = conv_B;
   if (pair == 2) {
-    if (bn == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, tmBt, p, dev.num_sms, stream);
-    if (bn == 192) return launch_gemm<192, 2>(tmA, tmB, tmC, tmR, tmBt, p, dev.num_sms, stream);
-    return launch_gemm<128, 2>(tmA, tmB, tmC, tmR, tmBt, p, dev.num_sms, stream);
+    if (bn == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+    if (bn == 192) return launch_gemm<192, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+    return launch_gemm<128, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
   }
-  if (bn == 256) return launch_gemm<256, 1>(tmA, tmB, tmC, tmR, tmBt, p, dev.num_sms, stream);
-  if (bn == 192) return launch_gemm<192, 1>(tmA, tmB, tmC, tmR, tmBt, p, dev.num_sms, stream);
-  return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, tmBt, p, dev.num_sms, stream);
+  if (bn == 256) return launch_gemm<256, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+  if (bn == 192) return launch_gemm<192, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+  return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
 }
 
 }  // namespace ds
@@ -804,7 +867,16 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
   p.num_m_tiles = (a->M + kBM - 1) / kBM;
   p.num_k_iters = (a->K + kBK - 1) / kBK;
   p.conv = 0;
-  return run_gemm(tmA, a->w, a->ldw, p, 0, static_cast<cudaStream_t>(stream), a->row_stats_zeroed != 0);
+  return run_gemm(tmA, a->w, a->ldw, p, 0, static_cast<cudaStream_t>(stream), a->row_stats_zeroed != 0, a->splitk_ws,
+                  a->splitk_ws_bytes);
+}
+
+extern "C" int64_t ds_gemm_splitk_ws_bytes(void) {
+  int sms = 256;
+  ds::DeviceInfo dev;
+  if (ds::get_device(&dev)) sms = dev.num_sms;
+  // at most (pairs - 1) tail units of 256 x 256 fp32, plus the counter header
+  return 1024 + static_cast<int64_t>(sms / 2) * 256 * 256 * 4;
 }
 
 extern "C" int ds_conv3x3_nhwc(const ds_conv3x3_args* a, void* stream) {
@@ -855,5 +927,6 @@ extern "C" int ds_conv3x3_nhwc(const ds_conv3x3_args* a, void* stream) {
   p.Ho = Ho;
   p.Wo = Wo;
   p.cin_chunks = a->Cin / kBK;
-  return run_gemm(tmA, a->w, 9 * a->Cin, p, a->B, static_cast<cudaStream_t>(stream));
+  return run_gemm(tmA, a->w, 9 * a->Cin, p, a->B, static_cast<cudaStream_t>(stream), false, a->splitk_ws,
+                  a->splitk_ws_bytes);
 }

@@ -116,6 +116,26 @@ def ip_mask(bbox: torch.Tensor, seq_len: int, aspect_ratio: float, tokens_per_ip
 
 
 # ---------------------------------------------------------------------------------------------- GEMM / conv
+_SPLITK_WS = {}
+SPLITK = True      # DenoiseStepper turns it off when it runs concurrent kernel chains (one workspace per device)
+
+
+def _splitk_ws():
+    """The zeroed split-K workspace of the current device: ds_gemm_bf16 / ds_conv3x3_nhwc leave it zeroed, so one
+    buffer serves every call as long as the calls are ordered (one stream, or a captured graph of one chain).
+    Allocated on first use — for graph capture that is the warm-up launch outside the capture."""
+    if not SPLITK:
+        return None
+    dev = torch.cuda.current_device()
+    ws = _SPLITK_WS.get(dev)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None                                    # never allocate (memset) inside a capture
+        ws = torch.zeros(int(lib.ds_gemm_splitk_ws_bytes()) // 4, dtype=f32, device=f"cuda:{dev}")
+        _SPLITK_WS[dev] = ws
+    return ws
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_NONE,
          residual: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
          out: Optional[torch.Tensor] = None, out_fp32: bool = False, out_scale: float = 0.0,
@@ -170,12 +190,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         _req(row_stats_out, f32, "gemm.row_stats_out", 1)
         if row_stats_out.numel() < 2 * M or out_fp32:
             raise DsEngineError("gemm: row_stats_out must hold 2*M floats and needs a bf16 output")
+    ws = _splitk_ws()
     args = GemmArgs(a=a.data_ptr(), w=w.data_ptr(), out=out.data_ptr(), bias=_ptr(bias), rowbias=_ptr(rowbias),
                     residual=_ptr(residual), M=M, N=N, K=K, lda=K, ldw=K, ldo=n_out, ldres=n_out,
                     rows_per_batch=rows_per_batch, rowbias_ld=rowbias_ld, epilogue=epilogue, out_fp32=int(out_fp32),
                     out_scale=out_scale, ln_stats=_ptr(ln_stats), ln_colsum=_ptr(ln_colsum), ln_eps=float(ln_eps),
                     row_stats_out=_ptr(row_stats_out), zero_rows=_ptr(zero_rows),
-                    row_stats_zeroed=int(bool(row_stats_zeroed)))
+                    row_stats_zeroed=int(bool(row_stats_zeroed)), splitk_ws=_ptr(ws),
+                    splitk_ws_bytes=0 if ws is None else ws.numel() * 4)
     check(lib.ds_gemm_bf16(C.byref(args), _stream()), "ds_gemm_bf16")
     return out
 
@@ -207,10 +229,12 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
         _req(residual, bf16, "conv3x3.residual")
         if residual.numel() != B * Ho * Wo * Cout:
             raise DsEngineError("conv3x3: residual must match the output shape")
+    ws = _splitk_ws()
     args = Conv3x3Args(x=x.data_ptr(), w=w.data_ptr(), out=out.data_ptr(), bias=_ptr(bias), rowbias=_ptr(rowbias),
                        residual=_ptr(residual), B=B, H=H, W=W, Cin=Cin, Cout=Cout, stride=stride,
                        rowbias_ld=0 if rowbias is None else rowbias.stride(0),
-                       out_fp32=int(out_fp32), out_scale=0.0)
+                       out_fp32=int(out_fp32), out_scale=0.0, splitk_ws=_ptr(ws),
+                       splitk_ws_bytes=0 if ws is None else ws.numel() * 4)
     check(lib.ds_conv3x3_nhwc(C.byref(args), _stream()), "ds_conv3x3_nhwc")
     return out
 

@@ -241,6 +241,7 @@ class DenoiseStepper:
         self.chains = max(1, min(want, B2))
         self._parts, self._side = [(0, B2)], []
         if self.chains > 1:
+            ops.SPLITK = False      # the split-K workspace is per device: concurrent chains must not share it
             cuts = [round(k * B2 / self.chains) for k in range(self.chains + 1)]
             self._parts = [(cuts[k], cuts[k + 1]) for k in range(self.chains) if cuts[k + 1] > cuts[k]]
             self._cond_parts = [self.cond.rows(s, e) for s, e in self._parts]

@@ -106,6 +106,12 @@ int ds_ip_mask(const float* bbox, float* mask, int B, int N, double aspect_ratio
  *             16-byte rows only.  zero_rows != NULL: the call also resets that [M][2] buffer (the first n-tile of
  *             every m-tile does it), which lets a chain of GEMMs rotate three statistics buffers without any
  *             memset node: the consumer of buffer k clears buffer k+2.
+ * Split-K tail: the kernel is persistent (one CTA pair per two SMs, static round-robin over 256 x BN output tiles);
+ *   when the tile count is not a multiple of the resident pairs, the tiles of the partial last round are cut along
+ *   K into slices that run on different pairs, reduced in fp32 through `splitk_ws` (vector red.global.add) and
+ *   finished by whichever slice arrives last.  The caller provides a 16-byte aligned workspace that is ALL ZERO on
+ *   entry (ds_gemm_splitk_ws_bytes() bytes cover every shape; the kernel leaves it all zero again) and must not be
+ *   shared by GEMMs running concurrently on different streams.  NULL simply disables the feature.
  * Constraints: K % 8 == 0, lda % 8 == 0 (16-byte TMA strides). M, N, K tails are handled by TMA
  * zero-fill and masked stores.
  * --------------------------------------------------------------------------------------------- */
@@ -134,9 +140,13 @@ typedef struct {
   float* row_stats_out;   /* [M][2] fp32 or NULL (see "producer" above)     */
   float* zero_rows;       /* [M][2] fp32 or NULL: rows reset to 0 by this call */
   int32_t row_stats_zeroed; /* 1: row_stats_out is already 0, skip the memset  */
+  void* splitk_ws;        /* split-K workspace (see below) or NULL             */
+  int64_t splitk_ws_bytes;
 } ds_gemm_args;
 
 int ds_gemm_bf16(const ds_gemm_args* args, void* stream);
+/* bytes of split-K workspace that suffice for any ds_gemm_bf16 / ds_conv3x3_nhwc call on the current device */
+int64_t ds_gemm_splitk_ws_bytes(void);
 
 /* ---------------------------------------------------------------------------------------------
  * 3x3 convolution, padding 1, stride 1 or 2, NHWC bf16, as an implicit GEMM on tcgen05:
@@ -162,6 +172,8 @@ typedef struct {
   int32_t rowbias_ld; /* row stride of rowbias in floats; 0 means Cout */
   int32_t out_fp32;
   float out_scale;
+  void* splitk_ws;    /* as in ds_gemm_args */
+  int64_t splitk_ws_bytes;
 } ds_conv3x3_args;
 
 int ds_conv3x3_nhwc(const ds_conv3x3_args* args, void* stream);

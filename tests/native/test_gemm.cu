@@ -148,6 +148,11 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(dRes, hRes.data(), hRes.size() * 2, cudaMemcpyHostToDevice));
   }
 
+  // split-K workspace: all zero on entry, the kernels must leave it all zero (checked below)
+  const long long ws_bytes = ds_gemm_splitk_ws_bytes();
+  void* dWs = nullptr;
+  CK(cudaMalloc(&dWs, ws_bytes));
+  CK(cudaMemset(dWs, 0, ws_bytes));
   auto run = [&]() -> int {
     if (c.conv) {
       ds_conv3x3_args a;
@@ -165,6 +170,8 @@ int main(int argc, char** argv) {
       a.Cout = c.Cout;
       a.stride = c.stride;
       a.out_fp32 = c.out_fp32;
+      a.splitk_ws = dWs;
+      a.splitk_ws_bytes = ws_bytes;
       return ds_conv3x3_nhwc(&a, nullptr);
     }
     ds_gemm_args a;
@@ -185,10 +192,13 @@ int main(int argc, char** argv) {
     a.rows_per_batch = rows_per_batch;
     a.epilogue = c.epi;
     a.out_fp32 = c.out_fp32;
+    a.splitk_ws = dWs;
+    a.splitk_ws_bytes = ws_bytes;
     return ds_gemm_bf16(&a, nullptr);
   };
 
   int rc = run();
+  if (rc == DS_OK) rc = run();  // a second launch on the same workspace: it must have been left clean
   if (rc != DS_OK) {
     printf("CASE %d %s FAIL rc=%d err=%s\n", id, c.name, rc, ds_last_error());
     return 1;
@@ -200,6 +210,16 @@ int main(int argc, char** argv) {
   }
   std::vector<uint8_t> hOut(out_bytes);
   CK(cudaMemcpy(hOut.data(), dOut, out_bytes, cudaMemcpyDeviceToHost));
+  {
+    std::vector<uint32_t> hWs((size_t)ws_bytes / 4);
+    CK(cudaMemcpy(hWs.data(), dWs, ws_bytes, cudaMemcpyDeviceToHost));
+    size_t dirty = 0;
+    for (uint32_t v : hWs) dirty += (v & 0x7fffffffu) != 0;  // -0.0f counts as clean
+    if (dirty) {
+      printf("CASE %d %s FAIL split-K workspace not left clean: %zu non-zero words\n", id, c.name, dirty);
+      return 1;
+    }
+  }
 
   // ---- CPU restatement on all / sampled outputs
   auto a_at = [&](int m, int k) -> float {

@@ -43,7 +43,7 @@ def test_struct_layout_matches_header_field_order():
             decl = decl.strip()
             if not decl:
                 continue
-            decl = re.sub(r"^(const\s+)?(void|float|double|int32_t)\s*\*?\s*", "", decl)
+            decl = re.sub(r"^(const\s+)?(void|float|double|int32_t|int64_t)\s*\*?\s*", "", decl)
             names += [n.strip().lstrip("*") for n in decl.split(",")]
         assert names == [f[0] for f in cls._fields_], struct_name
 
