@@ -1,5 +1,14 @@
 // attn_tcgen05.cu — fused attention for head_dim 64 on tcgen05 tensor cores (sm_100a).
 //
+// Kernels in this file (defaults first; the older variants stay selectable for A/B timing and as fallbacks):
+//   flash_attn_v5_kernel     self-attention / Resampler attention, DEFAULT (DS_FLASH=5): two independent
+//                            online-softmax streams per CTA, S / O / P all in TMEM (section 1d)
+//   flash_attn_kernel        the round-1 self-attention kernel (DS_FLASH=2): P through shared memory (section 1)
+//   cross_ip_attn_v2_kernel  text + bbox-masked IP cross-attention, DEFAULT: persistent, two softmax warp groups,
+//                            P in TMEM (section 2b)
+//   cross_ip_attn_kernel     one-tile-per-CTA version (DS_CROSS=1, and the fallback when the padded key counts do
+//                            not fit v2's TMEM layout) (section 2)
+//
 // (1) flash_attn_kernel — softmax(Q K^T * scale) V with an online softmax, no mask (self-attention of
 //     AttnProcessor2_0, src/models/attention_processor.py:69-81; also used for the Resampler's perceiver
 //     attention, src/models/resampler.py:64-74).  One CTA = one 128-query tile of one (batch, head);
@@ -8,9 +17,9 @@
 //       warp 1   MMA issuer   : S = Q K_j^T (M128 N128 K64) into TMEM; O (+)= P_j V_j (M128 N64 K128),
 //                               V consumed MN-major straight from its [kv][d] TMA tile
 //       warp 2   TMEM allocator (256 columns: S 0..127, O 128..191)
-//       warps 4-11 softmax    : 2 threads per query row (64 key columns each).  tcgen05.ld S, running max in the log2 domain with LAZY
-//                               rescaling (O/l are only rescaled when the row max grows by > 2^8), exp2,
-//                               P_j -> bf16 into swizzled shared memory as the next MMA's A operand.
+//       warps 4-11 softmax    : 2 threads per query row (64 key columns each).  tcgen05.ld S, running max in the
+//                               log2 domain with LAZY rescaling (O/l are only rescaled when the row max grows by
+//                               > 2^8), exp2, P_j -> bf16 into swizzled shared memory as the next MMA's A operand.
 //                               O never leaves TMEM until the final 1/l normalisation.
 //     Q/K/V are addressed by 3-D tensor maps {columns, tokens, batch} over the fused projection output, so
 //     the head split/transposes of the reference (:69-72,80) are never materialised.

@@ -2,18 +2,24 @@
 //
 //   out[M][Nout] = epilogue( A[M][K] * W[N][K]^T ),  fp32 accumulation in TMEM.
 //
-// One CTA per SM (persistent, static round-robin over 128 x BN output tiles), 384 threads:
-//   warp 0    TMA producer   : one lane streams A (128x64) and W (BNx64) k-slices into a STAGES-deep
-//                              shared-memory ring (128-byte swizzle), arming a "full" mbarrier per stage
-//   warp 1    MMA issuer     : one lane issues 4 x tcgen05.mma (M=128, N=BN, K=16) per stage into one of
-//                              two TMEM accumulators, tcgen05.commit frees the stage / publishes the tile
-//   warp 2    TMEM allocator : 2*BN columns (double-buffered accumulator)
+// One CTA per SM, persistent, 384 threads; normally launched as CTA PAIRS (cluster of 2, tcgen05 cta_group::2): a pair
+// owns a 256 x BN output tile (BN = 256; 192 for N = 320; 128 only for N <= 128), static round-robin over the tiles:
+//   warp 0    TMA producer   : one lane streams A (128x64) and this CTA's half of W (BN/2 x 64) k-slices into a
+//                              5-7-stage shared-memory ring (128-byte swizzle), arming a "full" mbarrier per stage
+//   warp 1    MMA issuer     : the pair's leader issues 4 x tcgen05.mma (M=256, N=BN, K=16) per stage into one of
+//                              two TMEM accumulators; tcgen05.commit (multicast to both CTAs) frees the stage /
+//                              publishes the tile
+//   warp 2    TMEM allocator : double-buffered accumulator (256 or 512 columns)
 //   warps 4-11 epilogue      : tcgen05.ld the finished accumulator (thread <-> output row; 4 lane quadrants
-//                              x 2 column halves); bf16 outputs are staged as 128-B-swizzled [128][64] smem tiles
-//                              and written with TMA stores (residual tiles arrive by TMA loads into the same
-//                              staging tile), so all epilogue global traffic is full-line and coalesced; apply
-//                              bias / row-bias / GEGLU / activation / residual in fp32, round once, store —
-//                              overlapping the next tile's MMAs thanks to the second accumulator
+//                              x 2 column groups); per-tile bias / LayerNorm column sums / conv row-bias are staged
+//                              in shared memory once per tile; bf16 outputs are staged as 128-B-swizzled [128][64]
+//                              smem tiles and written with TMA stores (residual tiles arrive by TMA loads into the
+//                              same staging tile), so all epilogue global traffic is full-line and coalesced;
+//                              bias / row-bias / LayerNorm-on-A / GEGLU / activation / residual in fp32, one
+//                              rounding, optional per-row (sum, sum of squares) of the outputs for the next
+//                              LayerNorm — overlapping the next tile's MMAs thanks to the second accumulator
+// Split-K tail (big 3x3 convs): see GemmParams.  Programmatic dependent launch: the prologue (barriers, TMEM, tensor
+// map prefetch) runs while the previous kernel drains.
 //
 // conv3x3 mode (ds_conv3x3_nhwc): identical MMA pipeline; only the producer and the row->address map
 // change.  An M tile is an 8x16 patch of output pixels of one image; for filter tap (r,s) and channel
