@@ -67,7 +67,7 @@ static const Case cases[] = {
     // full check; the second also has an N tail (640 = 2.5 tiles) and a residual, the third is a conv
     {"gemm_tailsplit_20480x512x128", 0, 20480, 512, 128, 0, 0, 0, 0, 0, 0, DS_EPI_NONE, 1, 0, 0, 0, 0, 0},
     {"gemm_tailsplit_ntail_9984x640x64_res", 0, 9984, 640, 64, 0, 0, 0, 0, 0, 0, DS_EPI_NONE, 1, 0, 1, 0, 0, 0},
-    {"conv_tailsplit_5x64x64_64_512", 1, 0, 0, 0, 5, 64, 64, 64, 512, 1, DS_EPI_NONE, 1, 1, 1, 0, 0, 0},
+    {"conv_tailsplit_5x64x64_64_512", 1, 0, 0, 0, 5, 64, 64, 64, 512, 1, DS_EPI_NONE, 1, 1, 1, 0, 1, 0},
     // timing cases (cfg2 shapes), sampled check
     {"T_gemm_attnproj_32768x640x640", 0, 32768, 640, 640, 0, 0, 0, 0, 0, 0, DS_EPI_NONE, 1, 0, 1, 0, 1, 1},
     {"T_gemm_qkv_8192x3840x1280", 0, 8192, 3840, 1280, 0, 0, 0, 0, 0, 0, DS_EPI_NONE, 0, 0, 0, 0, 1, 1},

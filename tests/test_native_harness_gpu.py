@@ -31,4 +31,12 @@ def test_native_cases_pass(name):
         line = (r.stdout.strip().splitlines() or ["<no output>"])[-1]
         if r.returncode != 0 or " PASS " not in line:
             failed.append(f"case {i}: rc={r.returncode} {line} {r.stderr[-200:]}")
+        elif "tailsplit" in line:
+            # the split-K tail is on by default only for tiles of >= 128 k-blocks (the big convs); force it for
+            # these small full-check shapes so the reduction / last-arriver / workspace-cleanliness logic is covered
+            r = subprocess.run([exe, str(i)], capture_output=True, text=True, timeout=300,
+                               env=dict(os.environ, DS_GEMM_SPLITK="1"))
+            line = (r.stdout.strip().splitlines() or ["<no output>"])[-1]
+            if r.returncode != 0 or " PASS " not in line:
+                failed.append(f"case {i} (DS_GEMM_SPLITK=1): rc={r.returncode} {line} {r.stderr[-200:]}")
     assert not failed, "\n".join(failed)
