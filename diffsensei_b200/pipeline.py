@@ -241,7 +241,6 @@ class DenoiseStepper:
         self.chains = max(1, min(want, B2))
         self._parts, self._side = [(0, B2)], []
         if self.chains > 1:
-            ops.SPLITK = False      # the split-K workspace is per device: concurrent chains must not share it
             cuts = [round(k * B2 / self.chains) for k in range(self.chains + 1)]
             self._parts = [(cuts[k], cuts[k + 1]) for k in range(self.chains) if cuts[k + 1] > cuts[k]]
             self._cond_parts = [self.cond.rows(s, e) for s, e in self._parts]
@@ -268,15 +267,20 @@ class DenoiseStepper:
         else:
             main = torch.cuda.current_stream(self.dev)
             eps = self._eps
-            for k, (s, e) in enumerate(self._parts):
-                st = main if k == 0 else self._side[k - 1]
-                if k:
-                    st.wait_stream(main)                       # fork (inside a capture: joins the captured graph)
-                with torch.cuda.stream(st):
-                    self.unet.forward_nhwc(self.model_in[s:e], self.temb_cur[s:e], self._cond_parts[k],
-                                           None if self.db is None else self.db[s:e], self.round_bf16, out=eps[s:e])
-            for st in self._side:
-                main.wait_stream(st)                           # join before the CFG blend needs both halves
+            prev_splitk, ops.SPLITK = ops.SPLITK, False   # one split-K workspace per device: never shared by
+            try:                                           # kernels that may overlap (also keeps it out of the capture)
+                for k, (s, e) in enumerate(self._parts):
+                    st = main if k == 0 else self._side[k - 1]
+                    if k:
+                        st.wait_stream(main)                   # fork (inside a capture: joins the captured graph)
+                    with torch.cuda.stream(st):
+                        self.unet.forward_nhwc(self.model_in[s:e], self.temb_cur[s:e], self._cond_parts[k],
+                                               None if self.db is None else self.db[s:e], self.round_bf16,
+                                               out=eps[s:e])
+                for st in self._side:
+                    main.wait_stream(st)                       # join before the CFG blend needs both halves
+            finally:
+                ops.SPLITK = prev_splitk
         ops.cfg_ddim_step_(eps, self.lat, self.model_in, self.coef_cur, self.guidance)   # :332-337 (+ :315 of next)
 
     @torch.no_grad()
