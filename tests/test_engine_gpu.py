@@ -189,3 +189,38 @@ def test_resampler_matches_executed_reference():
 def test_smoke_entry_point():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+@pytest.mark.skipif(os.environ.get("DS_FULL_PARITY") != "1",
+                    reason="full-size SDXL oracle forward on the host (~1 min, 12 GB of fp32 weights): opt-in, "
+                           "DS_FULL_PARITY=1")
+def test_full_size_cfg1_unet_forward_matches_oracle():
+    """BASELINE configs[0] (512x512, bs 1, 1 character ref) at the REAL SDXL+IP topology: one UNetMangaModel.forward
+    of the engine against the CPU oracle on the same random weights and inputs.  Exercises what the TINY config
+    cannot: 10-layer transformers at C = 1280, the LayerNorm-folded GEMMs at real widths, N = 4096 / 1024 attention."""
+    import diffsensei_b200 as ds
+    from diffsensei_b200.weights import random_state_dict, unet_param_shapes
+    from oracle.unet import OracleUNet
+    cfg = ds.SDXL_MANGA
+    sd = random_state_dict(unet_param_shapes(cfg), seed=7, device="cpu", dtype=torch.bfloat16)
+    with torch.device("meta"):
+        oracle = OracleUNet(cfg)
+    oracle = oracle.to_empty(device="cpu")
+    oracle.load_state_dict({k: v.float() for k, v in sd.items()})
+    oracle.eval().set_ip_scale(0.6)
+    engine = ds.UNetMangaEngine(cfg, DEV)
+    engine.load_state_dict(sd)
+    engine.set_ip_scale(0.6)
+    h = w = 64
+    lat, ehs, pooled, time_ids, bbox, dialog = _inputs(cfg, 1, h, w, seed=11, n_chars=1, dialogs=True)
+    x = torch.cat([lat] * 2)
+    ehs = ehs.to(bf16).float()            # both sides see the same bf16-representable conditions
+    with torch.no_grad():
+        want = oracle(x, 741, ehs, pooled, time_ids, bbox, 1.0, dialog)
+    out = engine.forward(x.to(DEV), torch.tensor(741), ehs.to(DEV, bf16),
+                         added_cond_kwargs={"text_embeds": pooled.to(DEV), "time_ids": time_ids.to(DEV)},
+                         cross_attention_kwargs={"bbox": bbox.to(DEV), "aspect_ratio": 1.0},
+                         dialog_bbox=dialog.to(DEV)).sample
+    err = rel_l2(out, want)
+    print(f"full-size cfg1 UNet forward rel-L2 vs fp32 oracle: {err:.3e}")
+    assert err < 5e-2
