@@ -191,9 +191,9 @@ def test_smoke_entry_point():
     __graft_entry__.smoke()
 
 
-@pytest.mark.skipif(os.environ.get("DS_FULL_PARITY") != "1",
-                    reason="full-size SDXL oracle forward on the host (~1 min, 12 GB of fp32 weights): opt-in, "
-                           "DS_FULL_PARITY=1")
+@pytest.mark.skipif(os.environ.get("DS_FULL_PARITY") == "0",
+                    reason="full-size SDXL oracle forward on the host (45 s, ~25 GB of host RAM) disabled by "
+                           "DS_FULL_PARITY=0")
 def test_full_size_cfg1_unet_forward_matches_oracle():
     """BASELINE configs[0] (512x512, bs 1, 1 character ref) at the REAL SDXL+IP topology: one UNetMangaModel.forward
     of the engine against the CPU oracle on the same random weights and inputs.  Exercises what the TINY config
@@ -222,5 +222,5 @@ def test_full_size_cfg1_unet_forward_matches_oracle():
                          cross_attention_kwargs={"bbox": bbox.to(DEV), "aspect_ratio": 1.0},
                          dialog_bbox=dialog.to(DEV)).sample
     err = rel_l2(out, want)
-    print(f"full-size cfg1 UNet forward rel-L2 vs fp32 oracle: {err:.3e}")
-    assert err < 5e-2
+    print(f"full-size cfg1 UNet forward rel-L2 vs fp32 oracle: {err:.3e}")   # measured on B200: 1.75e-2
+    assert err < 3e-2
