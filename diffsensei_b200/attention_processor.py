@@ -46,17 +46,23 @@ def _unsupported(attn, hidden_states, attention_mask):
 
 
 class _PackCache:
-    """Fused/packed copies of the owning Attention module's weights, rebuilt when the parameters change."""
+    """Derived tensors (packed weights, projected K|V) keyed on the IDENTITY and version of their source tensors.
+
+    The cache keeps strong references to the keyed tensors: an address can therefore never be recycled by the
+    caching allocator while its entry is alive (a `data_ptr()` key would silently hit on panel 2's freshly allocated
+    ``encoder_hidden_states`` that landed in panel 1's freed block), and an in-place update bumps ``_version``."""
 
     def __init__(self):
-        self._key = None
+        self._refs = None
         self._val = None
 
     def get(self, tensors, build):
-        key = tuple((t.data_ptr(), t._version, t.dtype) for t in tensors)
-        if key != self._key:
+        tensors = tuple(tensors)
+        hit = (self._refs is not None and len(self._refs) == len(tensors) and
+               all(t is r and t._version == v for t, (r, v) in zip(tensors, self._refs)))
+        if not hit:
             self._val = build()
-            self._key = key
+            self._refs = tuple((t, t._version) for t in tensors)
         return self._val
 
 
@@ -128,20 +134,36 @@ class MaskedIPAttnProcessor2_0(nn.Module):
         return _out_proj(attn, a, hs)
 
 
-class _SiteView:
-    """What ``UNetMangaEngine.attn_processors`` hands out per site: API-shaped, not on the compute path."""
+def build_processor_table(engine) -> Dict[str, nn.Module]:
+    """The 140 processors ``UNetMangaModel.set_manga_modules`` installs (src/models/unet.py:56-83), as real
+    ``nn.Module`` s in diffusers' ``attn_processors`` order — module registration order of UNet2DConditionModel:
+    ``down_blocks``, ``up_blocks``, then ``mid_block`` (which is why IP-Adapter checkpoints index the mid-block
+    processor last) — so ``torch.nn.ModuleList(unet.attn_processors.values()).load_state_dict(sd["ip_adapter"])``
+    (src/models/utils.py:46-48) addresses the same ``"<2i+1>.to_k_ip.weight"`` keys as on the reference.
 
-    def __init__(self, engine, is_cross: bool):
-        self._engine = engine
-        if is_cross:
-            self.scale = engine.ip_scale
-
-
-def build_processor_table(engine) -> Dict[str, object]:
+    ``to_k_ip.weight`` / ``to_v_ip.weight`` are Parameters that ALIAS the two halves of the engine's packed
+    ``[to_k_ip ; to_v_ip]`` matrix: loading a checkpoint into the processors writes the weights the fused
+    cross-attention path reads (the engine re-projects its hoisted K|V when their version counter moves), and
+    ``proc.scale`` is the value the engine passes to the kernel for that layer (pipeline_diffsensei.py:172-178)."""
     from .weights import transformer_sites
-    table: Dict[str, object] = {}
-    for p, _c, depth in transformer_sites(engine.cfg):
+    if not getattr(engine, "_loaded", False):
+        raise RuntimeError("attn_processors: load_state_dict first (the processors alias the engine's weights)")
+    cfg = engine.cfg
+    sites = list(transformer_sites(cfg))
+    order = [s for s in sites if s[0].startswith("down_blocks")] + [s for s in sites if s[0].startswith("up_blocks")] \
+        + [s for s in sites if s[0].startswith("mid_block")]
+    table: Dict[str, nn.Module] = {}
+    for p, c, depth in order:
+        t = engine.transformers[p]
         for k in range(depth):
-            table[f"{p}.transformer_blocks.{k}.attn1.processor"] = _SiteView(engine, False)
-            table[f"{p}.transformer_blocks.{k}.attn2.processor"] = _SiteView(engine, True)
+            blk = t.blocks[k]
+            table[f"{p}.transformer_blocks.{k}.attn1.processor"] = AttnProcessor2_0()
+            with torch.device("meta"):                  # no host allocation / init for the 2 x [C, 2048] Linears
+                proc = MaskedIPAttnProcessor2_0(hidden_size=c, cross_attention_dim=cfg.cross_attention_dim,
+                                                scale=engine.ip_scale, num_ip_tokens=cfg.num_ip_tokens,
+                                                num_dummy_tokens=cfg.num_dummy_tokens)
+            proc.to_k_ip.weight = nn.Parameter(blk.wkv_ip[:c], requires_grad=False)
+            proc.to_v_ip.weight = nn.Parameter(blk.wkv_ip[c:], requires_grad=False)
+            blk.proc = proc
+            table[f"{p}.transformer_blocks.{k}.attn2.processor"] = proc
     return table

@@ -1242,10 +1242,10 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
   if (!make_tok_map(&tmQ, q, q_cols, ldq, Nq, B, kTile)) return DS_ERR_CUDA;
   if (!make_tok_map(&tmK, k, kv_cols, ldkv, Nkv, B, kTile)) return DS_ERR_CUDA;
   if (!make_tok_map(&tmV, v, kv_cols, ldkv, Nkv, B, kTile)) return DS_ERR_CUDA;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  if (!attr_set[device_slot()]) {
     DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlashSmemBytes));
-    attr_set = true;
+    attr_set[device_slot()] = true;
   }
   FlashParams p;
   p.out = static_cast<__nv_bfloat16*>(out);
@@ -1277,7 +1277,8 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
       const char* e = getenv("DS_FLASH_F2");
       return e ? atoi(e) : 1;
     }();
-    static bool attr5_set = false;
+    static bool attr5_set_dev[kMaxDevices] = {};
+    bool& attr5_set = attr5_set_dev[device_slot()];
     if (!attr5_set) {
       DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
       DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
@@ -1363,7 +1364,8 @@ extern "C" int ds_attention_cross_ip(const ds_cross_ip_args* a, void* stream) {
   const int n_keys = nt_pad + nip_pad;
   const int kv_bytes = ((n_keys * 128) + 1023) & ~1023;
   const int smem = kTileBytes + 2 * kv_bytes + ((n_keys + 63) / 64) * kTileBytes + 1024 + 128;
-  static int attr_smem = 0;
+  static int attr_smem_dev[kMaxDevices] = {};
+  int& attr_smem = attr_smem_dev[device_slot()];
   if (smem > attr_smem) {
     DS_CUDA_OK(cudaFuncSetAttribute(cross_ip_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
@@ -1394,7 +1396,8 @@ extern "C" int ds_attention_cross_ip(const ds_cross_ip_args* a, void* stream) {
     DS_REQUIRE(total_ll < (1ll << 30), "ds_attention_cross_ip: too many tiles");
     const int total = static_cast<int>(total_ll);
     const int smem2 = 2 * kTileBytes + 2 * kv_bytes + 1024 + 128 + 2 * kTile * 4;
-    static int attr_smem2 = 0;
+    static int attr_smem2_dev[kMaxDevices] = {};
+    int& attr_smem2 = attr_smem2_dev[device_slot()];
     if (smem2 > attr_smem2) {
       DS_CUDA_OK(cudaFuncSetAttribute(cross_ip_attn_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
       DS_CUDA_OK(cudaFuncSetAttribute(cross_ip_attn_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));

@@ -36,8 +36,10 @@ __global__ void dialog_embed_add_kernel(uint4* __restrict__ sample, const float*
     }
     box[threadIdx.x][0] = max(0, v[0]);
     box[threadIdx.x][1] = max(0, v[1]);
-    box[threadIdx.x][2] = min(W, v[2]);
-    box[threadIdx.x][3] = min(H, v[3]);
+    // x2 / y2 are only clamped from above (unet.py:107-108) and then used as Python slice ends: a NEGATIVE end
+    // counts from the far edge (sample[..., y1:y2, x1:x2] with y2 = -3 stops 3 rows before the bottom).
+    box[threadIdx.x][2] = v[2] < 0 ? max(0, W + v[2]) : min(W, v[2]);
+    box[threadIdx.x][3] = v[3] < 0 ? max(0, H + v[3]) : min(H, v[3]);
   }
   __syncthreads();
   const int cv = C >> 3;

@@ -26,6 +26,15 @@ struct DeviceInfo {
 };
 bool get_device(DeviceInfo* out);
 
+// Function attributes (dynamic-smem opt-in) and occupancy answers are PER DEVICE: every cache of them is an array
+// indexed by the current device's ordinal (a process may drive several GPUs through the same library).
+constexpr int kMaxDevices = 64;
+inline int device_slot() {
+  int d = 0;
+  (void)cudaGetDevice(&d);
+  return d & (kMaxDevices - 1);
+}
+
 #define DS_REQUIRE(cond, ...)        \
   do {                               \
     if (!(cond)) {                   \

@@ -660,11 +660,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
                        void* splitk_ws, long long splitk_ws_bytes) {
   GemmParams p = p_in;
   using Cfg = GemmCfg<BN, PAIR>;
-  static bool attr_set = false;  // benign race: idempotent
-  if (!attr_set) {
+  const int slot = device_slot();
+  static bool attr_set[kMaxDevices] = {};  // per device; benign race: idempotent
+  if (!attr_set[slot]) {
     DS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
-    attr_set = true;
+    attr_set[slot] = true;
   }
   const int units = ((p.num_m_tiles + PAIR - 1) / PAIR) * p.num_n_tiles;
   cudaLaunchConfig_t cfg = {};
@@ -681,7 +682,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   cfg.numAttrs = 2;
   // The schedule is persistent with a static stride, so every CTA (pair) must be co-resident: a pair needs both
   // SMs of one TPC, and not every TPC of a 148-SM part has two enabled SMs.  Ask the runtime how many clusters fit.
-  static int max_groups = 0;
+  static int max_groups_dev[kMaxDevices] = {};
+  int& max_groups = max_groups_dev[slot];
   if (max_groups == 0) {
     int n = num_sms / PAIR;
     if (PAIR == 2) {

@@ -205,10 +205,10 @@ extern "C" int ds_conv_in_3x3(const void* x, const float* w, const float* bias, 
   DeviceInfo dev;
   if (!get_device(&dev)) return DS_ERR_CUDA;
   const int smem = 37 * Cout * 4;
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
+  static bool attr_set[kMaxDevices] = {};
+  if (!attr_set[device_slot()] && smem > 48 * 1024) {
     DS_CUDA_OK(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+    attr_set[device_slot()] = true;
   }
   const int n_grp = H * ((W + 3) / 4);  // 4-pixel groups per image
   int gpc = (B * n_grp + dev.num_sms * 4 - 1) / (dev.num_sms * 4);  // ~4 CTAs per SM: amortise the weight staging

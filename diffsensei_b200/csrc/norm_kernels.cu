@@ -546,10 +546,10 @@ extern "C" int ds_groupnorm_silu(const void* x, void* y, const float* gamma, con
       const size_t smem = 128 + 5760 + static_cast<size_t>(nbuf) * slice_stride;
       const void* fn = apply_silu ? reinterpret_cast<const void*>(gn_fused_kernel<true>)
                                   : reinterpret_cast<const void*>(gn_fused_kernel<false>);
-      static size_t attr_smem[2] = {0, 0};
-      if (smem > attr_smem[apply_silu ? 1 : 0]) {
+      static size_t attr_smem[kMaxDevices][2] = {};
+      if (smem > attr_smem[device_slot()][apply_silu ? 1 : 0]) {
         DS_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_smem[apply_silu ? 1 : 0] = smem;
+        attr_smem[device_slot()][apply_silu ? 1 : 0] = smem;
       }
       // scratch (ds_groupnorm_scratch_floats): [4*B*groups floats: fp64 sums of the two-kernel path] [2*B: arrival
       // counters] [B][num_sms][2*groups] fp32 partials

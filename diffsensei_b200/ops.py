@@ -24,10 +24,19 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _on_current_device(t: torch.Tensor, name: str) -> None:
+    """libdsengine launches on the CURRENT device's current stream (its function attributes, occupancy answers and
+    split-K workspace are per device): a tensor on another GPU is an error, never a silent cross-device launch."""
+    if t.device.index != torch.cuda.current_device():
+        raise DsEngineError(f"{name}: tensor lives on {t.device} but the current CUDA device is "
+                            f"cuda:{torch.cuda.current_device()} (wrap the call in torch.cuda.device(...))")
+
+
 def _req_rows(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     """2-D tensor whose rows are contiguous (a column slice of a wider contiguous table is allowed)."""
     if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != dtype or t.dim() != 2 or t.stride(1) != 1:
         raise DsEngineError(f"{name}: expected a 2-D CUDA {dtype} tensor with unit column stride")
+    _on_current_device(t, name)
     return t
 
 
@@ -36,6 +45,7 @@ def _req(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None) -> torch
         raise DsEngineError(f"{name}: expected a torch.Tensor, got {type(t)}")
     if not t.is_cuda:
         raise DsEngineError(f"{name}: tensor is on {t.device}; diffsensei_b200 has no CPU path")
+    _on_current_device(t, name)
     if t.dtype != dtype:
         raise DsEngineError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():

@@ -43,8 +43,10 @@ class DiffSenseiPipeline:
         self.image_proj_model = None
         self.magi_image_encoder = None
         self._guidance_scale = 5.0
-        self._graph = None
-        self._graph_key = None
+        # captured steppers, keyed by everything a CUDA graph bakes in (shapes, T, guidance, ip scales, dialog mode):
+        # panels of one shape re-use the graph and only refill its static buffers (DenoiseStepper.load_panel)
+        self._steppers = {}
+        self.max_cached_steppers = 8
 
     # ------------------------------------------------------------------------------ reference surface
     def register_manga_modules(self, magi_image_encoder=None, image_proj_model=None):
@@ -83,11 +85,21 @@ class DiffSenseiPipeline:
         dev = self.unet.device
         m = cfg.max_num_ips
         ip_bbox = [list(b) for b in ip_bbox[:m]]
+        rc = getattr(self.image_proj_model, "rc", None)
+        if clip_image_embeds is None or magi_image_embeds is None:
+            # a panel without characters: the reference pads with black images and then zeroes every padded
+            # character's embeddings (:118-132), i.e. the Resampler sees all-zero inputs on both branches
+            if rc is None:
+                raise ValueError("a panel without character references needs an image_proj_model that exposes its "
+                                 "ResamplerConfig (`.rc`) to size the zero embeddings")
+            clip_image_embeds = torch.zeros(1, 0, 257, rc.embedding_dim, dtype=bf16, device=dev)
+            magi_image_embeds = torch.zeros(1, 0, rc.magi_embedding_dim, dtype=bf16, device=dev)
         num_ips = min(clip_image_embeds.shape[1], m)
         clip = torch.zeros(1, m, *clip_image_embeds.shape[2:], dtype=clip_image_embeds.dtype, device=dev)
         magi = torch.zeros(1, m, magi_image_embeds.shape[-1], dtype=magi_image_embeds.dtype, device=dev)
-        clip[0, :num_ips] = clip_image_embeds[0, :num_ips].to(dev)      # padded characters stay zero (:131-132)
-        magi[0, :num_ips] = magi_image_embeds[0, :num_ips].to(dev)
+        if num_ips:
+            clip[0, :num_ips] = clip_image_embeds[0, :num_ips].to(dev)  # padded characters stay zero (:131-132)
+            magi[0, :num_ips] = magi_image_embeds[0, :num_ips].to(dev)
         while len(ip_bbox) < m:
             ip_bbox.append([0.0, 0.0, 0.0, 0.0])                        # :121-122
         image_embeds = self.image_proj_model(clip, magi)                               # :133
@@ -126,6 +138,24 @@ class DiffSenseiPipeline:
         return DenoiseStepper(self, latents, prompt_embeds, add_text_embeds, add_time_ids, bbox, aspect_ratio,
                               dialog_bbox, num_inference_steps, guidance_scale, use_graph, chains)
 
+    def stepper_for(self, latents, prompt_embeds, add_text_embeds, add_time_ids, bbox, aspect_ratio, dialog_bbox,
+                    num_inference_steps, guidance_scale, chains=None) -> "DenoiseStepper":
+        """A graph-captured stepper loaded with this panel: a cached one of the same key is refilled in place
+        (no re-capture), otherwise a new one is built and cached."""
+        key = (tuple(latents.shape), tuple(prompt_embeds.shape), None if dialog_bbox is None else
+               (tuple(dialog_bbox.shape), dialog_bbox.dtype == bf16), float(aspect_ratio), int(num_inference_steps),
+               float(guidance_scale), self.unet.scales_key(), chains, self.unet._ip_weights_version())
+        st = self._steppers.get(key)
+        if st is None:
+            st = self.make_stepper(latents, prompt_embeds, add_text_embeds, add_time_ids, bbox, aspect_ratio,
+                                   dialog_bbox, num_inference_steps, guidance_scale, True, chains)
+            while len(self._steppers) >= self.max_cached_steppers:
+                self._steppers.pop(next(iter(self._steppers)))
+            self._steppers[key] = st
+        else:
+            st.load_panel(latents, prompt_embeds, add_text_embeds, add_time_ids, bbox, dialog_bbox)
+        return st
+
     @torch.no_grad()
     def denoise(self, latents: torch.Tensor, prompt_embeds: torch.Tensor, add_text_embeds: torch.Tensor,
                 add_time_ids: torch.Tensor, bbox: torch.Tensor, aspect_ratio: float,
@@ -133,8 +163,12 @@ class DiffSenseiPipeline:
                 use_graph: bool = True, on_step=None) -> torch.Tensor:
         """pipeline_diffsensei.py:306-337.  ``latents`` NCHW fp32 (bs,4,h,w); conditions already concatenated
         [negative ; positive] along batch (:293-304).  Returns the final latents, NCHW fp32."""
-        st = self.make_stepper(latents, prompt_embeds, add_text_embeds, add_time_ids, bbox, aspect_ratio, dialog_bbox,
-                               num_inference_steps, guidance_scale, use_graph)
+        if use_graph:
+            st = self.stepper_for(latents, prompt_embeds, add_text_embeds, add_time_ids, bbox, aspect_ratio,
+                                  dialog_bbox, num_inference_steps, guidance_scale)
+        else:
+            st = self.make_stepper(latents, prompt_embeds, add_text_embeds, add_time_ids, bbox, aspect_ratio,
+                                   dialog_bbox, num_inference_steps, guidance_scale, False)
         for i, t in enumerate(st.timesteps):
             st.step(i)
             if on_step is not None:
@@ -175,6 +209,10 @@ class DiffSenseiPipeline:
         if num_ips != len(ip_bbox):
             raise ValueError(f"`ip_images` must have the same length as `ip_bbox`. But they are in length {num_ips} "
                              f"and {len(ip_bbox)}!")
+        if guidance_scale <= 1.0:
+            raise ValueError("guidance_scale <= 1 disables classifier-free guidance on the reference "
+                             "(pipeline_diffsensei.py:315-334: text-only batch, no blend); the engine's denoise step is "
+                             "the fused CFG + DDIM update and does not implement the guidance-free variant")
         self._guidance_scale = guidance_scale
         self.set_ip_scale(ip_scale)
         dev = self.unet.device
@@ -212,24 +250,19 @@ class DenoiseStepper:
                  aspect_ratio, dialog_bbox, num_inference_steps, guidance_scale, use_graph=True, chains=None):
         unet, dev = pipe.unet, pipe.unet.device
         self.unet, self.dev, self.guidance = unet, dev, float(guidance_scale)
-        bs = latents.shape[0]
-        if prompt_embeds.shape[0] != 2 * bs:
-            raise ValueError("denoise expects CFG-concatenated conditions: prompt_embeds.shape[0] == 2 * num_samples")
+        self.scheduler = pipe.scheduler
+        self.num_inference_steps = int(num_inference_steps)
+        self.aspect_ratio = float(aspect_ratio)
         self.timesteps = pipe.scheduler.set_timesteps(num_inference_steps, device=dev)
         self.coef_table = pipe.scheduler.coefficient_table(dev)                         # [T, 2]
-        self.cond = unet.prepare_conditions(prompt_embeds.to(dev), bbox, aspect_ratio)
-        self.temb_table = torch.stack([unet.time_rowbias(torch.tensor(float(t)), add_text_embeds, add_time_ids)
-                                       for t in self.timesteps])                        # [T, 2bs, sumC] fp32
-        self.lat = latents.to(device=dev, dtype=f32).permute(0, 2, 3, 1).contiguous()    # fp32 NHWC master copy
-        self.model_in = torch.cat([self.lat, self.lat]).to(bf16).contiguous()           # :315 (first step only)
-        self.db, self.round_bf16 = None, True
-        if dialog_bbox is not None:
-            self.round_bf16 = dialog_bbox.dtype == bf16
-            self.db = dialog_bbox.to(device=dev, dtype=f32).contiguous()
+        self.cond = None
+        self.lat = self.model_in = self.db = self.temb_table = None
+        self.round_bf16 = True
+        self.graph = None
+        self.load_panel(latents, prompt_embeds, add_text_embeds, add_time_ids, bbox, dialog_bbox)
         self.temb_cur = self.temb_table[0].clone()
         self.coef_cur = self.coef_table[0].clone()
         self._host_in = None
-        self.graph = None
         # Independent batch rows (the CFG halves, the panels) CAN run as `chains` concurrent kernel chains on separate
         # streams (graph branches), meant to back-fill the idle SMs of every kernel's last wave (flops-weighted tile
         # efficiency of one cfg2 step: 0.80, tools/shape_census.py).  MEASURED on B200 (cfg2, graph replay): 1 chain
@@ -260,6 +293,38 @@ class DenoiseStepper:
                 self._launch()
             self.lat.copy_(lat0)
             self.model_in.copy_(min0)
+
+    @torch.no_grad()
+    def load_panel(self, latents, prompt_embeds, add_text_embeds, add_time_ids, bbox, dialog_bbox) -> None:
+        """Everything that is per panel and timestep-invariant, written INTO the buffers the captured graph reads:
+        K|V of the text / IP tokens for all cross-attention layers, the time-embedding row-bias table for all T
+        steps, the bbox tables, the initial latents.  First call allocates; later calls (same shapes) refill."""
+        unet, dev = self.unet, self.dev
+        bs = latents.shape[0]
+        if prompt_embeds.shape[0] != 2 * bs:
+            raise ValueError("denoise expects CFG-concatenated conditions: prompt_embeds.shape[0] == 2 * num_samples")
+        self.cond = unet.prepare_conditions(prompt_embeds.to(dev), bbox, self.aspect_ratio, out=self.cond)
+        self.temb_table = unet.time_rowbias_table(self.timesteps, add_text_embeds, add_time_ids)   # [T, 2bs, sumC]
+        lat = latents.to(device=dev, dtype=f32).permute(0, 2, 3, 1).contiguous()         # fp32 NHWC master copy
+        first = self.lat is None
+        if first:
+            self.lat = lat
+            self.model_in = torch.cat([lat, lat]).to(bf16).contiguous()                 # :315 (first step only)
+        else:
+            if lat.shape != self.lat.shape or (dialog_bbox is None) != (self.db is None):
+                raise ValueError("load_panel: latent shape / dialog_bbox presence differs from the captured panel")
+            self.lat.copy_(lat)
+            self.model_in[:bs].copy_(lat)
+            self.model_in[bs:].copy_(lat)
+        if dialog_bbox is not None:
+            rb = dialog_bbox.dtype == bf16
+            db = dialog_bbox.to(device=dev, dtype=f32).contiguous()
+            if first:
+                self.db, self.round_bf16 = db, rb
+            else:
+                if rb != self.round_bf16 or db.shape != self.db.shape:
+                    raise ValueError("load_panel: dialog_bbox dtype / shape differs from the captured panel")
+                self.db.copy_(db)
 
     def _launch(self):
         if len(self._parts) == 1:

@@ -59,7 +59,7 @@ class _Resnet:
 
 class _Block:
     __slots__ = ("n1", "n2", "n3", "wqkv", "bqkv", "cs_qkv", "wo1", "bo1", "wq2", "bq2", "cs_q2", "wo2", "bo2", "wkv_t",
-                 "wkv_ip", "wff1", "bff1", "cs_ff1", "wff2", "bff2", "layer")
+                 "wkv_ip", "wff1", "bff1", "cs_ff1", "wff2", "bff2", "layer", "proc")
 
 
 class _Transformer:
@@ -78,11 +78,13 @@ class UNetMangaEngine:
         self.ip_scale = 1.0
         self._loaded = False
         self._cond_cache: Optional[Conditions] = None
+        self._processors = None
         self.num_upsamplers = len(cfg.block_out_channels) - 1
 
     # ------------------------------------------------------------------------------------------ API parity
     def set_manga_modules(self, max_num_ips=4, num_vision_tokens=16, max_num_dialogs=8):
-        """Registers the manga config keys (unet.py:50-53).  The processors themselves are native: the engine
+        """Registers the manga config keys (unet.py:50-53).  The 140 processors the reference installs here
+        (:56-83) exist as real nn.Modules behind ``attn_processors`` once the weights are loaded; the engine
         requires the checkpoint to carry ``...attn2.processor.to_k_ip/to_v_ip.weight`` and
         ``dialog_bbox_embedding`` (the reference creates them here before ``load_state_dict``)."""
         if (max_num_ips, num_vision_tokens, max_num_dialogs) != (self.cfg.max_num_ips, self.cfg.num_vision_tokens,
@@ -95,16 +97,33 @@ class UNetMangaEngine:
     def set_ip_scale(self, scale: float):
         """pipeline.set_ip_scale (pipeline_diffsensei.py:172-178) sets ``.scale`` on every IP processor."""
         self.ip_scale = float(scale)
-        for p in getattr(self, "_processors", {}).values():
+        for p in (self._processors or {}).values():
             if hasattr(p, "scale"):
                 p.scale = float(scale)
 
     @property
-    def attn_processors(self) -> Dict[str, object]:
-        if not hasattr(self, "_processors"):
+    def attn_processors(self) -> Dict[str, "torch.nn.Module"]:
+        """Name -> processor module, in diffusers' order (down, up, mid); see build_processor_table."""
+        if self._processors is None:
             from .attention_processor import build_processor_table
             self._processors = build_processor_table(self)
         return self._processors
+
+    def _scale_of(self, blk) -> float:
+        """``scale`` of the layer's IP processor (mutable per processor on the reference; pipeline.set_ip_scale sets
+        them all), or the engine-wide value while the processor table has not been materialised."""
+        proc = getattr(blk, "proc", None)
+        return float(proc.scale) if proc is not None else self.ip_scale
+
+    def scales_key(self) -> tuple:
+        """Everything a captured CUDA graph bakes in by value from the processors (the per-layer ip scales)."""
+        if self._processors is None:
+            return (self.ip_scale,)
+        return tuple(float(p.scale) for p in self._processors.values() if hasattr(p, "scale"))
+
+    def _ip_weights_version(self) -> int:
+        """Moves when a checkpoint is loaded INTO the processors (their Parameters alias the packed IP weights)."""
+        return sum(blk.wkv_ip._version for t in self.transformers.values() for blk in t.blocks)
 
     def state_dict_keys(self):
         return list(unet_param_shapes(self.cfg).keys())
@@ -186,6 +205,7 @@ class UNetMangaEngine:
                 blk.cs_ff1 = colsum_bf16(blk.wff1)
                 blk.wff2, blk.bff2 = bf(W(f"{b}.ff.net.2.weight")), fp(W(f"{b}.ff.net.2.bias"))
                 blk.layer = layer
+                blk.proc = None
                 layer += 1
                 t.blocks.append(blk)
             self.transformers[p] = t
@@ -199,13 +219,15 @@ class UNetMangaEngine:
         self.conv_out_w, self.conv_out_b = pack_conv3x3(W("conv_out.weight")), fp(W("conv_out.bias"))
         self._loaded = True
         self._cond_cache = None
+        self._processors = None
         return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
 
     # ------------------------------------------------------------------------------------------ hoisted work
     def prepare_conditions(self, encoder_hidden_states: torch.Tensor, bbox: torch.Tensor,
-                           aspect_ratio: float) -> Conditions:
+                           aspect_ratio: float, out: Optional[Conditions] = None) -> Conditions:
         """Project the text and IP tokens to K|V for every cross-attention layer once per panel
-        (attention_processor.py:213-226,245-246 run these 70 x per step in the reference)."""
+        (attention_processor.py:213-226,245-246 run these 70 x per step in the reference).  ``out``: an existing
+        Conditions of the same shapes to refill IN PLACE (the buffers a captured CUDA graph reads)."""
         cfg = self.cfg
         ehs = encoder_hidden_states
         if ehs.dtype != bf16:
@@ -218,14 +240,42 @@ class UNetMangaEngine:
             raise ValueError("encoder_hidden_states is shorter than the IP token block")
         text = ehs[:, :end].contiguous()
         ip = ehs[:, end:].contiguous()
-        kv_t: List[torch.Tensor] = [None] * self.num_cross_layers
-        kv_i: List[torch.Tensor] = [None] * self.num_cross_layers
+        if out is not None:
+            if out.batch != B or float(aspect_ratio) != out.aspect_ratio or out.kv_text[0].shape[1] != end:
+                raise ValueError("prepare_conditions(out=): shapes / aspect ratio differ from the captured panel")
+            kv_t, kv_i = out.kv_text, out.kv_ip
+        else:
+            kv_t: List[torch.Tensor] = [None] * self.num_cross_layers
+            kv_i: List[torch.Tensor] = [None] * self.num_cross_layers
         for t in self.transformers.values():
             for blk in t.blocks:
-                kv_t[blk.layer] = ops.gemm(text, blk.wkv_t)
-                kv_i[blk.layer] = ops.gemm(ip, blk.wkv_ip)
-        return Conditions(kv_text=kv_t, kv_ip=kv_i, bbox=bbox.to(device=self.device, dtype=f32).contiguous(),
-                          aspect_ratio=float(aspect_ratio), batch=B)
+                kv_t[blk.layer] = ops.gemm(text, blk.wkv_t, out=kv_t[blk.layer])
+                kv_i[blk.layer] = ops.gemm(ip, blk.wkv_ip, out=kv_i[blk.layer])
+        bb = bbox.to(device=self.device, dtype=f32).contiguous()
+        if out is not None:
+            out.bbox.copy_(bb)
+            return out
+        return Conditions(kv_text=kv_t, kv_ip=kv_i, bbox=bb, aspect_ratio=float(aspect_ratio), batch=B)
+
+    def time_rowbias_table(self, timesteps, text_embeds: torch.Tensor, time_ids: torch.Tensor) -> torch.Tensor:
+        """``time_rowbias`` for all T timesteps of a panel at once -> fp32 [T, B, sum(Cout)].  Same arithmetic per row
+        as T separate calls (the time MLP runs on T rows, the add-embedding MLP on B rows, their sum + SiLU + the
+        stacked time_emb_proj on T*B rows); ~12 launches instead of 7 T."""
+        cfg = self.cfg
+        B = text_embeds.shape[0]
+        t = torch.as_tensor([float(x) for x in timesteps], dtype=f32, device=self.device)
+        T = t.numel()
+        tsin = ops.timestep_embedding(t, cfg.block_out_channels[0])
+        h = ops.gemm(tsin, self.te[0][0], self.te[0][1], epilogue=ops.EPI_SILU)
+        emb_t = ops.gemm(h, self.te[1][0], self.te[1][1])                                     # [T, td]
+        ids = ops.timestep_embedding(time_ids.to(device=self.device, dtype=f32).reshape(-1).contiguous(),
+                                     cfg.addition_time_embed_dim).reshape(B, -1)
+        add_in = ops.concat_channels(text_embeds.to(device=self.device, dtype=bf16).contiguous(), ids)
+        h = ops.gemm(add_in, self.ae[0][0], self.ae[0][1], epilogue=ops.EPI_SILU)             # [B, td]
+        # emb[t, b] = add_embedding.linear_2(h[b]) + emb_t[t]: rows replicated host-side (tiny), sum in the epilogue
+        emb = ops.gemm(h.repeat(T, 1), self.ae[1][0], self.ae[1][1],
+                       residual=emb_t.repeat_interleave(B, dim=0).contiguous())               # [T*B, td]
+        return ops.gemm(ops.silu(emb), self.temb_w, self.temb_b, out_fp32=True).view(T, B, -1)
 
     def time_rowbias(self, timesteps: torch.Tensor, text_embeds: torch.Tensor, time_ids: torch.Tensor) -> torch.Tensor:
         """emb = time_embedding(sin(t)) + add_embedding([pooled | sin(time_ids)])   (unet.py:190-196), then every
@@ -284,7 +334,8 @@ class UNetMangaEngine:
             h = produce(a, blk.wo1, blk.bo1, residual=h, out=h)
             q = consume(h, blk.wq2, blk.bq2, blk.cs_q2, out=a)
             a = ops.attention_cross_ip(q, cond.kv_text[blk.layer], cond.kv_ip[blk.layer], cond.bbox, t.heads,
-                                       cond.aspect_ratio, self.ip_scale, cfg.num_vision_tokens, cfg.num_dummy_tokens)
+                                       cond.aspect_ratio, self._scale_of(blk), cfg.num_vision_tokens,
+                                       cfg.num_dummy_tokens)
             h = produce(a, blk.wo2, blk.bo2, residual=h, out=h)
             f = consume(h, blk.wff1, blk.bff1, blk.cs_ff1, epilogue=ops.EPI_GEGLU)
             h = produce(f, blk.wff2, blk.bff2, residual=h, out=h)
@@ -335,8 +386,13 @@ class UNetMangaEngine:
         return ops.conv3x3(h, self.conv_out_w, self.conv_out_b, out=out)
 
     def _conditions_for(self, ehs: torch.Tensor, bbox: torch.Tensor, aspect_ratio: float) -> Conditions:
-        key = (ehs.data_ptr(), ehs._version, tuple(ehs.shape), bbox.data_ptr(), bbox._version, float(aspect_ratio))
-        if self._cond_cache is None or self._cond_cache.key != key:
+        """Hoisted K|V for (ehs, bbox): reused across the steps of one panel.  The key holds the tensors THEMSELVES
+        (identity + version counter) — never addresses, which the caching allocator recycles between panels."""
+        c = self._cond_cache
+        key = (ehs, ehs._version, bbox, bbox._version, float(aspect_ratio), self._ip_weights_version())
+        hit = (c is not None and len(c.key) == len(key) and c.key[0] is ehs and c.key[2] is bbox and
+               c.key[1] == key[1] and c.key[3] == key[3] and c.key[4:] == key[4:])
+        if not hit:
             self._cond_cache = self.prepare_conditions(ehs, bbox, aspect_ratio)
             self._cond_cache.key = key
         return self._cond_cache

@@ -18,6 +18,10 @@ import torch
 import torch.nn.functional as F
 
 MASK_VALUE = -10000.0  # attention_processor.py:142
+# False: explicit softmax(QK^T/sqrt(d) + mask) V (documents the maths; what the parity tests use).
+# True : torch.nn.functional.scaled_dot_product_attention, the call the reference makes (:76,:235,:251) — used by
+#        bench.py's GPU-library baseline leg so that torch dispatches its fused (flash / cuDNN) attention kernels.
+USE_SDPA = False
 
 
 def derive_hw(seq_len: int, aspect_ratio: float) -> tuple[int, int]:
@@ -45,8 +49,8 @@ def ip_open_mask(bbox: torch.Tensor, seq_len: int, aspect_ratio: float, tokens_p
     """
     B, num_ips, _ = bbox.shape
     height, width = derive_hw(seq_len, aspect_ratio)
-    xs = torch.linspace(0, 1, steps=width)
-    ys = torch.linspace(0, 1, steps=height)
+    xs = torch.linspace(0, 1, steps=width, device=bbox.device)     # the reference builds the grid on the bbox device
+    ys = torch.linspace(0, 1, steps=height, device=bbox.device)
     gx = xs.repeat(height)                     # x varies fastest
     gy = ys.repeat_interleave(width)
     bb = bbox.to(torch.float32)
@@ -60,7 +64,8 @@ def ip_open_mask(bbox: torch.Tensor, seq_len: int, aspect_ratio: float, tokens_p
 def ip_additive_mask(bbox, seq_len, aspect_ratio, tokens_per_ip, num_dummy, dtype=torch.float32):
     """The additive mask the reference feeds SDPA, without the (redundant) head dimension."""
     open_ = ip_open_mask(bbox, seq_len, aspect_ratio, tokens_per_ip, num_dummy)
-    return torch.where(open_, torch.zeros((), dtype=dtype), torch.full((), MASK_VALUE, dtype=dtype))
+    return torch.where(open_, torch.zeros((), dtype=dtype, device=open_.device),
+                       torch.full((), MASK_VALUE, dtype=dtype, device=open_.device))
 
 
 def _split_heads(x: torch.Tensor, heads: int) -> torch.Tensor:
@@ -75,6 +80,8 @@ def _merge_heads(x: torch.Tensor) -> torch.Tensor:
 
 def sdpa(q, k, v, additive_mask=None):
     """softmax(q k^T / sqrt(d) + mask) v on (B, h, n, d) tensors — what F.scaled_dot_product_attention does."""
+    if USE_SDPA:
+        return F.scaled_dot_product_attention(q, k, v, attn_mask=additive_mask, dropout_p=0.0, is_causal=False)
     s = (q @ k.transpose(-1, -2)) / math.sqrt(q.shape[-1])
     if additive_mask is not None:
         s = s + additive_mask

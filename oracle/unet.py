@@ -21,15 +21,14 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from diffsensei_b200.config import UNetConfig
-
 from . import attention as A
+from .config import OracleUNetConfig
 
 
 def timestep_sinusoid(t: torch.Tensor, dim: int) -> torch.Tensor:
     """diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos | sin](t * w_i)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     arg = t.to(torch.float32)[:, None] * freqs[None, :]
     return torch.cat([torch.cos(arg), torch.sin(arg)], dim=-1)
 
@@ -106,7 +105,7 @@ class TransformerBlock(nn.Module):  # diffusers BasicTransformerBlock
         self.norm3 = nn.LayerNorm(dim, eps=1e-5)
         self.ff = FeedForward(dim)
 
-    def forward(self, hs, ehs, bbox, aspect_ratio, cfg: UNetConfig):
+    def forward(self, hs, ehs, bbox, aspect_ratio, cfg: OracleUNetConfig):
         a1, a2 = self.attn1, self.attn2
         hs = hs + A.self_attention(self.norm1(hs), a1.to_q.weight, a1.to_k.weight, a1.to_v.weight,
                                    a1.to_out[0].weight, a1.to_out[0].bias, a1.heads)
@@ -186,8 +185,9 @@ def encode_dialog_bbox(sample: torch.Tensor, dialog_bbox: torch.Tensor, emb: tor
 
 
 class OracleUNet(nn.Module):
-    def __init__(self, cfg: UNetConfig):
+    def __init__(self, cfg):
         super().__init__()
+        cfg = OracleUNetConfig.from_any(cfg)          # own dataclass: the oracle never imports the product package
         self.cfg = cfg
         ch, g, kv = cfg.block_out_channels, cfg.norm_num_groups, cfg.cross_attention_dim
         td, depth = cfg.time_embed_dim, cfg.transformer_layers_per_block
@@ -227,9 +227,10 @@ class OracleUNet(nn.Module):
 
     def embed_time(self, timestep, text_embeds, time_ids, batch):
         cfg = self.cfg
-        t = torch.as_tensor(timestep, dtype=torch.float32).reshape(-1).expand(batch)
-        emb = self.time_embedding(timestep_sinusoid(t, cfg.block_out_channels[0]))
-        tid = timestep_sinusoid(time_ids.reshape(-1), cfg.addition_time_embed_dim).reshape(batch, -1)
+        w = self.conv_in.weight                      # the oracle runs wherever (and in whatever dtype) its weights live
+        t = torch.as_tensor(timestep, dtype=torch.float32, device=w.device).reshape(-1).expand(batch)
+        emb = self.time_embedding(timestep_sinusoid(t, cfg.block_out_channels[0]).to(w.dtype))
+        tid = timestep_sinusoid(time_ids.reshape(-1), cfg.addition_time_embed_dim).reshape(batch, -1).to(w.dtype)
         return emb + self.add_embedding(torch.cat([text_embeds, tid], dim=-1))     # unet.py:190-196
 
     @torch.no_grad()

@@ -186,41 +186,167 @@ def test_resampler_matches_executed_reference():
     assert rel_l2(res(torch.zeros_like(g["x"]), torch.zeros_like(g["magi"])).float(), g["out_zero"]) < 2e-2
 
 
+def test_resampler_shipped_config_matches_executed_reference():
+    """The Resampler at the SHIPPED size (dim 1280, depth 4, 20 heads, 4 x (257 + 1) image tokens, 84 M params) on the
+    GPU vs the reference's own resampler.py executed on the same seeded weights (tests/golden/resampler_full.pt)."""
+    import diffsensei_b200 as ds
+    from test_oracle_golden import resampler_full_case
+    g, sd, x, magi = resampler_full_case()
+    res = ds.ResamplerEngine(**g["kwargs"], device=DEV)
+    res.load_state_dict(sd)
+    out = res(x, magi)
+    assert out.shape == (1, 80, 2048)
+    e1 = rel_l2(out.float(), g["out"])
+    e0 = rel_l2(res(torch.zeros_like(x), torch.zeros_like(magi)).float(), g["out_zero"])
+    print(f"shipped-config Resampler vs executed reference: rel-L2 {e1:.3e} (zero inputs: {e0:.3e})")
+    assert e1 < 2e-2 and e0 < 2e-2
+
+
 def test_smoke_entry_point():
     import __graft_entry__
     __graft_entry__.smoke()
 
 
-@pytest.mark.skipif(os.environ.get("DS_FULL_PARITY") == "0",
-                    reason="full-size SDXL oracle forward on the host (45 s, ~25 GB of host RAM) disabled by "
-                           "DS_FULL_PARITY=0")
-def test_full_size_cfg1_unet_forward_matches_oracle():
-    """BASELINE configs[0] (512x512, bs 1, 1 character ref) at the REAL SDXL+IP topology: one UNetMangaModel.forward
-    of the engine against the CPU oracle on the same random weights and inputs.  Exercises what the TINY config
-    cannot: 10-layer transformers at C = 1280, the LayerNorm-folded GEMMs at real widths, N = 4096 / 1024 attention."""
-    import diffsensei_b200 as ds
-    from diffsensei_b200.weights import random_state_dict, unet_param_shapes
-    from oracle.unet import OracleUNet
-    cfg = ds.SDXL_MANGA
-    sd = random_state_dict(unet_param_shapes(cfg), seed=7, device="cpu", dtype=torch.bfloat16)
-    with torch.device("meta"):
-        oracle = OracleUNet(cfg)
-    oracle = oracle.to_empty(device="cpu")
-    oracle.load_state_dict({k: v.float() for k, v in sd.items()})
-    oracle.eval().set_ip_scale(0.6)
-    engine = ds.UNetMangaEngine(cfg, DEV)
-    engine.load_state_dict(sd)
-    engine.set_ip_scale(0.6)
-    h = w = 64
-    lat, ehs, pooled, time_ids, bbox, dialog = _inputs(cfg, 1, h, w, seed=11, n_chars=1, dialogs=True)
+# ------------------------------------------------------------------------------------------ round-2 additions
+def test_fresh_conditioning_tensors_never_hit_a_stale_cache(tiny):
+    """two panels with different, freshly allocated, same-shaped encoder_hidden_states — the second
+    tensor very likely lands in the first one's freed block.  The hoisted K|V must be recomputed (the cache is keyed
+    on tensor identity + version, never on addresses) for UNetMangaEngine.forward AND for the drop-in processor."""
+    ds, oracle, engine = tiny
+    lat, ehs, pooled, time_ids, bbox, dialog = _inputs(ds.TINY, 1, 16, 24)
     x = torch.cat([lat] * 2)
-    ehs = ehs.to(bf16).float()            # both sides see the same bf16-representable conditions
-    with torch.no_grad():
-        want = oracle(x, 741, ehs, pooled, time_ids, bbox, 1.0, dialog)
-    out = engine.forward(x.to(DEV), torch.tensor(741), ehs.to(DEV, bf16),
-                         added_cond_kwargs={"text_embeds": pooled.to(DEV), "time_ids": time_ids.to(DEV)},
-                         cross_attention_kwargs={"bbox": bbox.to(DEV), "aspect_ratio": 1.0},
-                         dialog_bbox=dialog.to(DEV)).sample
-    err = rel_l2(out, want)
-    print(f"full-size cfg1 UNet forward rel-L2 vs fp32 oracle: {err:.3e}")   # measured on B200: 1.75e-2
-    assert err < 3e-2
+    outs, wants = [], []
+    for seed in (1, 2):
+        e = torch.randn(2, 157, ds.TINY.cross_attention_dim, generator=torch.Generator().manual_seed(seed))
+        e_dev = e.to(DEV, bf16)                       # fresh allocation each panel, freed at the end of the iteration
+        out = engine.forward(x.to(DEV), 500, e_dev,
+                             added_cond_kwargs={"text_embeds": pooled.to(DEV), "time_ids": time_ids.to(DEV)},
+                             cross_attention_kwargs={"bbox": bbox.to(DEV), "aspect_ratio": 16 / 24},
+                             dialog_bbox=dialog.to(DEV)).sample
+        outs.append(out.cpu())
+        wants.append(oracle(x, 500, e.to(bf16).float(), pooled, time_ids, bbox, 16 / 24, dialog))
+        del e_dev, out
+    assert not torch.equal(outs[0], outs[1])
+    assert rel_l2(outs[0], wants[0]) < 3e-2 and rel_l2(outs[1], wants[1]) < 3e-2
+    # in-place update of the SAME tensor object bumps its version -> recomputed as well
+    e_dev = torch.zeros(2, 157, ds.TINY.cross_attention_dim, device=DEV, dtype=bf16)
+    kw = dict(added_cond_kwargs={"text_embeds": pooled.to(DEV), "time_ids": time_ids.to(DEV)},
+              cross_attention_kwargs={"bbox": bbox.to(DEV), "aspect_ratio": 16 / 24}, dialog_bbox=dialog.to(DEV))
+    a = engine.forward(x.to(DEV), 500, e_dev, **kw).sample.clone()
+    e_dev.copy_(torch.randn(2, 157, ds.TINY.cross_attention_dim, generator=torch.Generator().manual_seed(3)))
+    assert not torch.equal(engine.forward(x.to(DEV), 500, e_dev, **kw).sample, a)
+
+
+def test_attn_processors_are_real_modules_in_diffusers_order(tiny):
+    """Seam B: `torch.nn.ModuleList(unet.attn_processors.values()).load_state_dict(ip_adapter_sd)`
+    (src/models/utils.py:46-48) must work: 2 x 70 nn.Modules in diffusers' order (down, up, mid), odd indices own
+    to_k_ip / to_v_ip, loading writes the weights the engine computes with, `scale` steers the layer."""
+    ds, oracle, engine = tiny
+    procs = engine.attn_processors
+    names = list(procs)
+    assert len(names) == 2 * engine.num_cross_layers and all(isinstance(p, torch.nn.Module) for p in procs.values())
+    first_up = next(i for i, n in enumerate(names) if n.startswith("up_blocks"))
+    first_mid = next(i for i, n in enumerate(names) if n.startswith("mid_block"))
+    assert names[0].startswith("down_blocks") and first_up < first_mid and names[-1].startswith("mid_block")
+    assert names[0].endswith("attn1.processor") and names[1].endswith("attn2.processor")
+    ml = torch.nn.ModuleList(procs.values())
+    sd = ml.state_dict()
+    assert set(sd) == {f"{2 * i + 1}.to_{kv}_ip.weight" for i in range(engine.num_cross_layers) for kv in "kv"}
+    lat, ehs, pooled, time_ids, bbox, dialog = _inputs(ds.TINY, 1, 16, 24)
+    x = torch.cat([lat] * 2)
+    run = lambda: engine.forward(x.to(DEV), 500, ehs.to(DEV, bf16),
+                                 added_cond_kwargs={"text_embeds": pooled.to(DEV), "time_ids": time_ids.to(DEV)},
+                                 cross_attention_kwargs={"bbox": bbox.to(DEV), "aspect_ratio": 16 / 24},
+                                 dialog_bbox=dialog.to(DEV)).sample.clone()
+    base = run()
+    old = {k: v.clone() for k, v in sd.items()}
+    try:
+        g = torch.Generator().manual_seed(0)
+        new = {k: (torch.randn(v.shape, generator=g) * v.shape[1] ** -0.5).to(v) for k, v in sd.items()}
+        ml.load_state_dict(new)                                  # the reference's load_ip_adapter call
+        moved = run()
+        assert not torch.equal(moved, base)
+        # the oracle with the same IP weights agrees -> the load reached the fused path
+        # index of processor n in the ModuleList is names.index(n)
+        osd = dict(oracle.state_dict())
+        for n in names:
+            if n.endswith("attn2.processor"):
+                for kv in "kv":
+                    osd[f"{n}.to_{kv}_ip.weight"] = new[f"{names.index(n)}.to_{kv}_ip.weight"].float().cpu()
+        import copy
+        o2 = copy.deepcopy(oracle)
+        o2.load_state_dict(osd)
+        o2.set_ip_scale(0.6)
+        assert rel_l2(moved, o2(x, 500, ehs, pooled, time_ids, bbox, 16 / 24, dialog)) < 3e-2
+        # per-processor scale (pipeline.set_ip_scale walks the processors and sets `.scale`)
+        for p in procs.values():
+            if hasattr(p, "scale"):
+                p.scale = 0.0
+        assert not torch.equal(run(), moved)
+    finally:
+        ml.load_state_dict(old)
+        engine.set_ip_scale(0.6)
+    assert torch.equal(run(), base)
+
+
+def test_graph_is_reused_across_panels_of_one_shape(tiny):
+    """DiffSenseiPipeline.denoise captures one CUDA graph per shape and refills its buffers for
+    the next panel (DenoiseStepper.load_panel) — the second panel must equal a from-scratch eager run."""
+    ds, _oracle, engine = tiny
+    pipe = ds.DiffSenseiPipeline(engine)
+    bs, h, w = 2, 16, 24
+    res = []
+    for seed in (3, 4):
+        lat, ehs, pooled, time_ids, bbox, dialog = _inputs(ds.TINY, bs, h, w, seed=seed)
+        got = pipe.denoise(lat, ehs, pooled, time_ids, bbox, h / w, dialog, 4, 7.5, use_graph=True)
+        want = pipe.denoise(lat, ehs, pooled, time_ids, bbox, h / w, dialog, 4, 7.5, use_graph=False)
+        assert torch.equal(got, want)
+        res.append(got)
+    assert len(pipe._steppers) == 1 and not torch.equal(res[0], res[1])
+
+
+def test_pipeline_without_characters_and_guidance_off(tiny):
+    """a panel without ip images pads with zero embeddings (pipeline_diffsensei.py:118-132) instead of
+    crashing; guidance_scale <= 1 (no CFG on the reference) is rejected explicitly."""
+    ds, _oracle, engine = tiny
+    from oracle.resampler import OracleResampler
+    torch.manual_seed(5)
+    kw = dataclasses.asdict(ds.RESAMPLER_TINY)
+    ref = OracleResampler(**kw).eval()
+    res = ds.ResamplerEngine(**kw, device=DEV)
+    res.load_state_dict(ref.state_dict())
+    pipe = ds.DiffSenseiPipeline(engine)
+    pipe.register_manga_modules(None, res)
+    g = torch.Generator().manual_seed(7)
+    pe, npe = torch.randn(1, 77, 128, generator=g), torch.randn(1, 77, 128, generator=g)
+    pp, npp = torch.randn(1, 96, generator=g), torch.randn(1, 96, generator=g)
+    common = dict(prompt="p", height=128, width=128, num_inference_steps=2, prompt_embeds=pe,
+                  negative_prompt_embeds=npe, pooled_prompt_embeds=pp, negative_pooled_prompt_embeds=npp)
+    out = pipe(guidance_scale=7.5, ip_bbox=[], **common)
+    assert out.images.shape == (1, 4, 16, 16) and torch.isfinite(out.images).all()
+    with pytest.raises(ValueError, match="guidance_scale"):
+        pipe(guidance_scale=1.0, ip_bbox=[], **common)
+
+
+def test_dialog_boxes_with_negative_coordinates_follow_python_slicing(tiny):
+    """x2 / y2 are only clamped from above and used as slice ENDS (unet.py:107-110): negative values
+    count from the far edge."""
+    ds, _oracle, _engine = tiny
+    from oracle.unet import encode_dialog_bbox
+    g = torch.Generator().manual_seed(4)
+    sample = torch.randn(1, 16, 20, 30, generator=g).to(bf16)
+    emb = torch.randn(16, generator=g).to(bf16)
+    db = torch.tensor([[[0.1, 0.2, -0.1, -0.25], [-0.2, 0.5, 0.4, 0.9], [0.5, 0.1, 0.9, -2.0]] + [[0.0] * 4] * 5])
+    want = encode_dialog_bbox(sample.float(), db, emb.float())
+    x = sample.permute(0, 2, 3, 1).contiguous().to(DEV)
+    got = ds.ops.dialog_embed_add_(x, emb.float().to(DEV), db.to(DEV), False).permute(0, 3, 1, 2).float().cpu()
+    assert torch.equal(got, want.to(bf16).float())
+
+
+def test_tensor_on_other_device_is_rejected(tiny):
+    ds, _o, _e = tiny
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    x = torch.zeros(1, 8, 8, 64, device="cuda:1", dtype=bf16)
+    with pytest.raises(ds.ops.DsEngineError, match="current CUDA device"):
+        ds.ops.silu(x)

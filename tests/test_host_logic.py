@@ -134,3 +134,60 @@ def test_host_thread_probe_returns_a_usable_count():
     import bench
     n = bench.pick_host_threads()
     assert 1 <= n <= (os.cpu_count() or 1)
+
+
+# ------------------------------------------------------------------------------------------ round-2 additions
+def test_oracle_topology_is_its_own_and_agrees_with_the_engine_config():
+    """oracle and engine must not share one topology dataclass.  oracle/config.py restates the published
+    SDXL + manga values independently; the engine's config has to agree with it field by field."""
+    import dataclasses
+    from oracle.config import SDXL, TINY as OTINY, OracleUNetConfig
+    for mine, theirs in ((SDXL_MANGA, SDXL), (TINY, OTINY)):
+        for f in dataclasses.fields(OracleUNetConfig):
+            assert tuple(getattr(mine, f.name)) == tuple(getattr(theirs, f.name)) if isinstance(
+                getattr(theirs, f.name), tuple) else getattr(mine, f.name) == getattr(theirs, f.name), f.name
+        assert mine.time_embed_dim == theirs.time_embed_dim and mine.num_ip_tokens == theirs.num_ip_tokens
+    assert OracleUNetConfig.from_any(SDXL_MANGA) == SDXL
+
+
+def test_oracle_and_reference_arm_never_load_the_product(tmp_path):
+    """`import oracle...` and `bench.py --impl reference` must not import diffsensei_b200 (which dlopens
+    libdsengine.so): the reference arm's evidence has to be clean of the product's native code."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = ("import sys; import oracle.unet, oracle.ddim, oracle.attention, oracle.resampler, oracle.config; "
+            "assert 'diffsensei_b200' not in sys.modules; "
+            "assert 'libdsengine' not in open('/proc/self/maps').read(); print('clean')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stderr[-2000:]
+    env = dict(os.environ, DS_BENCH_TINY="1")
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "2", "--warmup", "1"], cwd=ROOT,
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["product_package_imported"] is False
+    assert line["steps"] == 2 and line["warmup"] == 1 and line["cpu_baseline"]["kind"] == "port"
+    assert abs(line["value"] * 8 * line["ms_per_step"] / 1e3 - 1.0) < 0.01          # value = 1 / (8 rows x s/row)
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "cfg1_measured" in line
+
+
+def test_analytic_flop_model_matches_survey_numbers():
+    from oracle.config import SDXL, unet_flops
+    assert abs(unet_flops(SDXL, 8, 128, 128) / 1e12 - 54.8) < 0.05          # cfg2, SURVEY §8d
+    assert abs(unet_flops(SDXL, 2, 64, 64) / 1e12 - 3.30) < 0.01            # cfg1
+    assert abs(unet_flops(SDXL, 2, 256, 128) / 1e12 - 30.2) < 0.05          # cfg5
+    assert abs((unet_flops(SDXL, 8, 128, 128) - unet_flops(SDXL, 8, 128, 128, hoist_kv=True)) / 1e12 - 0.856) < 0.005
+
+
+def test_pack_cache_is_keyed_on_identity_not_address():
+    from diffsensei_b200.attention_processor import _PackCache
+    c, calls = _PackCache(), []
+    a = torch.zeros(4)
+    build = lambda: calls.append(1) or len(calls)
+    assert c.get((a,), build) == 1 and c.get((a,), build) == 1
+    a.add_(1)                                           # version bump
+    assert c.get((a,), build) == 2
+    b = torch.zeros(4)                                  # different object (whatever its address)
+    assert c.get((b,), build) == 3 and c.get((b,), build) == 3

@@ -93,3 +93,33 @@ def test_resampler_shipped_config_param_count():
     from diffsensei_b200.weights import resampler_param_shapes
     n = sum(torch.Size(s).numel() for s in resampler_param_shapes(RESAMPLER).values())
     assert n == 83_978_752
+
+
+def resampler_full_case():
+    """Regenerate the weights / inputs of tests/golden/resampler_full.pt from its seeds (tools/make_golden.py)."""
+    import dataclasses
+    from diffsensei_b200.config import RESAMPLER
+    from diffsensei_b200.weights import random_state_dict, resampler_param_shapes
+    g = _load("resampler_full.pt")
+    assert g["kwargs"] == dataclasses.asdict(RESAMPLER)
+    sd = random_state_dict(resampler_param_shapes(RESAMPLER), seed=g["weight_seed"], device="cpu")
+    sd = {k: v.to(torch.bfloat16).float() for k, v in sd.items()}
+    gx = torch.Generator().manual_seed(g["input_seed"])
+    x = torch.randn(1, 4, 257, 1280, generator=gx).to(torch.bfloat16).float()
+    magi = torch.randn(1, 4, 768, generator=gx).to(torch.bfloat16).float()
+    x[0, g["n_real"]:] = 0
+    magi[0, g["n_real"]:] = 0
+    return g, sd, x, magi
+
+
+def test_resampler_shipped_config_matches_executed_reference():
+    """configs/model/diffsensei.yaml Resampler (dim 1280, depth 4, 20 heads, 257 CLIP tokens + 1 Magi token per
+    character, 83,978,752 params): oracle restatement vs the reference's own resampler.py executed on the same
+    seeded weights / inputs."""
+    g, sd, x, magi = resampler_full_case()
+    m = OracleResampler(**g["kwargs"]).eval()
+    m.load_state_dict(sd)
+    assert sum(p.numel() for p in m.parameters()) == 83_978_752
+    with torch.no_grad():
+        assert rel_l2(m(x, magi), g["out"]) < 1e-5
+        assert rel_l2(m(torch.zeros_like(x), torch.zeros_like(magi)), g["out_zero"]) < 1e-5

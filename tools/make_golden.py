@@ -173,9 +173,28 @@ def main():
     magi[0, 2:] = 0
     torch.save({"kwargs": kw, "state_dict": model.state_dict(), "x": x, "magi": magi, "out": model(x, magi),
                 "out_zero": model(torch.zeros_like(x), torch.zeros_like(magi))}, f"{OUT}/resampler_tiny.pt")
-    full = rs.Resampler(dim=1280, depth=4, dim_head=64, heads=20, num_queries=16, num_dummy_tokens=16,
-                        embedding_dim=1280, output_dim=2048, ff_mult=4, magi_embedding_dim=768)
+    # ------------------------------------------------------------------ Resampler at the SHIPPED config
+    # (configs/model/diffsensei.yaml + scripts/demo/gradio_wo_mllm.py:174-185: 83,978,752 params).  The weights
+    # (336 MB) and inputs are NOT stored: both sides regenerate them from the seeds below with
+    # diffsensei_b200.weights.random_state_dict / torch.Generator (same torch build on the GPU box); only the
+    # reference's outputs are committed.
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from diffsensei_b200.config import RESAMPLER
+    from diffsensei_b200.weights import random_state_dict, resampler_param_shapes
+    import dataclasses
+    kwf = dataclasses.asdict(RESAMPLER)
+    full = rs.Resampler(**kwf).eval()
     print("Resampler(shipped config) params:", sum(p.numel() for p in full.parameters()))
+    sdf = random_state_dict(resampler_param_shapes(RESAMPLER), seed=42, device="cpu")
+    sdf = {k: v.to(torch.bfloat16).float() for k, v in sdf.items()}      # bf16-representable on both sides
+    full.load_state_dict(sdf)
+    gx = torch.Generator().manual_seed(43)
+    xf = torch.randn(1, 4, 257, 1280, generator=gx).to(torch.bfloat16).float()
+    mf = torch.randn(1, 4, 768, generator=gx).to(torch.bfloat16).float()
+    xf[0, 3:] = 0                                                        # 3 real characters, 1 padded (:131-132)
+    mf[0, 3:] = 0
+    torch.save({"kwargs": kwf, "weight_seed": 42, "input_seed": 43, "n_real": 3, "out": full(xf, mf),
+                "out_zero": full(torch.zeros_like(xf), torch.zeros_like(mf))}, f"{OUT}/resampler_full.pt")
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
