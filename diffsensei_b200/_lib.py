@@ -26,7 +26,9 @@ class GemmArgs(C.Structure):
                 ("out_scale", C.c_float),
                 ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float),
                 ("row_stats_out", C.c_void_p), ("zero_rows", C.c_void_p), ("row_stats_zeroed", C.c_int32),
-                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64)]
+                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
+                ("a2", C.c_void_p), ("K1", C.c_int32), ("lda2", C.c_int32),
+                ("chan_stats", C.c_void_p), ("stats_rows_per_sample", C.c_int32)]
 
 
 class Conv3x3Args(C.Structure):
@@ -34,7 +36,7 @@ class Conv3x3Args(C.Structure):
                 ("rowbias", C.c_void_p), ("residual", C.c_void_p),
                 ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
                 ("stride", C.c_int32), ("rowbias_ld", C.c_int32), ("out_fp32", C.c_int32), ("out_scale", C.c_float),
-                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64)]
+                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64), ("chan_stats", C.c_void_p)]
 
 
 class CrossIpArgs(C.Structure):
@@ -54,6 +56,8 @@ _vp, _i, _f, _d, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int64
 # (tests/test_abi.py checks that the header, this table and the .so's export list agree).
 SIGNATURES = {
     "ds_groupnorm_silu": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],
+    "ds_channel_stats": [_vp, _vp, _i, _i, _i, _vp],
+    "ds_groupnorm_apply": [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp],
     "ds_layernorm": [_vp, _vp, _vp, _vp, _i, _i, _f, _vp],
     "ds_dialog_embed_add": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "ds_ip_mask": [_vp, _vp, _i, _i, _d, _i, _i, _i, _vp],

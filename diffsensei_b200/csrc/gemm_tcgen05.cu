@@ -68,6 +68,17 @@ struct GemmParams {
   // the tile and the counter behind it.  tail_parts = 1: off.
   int tail_start, tail_parts, total_items;
   float* ws;  // [256 uint32 counters][left][PAIR * 128][BN] fp32, all zero between launches
+  // first M tile (in units of 128*PAIR rows) of this launch: ds_gemm_bf16 / ds_conv3x3_nhwc may cover the M range
+  // with TWO launches — wide BN=256 tiles for the full waves of the persistent schedule and BN=128 tiles for the
+  // m-rows of the under-filled last wave (see run_gemm)
+  int m_pair0;
+  // second A operand: k-blocks [k1_iters, num_k_iters) of a plain GEMM come from tmA2 (the channel concatenation
+  // [a | a2] along K is never materialised); k1_iters == num_k_iters: off
+  int k1_iters;
+  // per-(sample, channel) {sum, sum of squares} of the bf16 OUTPUT, fp64 [B][n_out][2], accumulated with atomics:
+  // the statistics the next GroupNorm needs, taken while the output tile still sits in shared memory
+  double* chan_stats;
+  int stats_rows_per_sample;  // GEMM mode: rows per sample (multiple of 128); conv mode: unused (tile = one image)
   // conv geometry
   int conv, stride, Ho, Wo, tiles_x, tiles_y, cin_chunks, conv_B;
 };
@@ -86,15 +97,16 @@ struct GemmCfg {
   static constexpr int kTmemCols = 2 * BN <= 256 ? 256 : 512;  // tcgen05.alloc wants a power of two
   static constexpr int kStageOutBytes = 2 * kBM * 64 * 2;  // two [128][64] bf16 epilogue staging tiles (one per column half)
   static constexpr int kVecBytes = 2 * 2 * BN * 4;         // double-buffered per-tile copies of bias[BN] and ln_colsum[BN]
+  static constexpr int kStatBytes = 2 * 4 * 64 * 2 * 4;    // channel statistics: [column half][row quarter][64 cols][2]
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + kStageOutBytes + kVecBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+      kStages * kStageBytes + kStageOutBytes + kVecBytes + kStatBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int PAIR>
+template <int BN, int PAIR, bool STATS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                  const GemmParams p) {
+                  const __grid_constant__ CUtensorMap tmA2, const GemmParams p) {
   using Cfg = GemmCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::kStages;
   const uint32_t cta_rank = (PAIR == 2) ? cluster_ctarank() : 0u;  // rank inside the CTA pair; 0 = leader
@@ -109,7 +121,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* sB = smem + STAGES * kABytes;
   uint8_t* sOut = sB + STAGES * Cfg::kBBytes;  // 2 x [128][64] bf16, 128-B swizzled (TMA store / residual load)
   float* sVec = reinterpret_cast<float*>(sOut + Cfg::kStageOutBytes);  // [2 tiles in flight][bias | colsum][BN]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + Cfg::kStageOutBytes + Cfg::kVecBytes);
+  float* sStat = reinterpret_cast<float*>(sOut + Cfg::kStageOutBytes + Cfg::kVecBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + Cfg::kStageOutBytes + Cfg::kVecBytes + Cfg::kStatBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;      // [2] accumulator drained
@@ -126,6 +139,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tma_prefetch_desc(&tmC);
       if (p.residual) tma_prefetch_desc(&tmR);
     }
+    if (p.k1_iters < p.num_k_iters) tma_prefetch_desc(&tmA2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -185,7 +199,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int unit, k0, k1, tail_idx;
         decode(tile, unit, k0, k1, tail_idx);
         const int n_blk = unit % p.num_n_tiles;
-        const int m_blk = (unit / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
+        const int m_blk = (p.m_pair0 + unit / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
         int img = 0, x0 = 0, y0 = 0;
         if (p.conv) {
           const int per_img = p.tiles_x * p.tiles_y;
@@ -215,10 +229,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_load_4d(sA + stage * kABytes, &tmA, &full_bar[stage], cc * kBK, x0 * p.stride + s - 1,
                           y0 * p.stride + r - 1, img);
           } else {
+            const bool second = kb >= p.k1_iters;  // [a | a2] along K
+            const CUtensorMap* am = second ? &tmA2 : &tmA;
+            const int kc = (second ? kb - p.k1_iters : kb) * kBK;
             if (PAIR == 2)
-              tma_load_2d_pair(sA + stage * kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM);
+              tma_load_2d_pair(sA + stage * kABytes, am, &full_bar[stage], kc, m_blk * kBM);
             else
-              tma_load_2d(sA + stage * kABytes, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM);
+              tma_load_2d(sA + stage * kABytes, am, &full_bar[stage], kc, m_blk * kBM);
           }
           if (PAIR == 2)
             tma_load_2d_pair(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, b_row0);
@@ -345,7 +362,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       decode(tile, unit, k0, k1, tail_idx);
       const int n_org = (unit % p.num_n_tiles) * BN;           // first weight row of the tile's columns
       constexpr int bn_cur = BN;
-      const int m_blk = (unit / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
+      const int m_blk = (p.m_pair0 + unit / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
       const int r_local = wq * 32 + lane;
       const int bn_out = geglu ? bn_cur / 2 : bn_cur;          // output columns of this item
       const int no_org = geglu ? n_org / 2 : n_org;            // first output column
@@ -585,6 +602,56 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                            : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (STATS && p.chan_stats) {
+            // Channel statistics of the staged [128 rows][64 cols] bf16 block (exactly the values the next GroupNorm
+            // will read), while the TMA store drains it: thread <-> (column pair = lane, row quarter = wq), a warp
+            // reads 128 contiguous (swizzled) bytes of one row per step — conflict-free.  Rows outside the tensor
+            // (partial conv patches, M tail) are masked.  The 4 row quarters are combined in a fixed order and each
+            // column adds ONE fp64 pair per (tile, column) to global memory: fp64 sums of <= 2^11 fp32 partials are
+            // exact, so the result does not depend on the arrival order.
+            uint32_t vmask;
+            int sbatch;
+            if (p.conv) {
+              uint32_t mx = 0;
+#pragma unroll
+              for (int j = 0; j < kConvTileW; ++j) mx |= (cx + j < p.Wo) ? (1u << j) : 0u;
+              const int yy = cy + wq * 2;
+              vmask = ((yy < p.Ho) ? mx : 0u) | ((yy + 1 < p.Ho) ? (mx << 16) : 0u);
+              if (cimg >= p.conv_B) vmask = 0u;
+              sbatch = cimg;
+            } else {
+              const int nv = p.M - (m_blk * kBM + wq * 32);
+              vmask = nv >= 32 ? 0xffffffffu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
+              sbatch = (m_blk * kBM) / p.stats_rows_per_sample;
+            }
+            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+            const uint32_t sbase = smem_u32(stage) + (wq * 32) * 128 + (lane & 3) * 4;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+              const int r = wq * 32 + i;
+              uint32_t wv;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(sbase + i * 128 + ((((lane >> 2) ^ (r & 7))) << 4)));
+              if (!((vmask >> i) & 1u)) wv = 0u;
+              const float a = bf16_lo(wv), c = bf16_hi(wv);
+              s0 += a;
+              q0 = fmaf(a, a, q0);
+              s1 += c;
+              q1 = fmaf(c, c, q1);
+            }
+            float* sst = sStat + half * (4 * 64 * 2) + wq * (64 * 2);
+            *reinterpret_cast<float4*>(sst + lane * 4) = make_float4(s0, q0, s1, q1);   // [col][2] for cols 2*lane, +1
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            const int tg = wq * 32 + lane;
+            const bool tile_ok = p.conv ? (cimg < p.conv_B) : (m_blk * kBM < p.M);
+            if (tg < 64 && tile_ok && no0 + tg < p.n_out) {
+              const float* sc = sStat + half * (4 * 64 * 2) + tg * 2;
+              const float ts = ((sc[0] + sc[128]) + sc[256]) + sc[384];
+              const float tq = ((sc[1] + sc[129]) + sc[257]) + sc[385];
+              double* gp = p.chan_stats + (static_cast<size_t>(sbatch) * p.n_out + (no0 + tg)) * 2;
+              atomicAdd(gp, static_cast<double>(ts));
+              atomicAdd(gp + 1, static_cast<double>(tq));
+            }
+          }
         }
         if (!released) release_acc(acc);  // this column half lies entirely beyond N
         if (p.row_stats_out && row_ok) {  // columns beyond N contributed exact zeros
@@ -654,16 +721,53 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// Co-resident CTA groups (pairs or singles) of gemm_bf16_tcgen05<BN, PAIR, *> on the current device.  The schedule
+// is persistent with a static stride, so every CTA (pair) must be co-resident: a pair needs both SMs of one TPC, and
+// not every TPC of a 148-SM part has two enabled SMs — ask the runtime how many clusters fit.  Cached per device.
 template <int BN, int PAIR>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                       const CUtensorMap& tmR, const GemmParams& p_in, int num_sms, cudaStream_t stream,
-                       void* splitk_ws, long long splitk_ws_bytes) {
+static int resident_groups(int num_sms) {
+  static int cache[kMaxDevices] = {};
+  int& g = cache[device_slot()];
+  if (g == 0) {
+    using Cfg = GemmCfg<BN, PAIR>;
+    (void)cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Cfg::kSmemBytes);
+    int n = num_sms / PAIR;
+    if (PAIR == 2) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.blockDim = dim3(kGemmThreads);
+      cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = PAIR;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cfg.gridDim = dim3((num_sms / PAIR) * PAIR);
+      int q = 0;
+      if (cudaOccupancyMaxActiveClusters(&q, gemm_bf16_tcgen05<BN, PAIR, false>, &cfg) == cudaSuccess && q > 0)
+        n = q < n ? q : n;
+      (void)cudaGetLastError();
+    }
+    g = n;
+    if (getenv("DS_DEBUG"))
+      fprintf(stderr, "[dsengine] gemm<%d,%d>: %d co-resident CTA %s of %d SMs\n", BN, PAIR, g,
+              PAIR == 2 ? "pairs" : "singles", num_sms);
+  }
+  return g;
+}
+
+template <int BN, int PAIR, bool STATS>
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                         const CUtensorMap& tmR, const CUtensorMap& tmA2, const GemmParams& p_in, int num_sms,
+                         cudaStream_t stream, void* splitk_ws, long long splitk_ws_bytes) {
   GemmParams p = p_in;
   using Cfg = GemmCfg<BN, PAIR>;
   const int slot = device_slot();
   static bool attr_set[kMaxDevices] = {};  // per device; benign race: idempotent
   if (!attr_set[slot]) {
-    DS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
     attr_set[slot] = true;
   }
@@ -680,23 +784,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   pdl_attr(&attr[1]);
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  // The schedule is persistent with a static stride, so every CTA (pair) must be co-resident: a pair needs both
-  // SMs of one TPC, and not every TPC of a 148-SM part has two enabled SMs.  Ask the runtime how many clusters fit.
-  static int max_groups_dev[kMaxDevices] = {};
-  int& max_groups = max_groups_dev[slot];
-  if (max_groups == 0) {
-    int n = num_sms / PAIR;
-    if (PAIR == 2) {
-      cfg.gridDim = dim3((num_sms / PAIR) * PAIR);
-      int q = 0;
-      if (cudaOccupancyMaxActiveClusters(&q, gemm_bf16_tcgen05<BN, PAIR>, &cfg) == cudaSuccess && q > 0) n = q < n ? q : n;
-      (void)cudaGetLastError();
-    }
-    max_groups = n;
-    if (getenv("DS_DEBUG"))
-      fprintf(stderr, "[dsengine] gemm<%d,%d>: %d co-resident CTA %s of %d SMs\n", BN, PAIR, max_groups,
-              PAIR == 2 ? "pairs" : "singles", num_sms);
-  }
+  const int max_groups = resident_groups<BN, PAIR>(num_sms);
   const int groups = units < max_groups ? units : max_groups;
   // split-K tail (see GemmParams): the units of the partial last wave are cut along K so that every CTA pair gets
   // a slice.  Needs the bf16 TMA epilogue, no GEGLU (its accumulator pairs value | gate columns) and a caller-provided
@@ -732,9 +820,19 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     }
   }
   cfg.gridDim = dim3(groups * PAIR);
-  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR>, tmA, tmB, tmC, tmR, p));
+  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR, STATS>, tmA, tmB, tmC, tmR, tmA2, p));
   DS_LAUNCH_OK("gemm_bf16_tcgen05");
   return DS_OK;
+}
+
+template <int BN, int PAIR>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                       const CUtensorMap& tmR, const CUtensorMap& tmA2, const GemmParams& p, int num_sms,
+                       cudaStream_t stream, void* splitk_ws, long long splitk_ws_bytes) {
+  // the statistics epilogue is a separate instantiation: the default one keeps its register budget
+  if (p.chan_stats)
+    return launch_gemm_t<BN, PAIR, true>(tmA, tmB, tmC, tmR, tmA2, p, num_sms, stream, splitk_ws, splitk_ws_bytes);
+  return launch_gemm_t<BN, PAIR, false>(tmA, tmB, tmC, tmR, tmA2, p, num_sms, stream, splitk_ws, splitk_ws_bytes);
 }
 
 static int pick_bn(int N, int epilogue) {
@@ -771,8 +869,8 @@ static bool make_out_map(CUtensorMap* m, const void* base, const GemmParams& p, 
   return encode_tmap_bf16(m, base, 2, dims, strides, box, nullptr);
 }
 
-static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& p, int conv_B, cudaStream_t stream,
-                    bool row_stats_zeroed, void* splitk_ws, long long splitk_ws_bytes) {
+static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const void* w, int ldw, GemmParams& p, int conv_B,
+                    cudaStream_t stream, bool row_stats_zeroed, void* splitk_ws, long long splitk_ws_bytes) {
   DeviceInfo dev;
   if (!get_device(&dev)) return DS_ERR_CUDA;
   const int bn = pick_bn(p.N, p.epilogue);
@@ -782,13 +880,6 @@ static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& 
     return e ? atoi(e) : 1;
   }();
   const int pair = (pair_env != 0 && p.num_m_tiles >= 2) ? 2 : 1;
-  CUtensorMap tmB;
-  {
-    const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
-    const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-    const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn / pair)};
-    if (!encode_tmap_bf16(&tmB, w, 2, dims, strides, box, nullptr)) return DS_ERR_CUDA;
-  }
   // coalesced TMA epilogue whenever the bf16 output (and residual) rows are 16-byte addressable
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.tma_epilogue = !p.out_fp32 && p.n_out % 8 == 0 && p.ldo % 8 == 0 && aligned16(p.out) &&
@@ -798,21 +889,68 @@ static int run_gemm(const CUtensorMap& tmA, const void* w, int ldw, GemmParams& 
     if (!row_stats_zeroed)
       DS_CUDA_OK(cudaMemsetAsync(p.row_stats_out, 0, sizeof(float) * 2 * static_cast<size_t>(p.M), stream));
   }
+  if (p.chan_stats) {
+    DS_REQUIRE(p.tma_epilogue && p.epilogue != DS_EPI_GEGLU,
+               "chan_stats needs a 16-byte addressable bf16 output and no GEGLU epilogue");
+    DS_REQUIRE((reinterpret_cast<uintptr_t>(p.chan_stats) & 15) == 0, "chan_stats must be 16-byte aligned");
+    if (!p.conv)
+      DS_REQUIRE(p.stats_rows_per_sample > 0 && p.stats_rows_per_sample % kBM == 0,
+                 "ds_gemm_bf16: chan_stats needs stats_rows_per_sample %% 128 == 0 (got %d)", p.stats_rows_per_sample);
+  }
   CUtensorMap tmC = tmA, tmR = tmA;  // placeholders when the direct epilogue is used
   if (p.tma_epilogue) {
     if (!make_out_map(&tmC, p.out, p, p.ldo, conv_B)) return DS_ERR_CUDA;
     if (p.residual && !make_out_map(&tmR, p.residual, p, p.ldres, conv_B)) return DS_ERR_CUDA;
   }
-  p.num_n_tiles = (p.N + bn - 1) / bn;
   p.conv_B = conv_B;
-  if (pair == 2) {
-    if (bn == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
-    if (bn == 192) return launch_gemm<192, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
-    return launch_gemm<128, 2>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+  p.m_pair0 = 0;
+  auto launch = [&](int bn_l, const GemmParams& q) -> int {
+    CUtensorMap tmB;
+    const uint64_t dims[2] = {static_cast<uint64_t>(q.K), static_cast<uint64_t>(q.N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn_l / pair)};
+    if (!encode_tmap_bf16(&tmB, w, 2, dims, strides, box, nullptr)) return DS_ERR_CUDA;
+    if (pair == 2) {
+      if (bn_l == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, tmA2, q, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+      if (bn_l == 192) return launch_gemm<192, 2>(tmA, tmB, tmC, tmR, tmA2, q, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+      return launch_gemm<128, 2>(tmA, tmB, tmC, tmR, tmA2, q, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+    }
+    if (bn_l == 256) return launch_gemm<256, 1>(tmA, tmB, tmC, tmR, tmA2, q, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+    if (bn_l == 192) return launch_gemm<192, 1>(tmA, tmB, tmC, tmR, tmA2, q, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+    return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, tmA2, q, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+  };
+  p.num_n_tiles = (p.N + bn - 1) / bn;
+  // ---- tail launch: 160 tiles on 74 CTA pairs are 2.16 rounds that cost 3.  Cover the m-rows of the full rounds with
+  // the wide tiles and the few remaining m-rows with BN=128 tiles (twice as many units, each half as long, ~0.62 of a
+  // wide round per narrow round: narrow pair tiles are shared-memory-port bound) in a second launch.
+  static const int tail_env = [] {
+    const char* e = getenv("DS_GEMM_TAIL");
+    return e ? atoi(e) : 1;
+  }();
+  if (tail_env && pair == 2 && bn == 256 && p.epilogue != DS_EPI_GEGLU) {
+    const int G = resident_groups<256, 2>(dev.num_sms);
+    const int G128 = resident_groups<128, 2>(dev.num_sms);
+    const int mp = (p.num_m_tiles + 1) / 2, nt = p.num_n_tiles;
+    const int units = mp * nt;
+    const int full = units / G, rem = units - full * G;
+    if (full >= 1 && rem > 0 && rem * 100 < G * 45 && G128 > 0) {
+      const int R = (full * G) / nt;                 // m-pairs the wide launch covers in exactly `full` rounds
+      const int nt128 = (p.N + 127) / 128;
+      const int units_b = (mp - R) * nt128;
+      const float cost = static_cast<float>((R * nt + G - 1) / G) + 0.62f * static_cast<float>((units_b + G128 - 1) / G128);
+      if (R >= 1 && R < mp && cost < 0.95f * static_cast<float>(full + 1)) {
+        GemmParams qa = p, qb = p;
+        qa.num_m_tiles = R * 2;                      // rows beyond are simply not visited by this launch
+        qb.m_pair0 = R;
+        qb.num_m_tiles = p.num_m_tiles - R * 2;
+        qb.num_n_tiles = nt128;
+        const int rc = launch(256, qa);
+        if (rc != DS_OK) return rc;
+        return launch(128, qb);
+      }
+    }
   }
-  if (bn == 256) return launch_gemm<256, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
-  if (bn == 192) return launch_gemm<192, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
-  return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+  return launch(bn, p);
 }
 
 }  // namespace ds
@@ -825,7 +963,7 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
              a->K);
   DS_REQUIRE(a->K % 8 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0,
              "ds_gemm_bf16: K, lda, ldw must be multiples of 8 (got %d,%d,%d)", a->K, a->lda, a->ldw);
-  DS_REQUIRE(a->lda >= a->K && a->ldw >= a->K, "ds_gemm_bf16: lda/ldw smaller than K");
+  DS_REQUIRE((a->a2 || a->lda >= a->K) && a->ldw >= a->K, "ds_gemm_bf16: lda/ldw smaller than K");
   DS_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
              "ds_gemm_bf16: a and w must be 16-byte aligned");
   DS_REQUIRE(a->epilogue >= DS_EPI_NONE && a->epilogue <= DS_EPI_SILU, "ds_gemm_bf16: bad epilogue %d", a->epilogue);
@@ -876,9 +1014,27 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
                "ds_gemm_bf16: zero_rows must be 8-byte aligned and distinct from ln_stats / row_stats_out");
   p.num_m_tiles = (a->M + kBM - 1) / kBM;
   p.num_k_iters = (a->K + kBK - 1) / kBK;
+  p.k1_iters = p.num_k_iters;
   p.conv = 0;
-  return run_gemm(tmA, a->w, a->ldw, p, 0, static_cast<cudaStream_t>(stream), a->row_stats_zeroed != 0, a->splitk_ws,
-                  a->splitk_ws_bytes);
+  p.chan_stats = a->chan_stats;
+  p.stats_rows_per_sample = a->stats_rows_per_sample;
+  CUtensorMap tmA2 = tmA;
+  if (a->a2) {
+    DS_REQUIRE(a->K1 > 0 && a->K1 < a->K && a->K1 % kBK == 0, "ds_gemm_bf16: a2 needs 0 < K1 < K and K1 %% 64 == 0");
+    DS_REQUIRE(a->lda >= a->K1 && a->lda2 >= a->K - a->K1 && a->lda2 % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(a->a2) & 15) == 0,
+               "ds_gemm_bf16: bad lda / lda2 / alignment for the two-operand form");
+    const uint64_t dims1[2] = {static_cast<uint64_t>(a->K1), static_cast<uint64_t>(a->M)};
+    const uint64_t strides1[1] = {static_cast<uint64_t>(a->lda) * 2};
+    const uint64_t dims2[2] = {static_cast<uint64_t>(a->K - a->K1), static_cast<uint64_t>(a->M)};
+    const uint64_t strides2[1] = {static_cast<uint64_t>(a->lda2) * 2};
+    const uint32_t box[2] = {kBK, kBM};
+    if (!encode_tmap_bf16(&tmA, a->a, 2, dims1, strides1, box, nullptr)) return DS_ERR_CUDA;
+    if (!encode_tmap_bf16(&tmA2, a->a2, 2, dims2, strides2, box, nullptr)) return DS_ERR_CUDA;
+    p.k1_iters = a->K1 / kBK;
+  }
+  return run_gemm(tmA, tmA2, a->w, a->ldw, p, 0, static_cast<cudaStream_t>(stream), a->row_stats_zeroed != 0,
+                  a->splitk_ws, a->splitk_ws_bytes);
 }
 
 extern "C" int64_t ds_gemm_splitk_ws_bytes(void) {
@@ -937,6 +1093,8 @@ extern "C" int ds_conv3x3_nhwc(const ds_conv3x3_args* a, void* stream) {
   p.Ho = Ho;
   p.Wo = Wo;
   p.cin_chunks = a->Cin / kBK;
-  return run_gemm(tmA, a->w, 9 * a->Cin, p, a->B, static_cast<cudaStream_t>(stream), false, a->splitk_ws,
+  p.k1_iters = p.num_k_iters;
+  p.chan_stats = a->chan_stats;
+  return run_gemm(tmA, tmA, a->w, 9 * a->Cin, p, a->B, static_cast<cudaStream_t>(stream), false, a->splitk_ws,
                   a->splitk_ws_bytes);
 }

@@ -2,12 +2,16 @@
 //
 // GroupNorm on NHWC: a group's channels are interleaved with every other group's inside each pixel, so the
 // coalesced decomposition is by PIXEL RANGE, not by group: a CTA streams a contiguous run of pixels (all
-// channels, 16-byte vectors, every thread pinned to the same 8 channels), accumulates per-channel
-// sum / sum-of-squares in registers, folds them to the 32 groups through shared memory and publishes one
-// double-precision atomicAdd pair per (sample, group).  The apply pass re-reads x (walking the chunks in the
-// reverse order so the tail of the stats pass is still resident in the 126 MB L2), normalises, applies
-// gamma/beta and SiLU in fp32 and rounds once to bf16.
-// Algorithmic bytes: read x + write y = 4 B/element; the stats re-read is overhead (roofline.traffic shows it).
+// channels, 16-byte vectors, every thread pinned to the same 8 channels).
+//   statistics : per-(sample, CHANNEL) {sum, sum of squares} in fp64, [B][C][2].  Normally they come for free from
+//                the epilogue of the GEMM / conv that PRODUCED the tensor (gemm_tcgen05.cu, `chan_stats`); tensors
+//                without such a producer (conv_in output, unaligned shapes) get them from chan_stats_kernel.
+//                Per-channel (not per-group) sums make them composable: the statistics of torch.cat([h, skip], 1)
+//                are the two tensors' statistics side by side, whatever the group boundaries of the result.
+//   apply      : gn_apply2_kernel reads x ONCE (from one or two source tensors — the up-block concatenation is never
+//                written), folds the channel sums into the 32 groups' mean / rstd in shared memory (fixed order),
+//                normalises, applies gamma / beta (+ SiLU) in fp32 and rounds once to bf16.
+// Algorithmic bytes: read x + write y = 4 B/element — which is all the apply kernel moves.
 //
 // Replaces diffusers ResnetBlock2D.norm1/norm2+SiLU, Transformer2DModel.norm, conv_norm_out+conv_act
 // (reached from src/models/unet.py:251-261,281-290,316-338) and BasicTransformerBlock / Resampler LayerNorms
@@ -45,29 +49,31 @@ __device__ __forceinline__ uint4 ldg_hint(const uint4* ptr, uint64_t pol) {
   return v;
 }
 
-// Work decomposition shared by both passes: the tensor is cut into ITEMS of `ipx` consecutive pixels of one sample
-// (item id = sample * items_per_sample + k); a launch has exactly one resident wave of CTAs (grid = SMs x
-// occupancy) and CTA c owns the contiguous item range [c*I/G, (c+1)*I/G) — so no tail wave, and a CTA touches at
-// most a couple of samples.  blockDim.x = cv * rpb (cv = C/8 16-byte vectors per pixel, rpb pixel rows per sweep);
-// every thread stays pinned to the same 8 channels.
+// Work decomposition: the tensor is cut into ITEMS of `ipx` consecutive pixels of one sample (item id = sample *
+// items_per_sample + k); a launch has exactly one resident wave of CTAs (grid = SMs x occupancy) and CTA c owns the
+// contiguous item range [c*I/G, (c+1)*I/G) — so no tail wave, and a CTA touches at most a couple of samples.
+// blockDim.x = cv * rpb (cv = C/8 16-byte vectors per pixel, rpb pixel rows per sweep); every thread stays pinned to
+// the same 8 channels.
 __device__ __forceinline__ void gn_item_range(int total_items, int& i0, int& i1) {
   const long long g = gridDim.x, c = blockIdx.x;
   i0 = static_cast<int>(c * total_items / g);
   i1 = static_cast<int>((c + 1) * total_items / g);
 }
 
-__global__ void gn_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int HW, int C, int groups,
-                                int items_per_sample, int ipx, int total_items, int l2_hints) {
-  extern __shared__ double sh[];  // [2*groups]
+// Per-(sample, channel) {sum, sum of squares} of a [B][HW][C] bf16 tensor -> fp64 [B][C][2] (accumulated: the caller
+// zeroes it).  Threads keep fp32 partials over <= a few hundred pixels, the CTA's pixel rows are combined in a fixed
+// order in shared memory and every channel adds ONE fp64 pair per (CTA, sample) — fp64 sums of a few hundred fp32
+// partials are exact, so the result does not depend on the arrival order.
+__global__ void chan_stats_kernel(const uint4* __restrict__ x, double* __restrict__ stats, int HW, int C,
+                                  int items_per_sample, int ipx, int total_items) {
+  extern __shared__ float shs[];  // [rpb][C][2]
   const int cv = C >> 3;
   const int rpb = blockDim.x / cv;
   const int cvec = threadIdx.x % cv;
   const int prow = threadIdx.x / cv;
-  const int cpg = C / groups;
   int i0, i1;
   gn_item_range(total_items, i0, i1);
   if (i0 >= i1) return;
-
   float s[8], q[8];
   auto reset = [&]() {
 #pragma unroll
@@ -84,35 +90,28 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x, double* __restrict_
       q[2 * j + 1] = fmaf(c, c, q[2 * j + 1]);
     }
   };
-  // fold this thread's 8 channel partials into their groups (smem, fp64) and publish one atomic pair per group
   auto flush = [&](int b) {
-    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sh[i] = 0.0;
-    __syncthreads();
-    const int c0 = cvec * 8;
-    int g_run = c0 / cpg;
-    double rs = 0.0, rq = 0.0;
+    float* row = shs + (static_cast<size_t>(prow) * C + cvec * 8) * 2;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (c0 + j) / cpg;
-      if (g != g_run) {
-        atomicAdd(&sh[2 * g_run], rs);
-        atomicAdd(&sh[2 * g_run + 1], rq);
-        g_run = g;
-        rs = rq = 0.0;
-      }
-      rs += static_cast<double>(s[j]);
-      rq += static_cast<double>(q[j]);
+      row[2 * j] = s[j];
+      row[2 * j + 1] = q[j];
     }
-    atomicAdd(&sh[2 * g_run], rs);
-    atomicAdd(&sh[2 * g_run + 1], rq);
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
-      atomicAdd(&stats[static_cast<size_t>(b) * 2 * groups + i], sh[i]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float ts = 0.f, tq = 0.f;
+      for (int r = 0; r < rpb; ++r) {
+        ts += shs[(static_cast<size_t>(r) * C + c) * 2];
+        tq += shs[(static_cast<size_t>(r) * C + c) * 2 + 1];
+      }
+      double* gp = stats + (static_cast<size_t>(b) * C + c) * 2;
+      atomicAdd(gp, static_cast<double>(ts));
+      atomicAdd(gp + 1, static_cast<double>(tq));
+    }
     __syncthreads();
   };
-
   reset();
-  const uint64_t pol = l2_hints ? l2_policy_evict_last() : l2_policy_normal();
+  const uint64_t pol = l2_policy_evict_last();  // the GroupNorm apply pass that follows re-reads x
   int cur_b = i0 / items_per_sample;
   for (int it = i0; it < i1; ++it) {
     const int b = it / items_per_sample;
@@ -137,35 +136,68 @@ __global__ void gn_stats_kernel(const uint4* __restrict__ x, double* __restrict_
   flush(cur_b);
 }
 
-template <bool kSilu>
-__global__ void gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const double* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C,
-                                int groups, float eps, int items_per_sample, int ipx, int total_items, int l2_hints) {
-  const int cv = C >> 3;
+// GroupNorm(+SiLU) apply from per-channel statistics; x = [x1 | x2] along channels (x2 may be NULL).
+// kU = independent 16-byte loads in flight per thread.
+template <bool kSilu, int kU>
+__global__ void gn_apply2_kernel(const uint4* __restrict__ x1, const uint4* __restrict__ x2, uint4* __restrict__ y,
+                                 const double* __restrict__ st1, const double* __restrict__ st2,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C1, int C2,
+                                 int groups, float eps, int items_per_sample, int ipx, int total_items) {
+  extern __shared__ double shd[];  // [C][2] channel sums of the current sample, then [groups][2] {mean, rstd}
+  const int C = C1 + C2;
+  const int cv = C >> 3, cv1 = C1 >> 3;
   const int rpb = blockDim.x / cv;
   const int cvec = threadIdx.x % cv;
   const int prow = threadIdx.x / cv;
   const int cpg = C / groups;
   const double inv_n = 1.0 / (static_cast<double>(HW) * cpg);
+  float* sh_coef = reinterpret_cast<float*>(shd + 2 * static_cast<size_t>(C));  // [groups][2]
   int i0, i1;
   gn_item_range(total_items, i0, i1);
   if (i0 >= i1) return;
+  // this thread's source: its 8 channels live entirely in x1 or entirely in x2 (C1 % 8 == 0)
+  const bool second = cvec >= cv1;
+  const uint4* xsrc = second ? x2 : x1;
+  const int scv = second ? (cv - cv1) : cv1;        // row pitch of the source in 16-byte vectors
+  const int svec = second ? (cvec - cv1) : cvec;
   float ga[8], be[8], sc[8], sf[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     ga[j] = __ldg(gamma + cvec * 8 + j);
     be[j] = __ldg(beta + cvec * 8 + j);
   }
+  const uint64_t pol = l2_policy_evict_first();      // x is dead after this read; y stays for the consumer conv
+  // group coefficients of sample b: channel sums -> smem -> 32 threads fold cpg channels each, in order
   auto load_coeffs = [&](int b) {
+    __syncthreads();                                 // previous sample's coefficients no longer in use
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double* gp = (c < C1) ? st1 + (static_cast<size_t>(b) * C1 + c) * 2
+                                  : st2 + (static_cast<size_t>(b) * C2 + (c - C1)) * 2;
+      const double2 v = *reinterpret_cast<const double2*>(gp);
+      shd[2 * c] = v.x;
+      shd[2 * c + 1] = v.y;
+    }
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      double ts = 0.0, tq = 0.0;
+      const double* gp = shd + 2 * static_cast<size_t>(threadIdx.x) * cpg;
+      for (int k = 0; k < cpg; ++k) {
+        ts += gp[2 * k];
+        tq += gp[2 * k + 1];
+      }
+      const double mean = ts * inv_n;
+      double var = tq * inv_n - mean * mean;
+      var = var < 0.0 ? 0.0 : var;
+      sh_coef[2 * threadIdx.x] = static_cast<float>(mean);
+      sh_coef[2 * threadIdx.x + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int g = (cvec * 8 + j) / cpg;
-      const double mean = stats[static_cast<size_t>(b) * 2 * groups + 2 * g] * inv_n;
-      double var = stats[static_cast<size_t>(b) * 2 * groups + 2 * g + 1] * inv_n - mean * mean;
-      var = var < 0.0 ? 0.0 : var;
-      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      const float mean = sh_coef[2 * g], rstd = sh_coef[2 * g + 1];
       sc[j] = rstd * ga[j];
-      sf[j] = be[j] - static_cast<float>(mean) * rstd * ga[j];
+      sf[j] = be[j] - mean * rstd * ga[j];
     }
   };
   auto norm8 = [&](const uint4& u) -> uint4 {
@@ -184,231 +216,36 @@ __global__ void gn_apply_kernel(const uint4* __restrict__ x, uint4* __restrict__
     return make_uint4(o[0], o[1], o[2], o[3]);
   };
   int cur_b = -1;
-  const uint64_t pol = l2_hints ? l2_policy_evict_first() : l2_policy_normal();
-  // walk this CTA's range backwards: the stats pass streamed it forwards, so its tail is the most likely part of
-  // x to still sit in the 126 MB L2
-  for (int it = i1 - 1; it >= i0; --it) {
+  for (int it = i0; it < i1; ++it) {
     const int b = it / items_per_sample;
-    if (b != cur_b) {
+    const int p0 = (it - b * items_per_sample) * ipx;
+    const int p1 = min(p0 + ipx, HW);
+    const uint4* xb = xsrc + (static_cast<size_t>(b) * HW) * scv + svec;
+    uint4* yb = y + (static_cast<size_t>(b) * HW) * cv + cvec;
+    int p = p0 + prow;
+    // the first batch of loads is issued BEFORE the (CTA-wide, L2-latency-bound) coefficient fold of a new sample
+    uint4 u[kU];
+    const bool full = p + (kU - 1) * rpb < p1;
+    if (full) {
+#pragma unroll
+      for (int k = 0; k < kU; ++k) u[k] = ldg_hint(xb + static_cast<size_t>(p + k * rpb) * scv, pol);
+    }
+    if (b != cur_b) {  // CTA-uniform
       load_coeffs(b);
       cur_b = b;
     }
-    const int p0 = (it - b * items_per_sample) * ipx;
-    const int p1 = min(p0 + ipx, HW);
-    const size_t off = (static_cast<size_t>(b) * HW) * cv + cvec;
-    const uint4* xb = x + off;
-    uint4* yb = y + off;
-    int p = p0 + prow;
-    for (; p + 3 * rpb < p1; p += 4 * rpb) {
-      uint4 u[4];
+    if (full) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = ldg_hint(xb + static_cast<size_t>(p + k * rpb) * cv, pol);
+      for (int k = 0; k < kU; ++k) yb[static_cast<size_t>(p + k * rpb) * cv] = norm8(u[k]);
+      p += kU * rpb;
+    }
+    for (; p + (kU - 1) * rpb < p1; p += kU * rpb) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) yb[static_cast<size_t>(p + k * rpb) * cv] = norm8(u[k]);
-    }
-    for (; p < p1; p += rpb) yb[static_cast<size_t>(p) * cv] = norm8(ldg_hint(xb + static_cast<size_t>(p) * cv, pol));
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// gn_fused_kernel — GroupNorm(+SiLU) in ONE pass over HBM: x is read once and y written once (the algorithmic
-// 4 B/element; the two-kernel path above reads x twice).
-//   * cooperative persistent grid, one CTA per SM.  Sample b is cut into gridDim.x contiguous pixel slices; CTA c
-//     owns slice c of EVERY sample and keeps it in shared memory (1-D bulk-async copies, NBUF-deep ring), so the
-//     second "pass" (normalise) reads shared memory, not HBM.
-//   * per sample: partial (sum, sum of squares) per group -> fp64 atomics in global memory -> arrival counter;
-//     a CTA normalises sample b only after all gridDim.x slices of b have arrived.  The wait is software-pipelined:
-//     the CTA accumulates the statistics of sample b+1 (already in its ring) before it waits for sample b, and the
-//     loads of samples b+2.. are in flight meanwhile, so HBM never idles on the barrier.
-//   * the spin on the arrival counter is bounded (trap), and the launch is cooperative, so a scheduling surprise
-//     is a launch error, not a hung GPU.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-template <bool kSilu>
-__global__ void __launch_bounds__(512, 1)
-gn_fused_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, float* __restrict__ partials,
-                unsigned int* __restrict__ arrived, const float* __restrict__ gamma, const float* __restrict__ beta,
-                int B, int HW, int C, int groups, float eps, int nbuf, int slice_stride) {
-  extern __shared__ uint8_t gsm_raw[];
-  uint8_t* gsm = gsm_raw + ((128u - (smem_u32(gsm_raw) & 127u)) & 127u);
-  uint64_t* full = reinterpret_cast<uint64_t*>(gsm);           // [nbuf]
-  double* sh_part = reinterpret_cast<double*>(gsm + 64);        // [2*groups] CTA partials, fp64 so that the order of
-                                                                // the shared-memory atomics cannot change the result
-  float* sh_coef = reinterpret_cast<float*>(gsm + 64 + 1024);   // [2*groups] mean, rstd of the sample being applied
-  float* sh_red = sh_coef + 128;                                // [8][2*groups] chunked column sums of the partials
-  uint8_t* ring = gsm + 5760;                                   // nbuf x slice_stride bytes
-
-  const int cv = C >> 3;                 // 16-byte vectors per pixel
-  const int rpb = blockDim.x / cv;       // pixel rows per sweep (blockDim.x == cv * rpb)
-  const int cvec = threadIdx.x % cv;
-  const int prow = threadIdx.x / cv;
-  const int cpg = C / groups;
-  const int G2 = 2 * groups;
-  // this CTA's pixel slice (same for every sample)
-  const int p0 = static_cast<int>(static_cast<long long>(blockIdx.x) * HW / gridDim.x);
-  const int p1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * HW / gridDim.x);
-  const int npx = p1 - p0;
-  const uint32_t bytes = static_cast<uint32_t>(npx) * C * 2;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < nbuf; ++i) mbar_init(&full[i], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  auto issue_load = [&](int b) {  // thread 0 only
-    uint64_t* bar = &full[b % nbuf];
-    if (bytes == 0) {
-      mbar_arrive(bar);
-      return;
-    }
-    mbar_arrive_expect_tx(bar, bytes);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(x) + (static_cast<size_t>(b) * HW + p0) * C * 2;
-    uint8_t* dst = ring + static_cast<size_t>(b % nbuf) * slice_stride;
-    uint32_t off = 0;
-    while (off < bytes) {  // bulk copies of at most 64 KB
-      const uint32_t n = bytes - off < 65536u ? bytes - off : 65536u;
-      bulk_load_1d(dst + off, src + off, n, bar);
-      off += n;
-    }
-  };
-  if (threadIdx.x == 0)
-    for (int b = 0; b < nbuf && b < B; ++b) issue_load(b);
-
-  float ga[8], be[8];
+      for (int k = 0; k < kU; ++k) u[k] = ldg_hint(xb + static_cast<size_t>(p + k * rpb) * scv, pol);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    ga[j] = __ldg(gamma + cvec * 8 + j);
-    be[j] = __ldg(beta + cvec * 8 + j);
-  }
-  const double inv_n = 1.0 / (static_cast<double>(HW) * cpg);
-
-  // statistics of sample b from its shared-memory slice -> this CTA's row of the partials table -> arrival counter.
-  // No global atomics except the counter: 148 CTAs x 64 same-address fp64 atomics per sample were what made the
-  // first version slower than the two-kernel path.
-  auto do_stats = [&](int b) {
-    mbar_wait(&full[b % nbuf], (b / nbuf) & 1);
-    for (int i = threadIdx.x; i < G2; i += blockDim.x) sh_part[i] = 0.0;
-    __syncthreads();
-    const uint4* tile = reinterpret_cast<const uint4*>(ring + static_cast<size_t>(b % nbuf) * slice_stride);
-    float s[8], q[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    for (int r = prow; r < npx; r += rpb) {
-      const uint4 u = tile[static_cast<size_t>(r) * cv + cvec];
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a = bf16_lo(w[j]), c = bf16_hi(w[j]);
-        s[2 * j] += a;
-        q[2 * j] = fmaf(a, a, q[2 * j]);
-        s[2 * j + 1] += c;
-        q[2 * j + 1] = fmaf(c, c, q[2 * j + 1]);
-      }
+      for (int k = 0; k < kU; ++k) yb[static_cast<size_t>(p + k * rpb) * cv] = norm8(u[k]);
     }
-    const int c0 = cvec * 8;
-    int g_run = c0 / cpg;
-    double rs = 0.0, rq = 0.0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (c0 + j) / cpg;
-      if (g != g_run) {
-        atomicAdd(&sh_part[2 * g_run], rs);
-        atomicAdd(&sh_part[2 * g_run + 1], rq);
-        g_run = g;
-        rs = rq = 0.0;
-      }
-      rs += static_cast<double>(s[j]);
-      rq += static_cast<double>(q[j]);
-    }
-    atomicAdd(&sh_part[2 * g_run], rs);
-    atomicAdd(&sh_part[2 * g_run + 1], rq);
-    __syncthreads();
-    float* mine = partials + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * G2;
-    for (int i = threadIdx.x; i < G2; i += blockDim.x) __stcg(mine + i, static_cast<float>(sh_part[i]));
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(&arrived[b], 1u);
-  };
-
-  for (int b = 0; b < B; ++b) {
-    if (b == 0) do_stats(0);
-    if (b + 1 < B) do_stats(b + 1);  // its slice is already in the ring: hide sample b's barrier behind this work
-    // ---- wait until every CTA has published sample b's partial statistics
-    if (threadIdx.x == 0) {
-      const long long t0 = clock64();
-      unsigned int v;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(arrived + b) : "memory");
-        if (clock64() - t0 > 4000000000LL) __trap();
-      } while (v < gridDim.x);
-    }
-    __syncthreads();
-    // ---- column sums of the [gridDim.x][2*groups] partials table in a fixed order (deterministic)
-    {
-      const int col = threadIdx.x % G2, chunk = threadIdx.x / G2;  // blockDim.x >= 448 >= 7 * 64 when groups = 32
-      const int nchunks = blockDim.x / G2 < 8 ? blockDim.x / G2 : 8;
-      if (chunk < nchunks) {
-        const int per = (gridDim.x + nchunks - 1) / nchunks;
-        const int r0 = chunk * per, r1 = min(r0 + per, static_cast<int>(gridDim.x));
-        const float* tab = partials + static_cast<size_t>(b) * gridDim.x * G2 + col;
-        float acc = 0.f;
-        for (int r = r0; r < r1; ++r) acc += __ldcg(tab + static_cast<size_t>(r) * G2);
-        sh_red[chunk * G2 + col] = acc;
-      }
-      __syncthreads();
-      for (int i = threadIdx.x; i < groups; i += blockDim.x) {
-        double sum = 0.0, sq = 0.0;
-        for (int c = 0; c < nchunks; ++c) {
-          sum += static_cast<double>(sh_red[c * G2 + 2 * i]);
-          sq += static_cast<double>(sh_red[c * G2 + 2 * i + 1]);
-        }
-        const double mean = sum * inv_n;
-        double var = sq * inv_n - mean * mean;
-        var = var < 0.0 ? 0.0 : var;
-        sh_coef[2 * i] = static_cast<float>(mean);
-        sh_coef[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-      }
-      __syncthreads();
-    }
-    // ---- normalise sample b from shared memory, write y
-    {
-      float sc[8], sf[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int g = (cvec * 8 + j) / cpg;
-        const float mean = sh_coef[2 * g], rstd = sh_coef[2 * g + 1];
-        sc[j] = rstd * ga[j];
-        sf[j] = be[j] - mean * rstd * ga[j];
-      }
-      const uint4* tile = reinterpret_cast<const uint4*>(ring + static_cast<size_t>(b % nbuf) * slice_stride);
-      uint4* yb = y + (static_cast<size_t>(b) * HW + p0) * cv + cvec;
-      for (int r = prow; r < npx; r += rpb) {
-        const uint4 u = tile[static_cast<size_t>(r) * cv + cvec];
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-        uint32_t o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float a = fmaf(bf16_lo(w[j]), sc[2 * j], sf[2 * j]);
-          float c = fmaf(bf16_hi(w[j]), sc[2 * j + 1], sf[2 * j + 1]);
-          if (kSilu) {
-            a = silu_tanh_f(a);
-            c = silu_tanh_f(c);
-          }
-          o[j] = pack_bf16_alu(a, c);
-        }
-        yb[static_cast<size_t>(r) * cv] = make_uint4(o[0], o[1], o[2], o[3]);
-      }
-    }
-    // ---- recycle the ring slot: generic-proxy reads above must be ordered before the async-proxy refill
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0 && b + nbuf < B) issue_load(b + nbuf);
+    for (; p < p1; p += rpb) yb[static_cast<size_t>(p) * cv] = norm8(ldg_hint(xb + static_cast<size_t>(p) * scv, pol));
   }
 }
 
@@ -476,131 +313,146 @@ __global__ void layernorm_kernel(const uint4* __restrict__ x, uint4* __restrict_
 
 }  // namespace ds
 
+namespace {
+struct GnPlan {
+  int threads, rpb, ipx, items_per_sample, total_items;
+};
+// blockDim = cv * rpb threads (<= target), items of `sweeps` sweeps of the CTA's pixel rows
+static bool gn_plan(int B, int HW, int C, int target_threads, int sweeps, GnPlan* pl) {
+  const int cv = C / 8;
+  if (cv > 1024) return false;
+  int rpb = target_threads / cv;
+  if (rpb < 1) rpb = 1;
+  pl->rpb = rpb;
+  pl->threads = cv * rpb;
+  pl->ipx = sweeps * rpb;
+  pl->items_per_sample = (HW + pl->ipx - 1) / pl->ipx;
+  const long long t = static_cast<long long>(B) * pl->items_per_sample;
+  if (t >= (1ll << 30)) return false;
+  pl->total_items = static_cast<int>(t);
+  return true;
+}
+static int gn_env(const char* name, int dflt, int lo, int hi) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : dflt;
+  return v >= lo && v <= hi ? v : dflt;
+}
+}  // namespace
+
+extern "C" int ds_channel_stats(const void* x, double* stats, int B, int HW, int C, void* stream) {
+  using namespace ds;
+  DS_REQUIRE(x && stats, "ds_channel_stats: NULL pointer");
+  DS_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && C <= 8192, "ds_channel_stats: bad shape (C %% 8 == 0, C <= 8192)");
+  DS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(stats) & 15) == 0,
+             "ds_channel_stats: x / stats must be 16-byte aligned");
+  DeviceInfo dev;
+  if (!get_device(&dev)) return DS_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const int tt = gn_env("DS_GN_STATS_THREADS", 512, 64, 1024);
+  GnPlan pl;
+  DS_REQUIRE(gn_plan(B, HW, C, tt, 8, &pl), "ds_channel_stats: tensor too large");
+  const size_t smem = static_cast<size_t>(pl.rpb) * C * 2 * sizeof(float);
+  static size_t attr[kMaxDevices] = {};
+  if (smem > 48 * 1024 && smem > attr[device_slot()]) {
+    DS_CUDA_OK(cudaFuncSetAttribute(chan_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr[device_slot()] = smem;
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chan_stats_kernel, pl.threads, smem) != cudaSuccess || occ < 1) {
+    (void)cudaGetLastError();
+    occ = 1;
+  }
+  if (occ > 2) occ = 2;  // few, fat CTAs: every CTA ends with 2*C fp64 atomics per sample it touched
+  const long long g = static_cast<long long>(occ) * dev.num_sms;
+  const int grid = static_cast<int>(g < pl.total_items ? g : pl.total_items);
+  chan_stats_kernel<<<grid, pl.threads, smem, st>>>(static_cast<const uint4*>(x), stats, HW, C, pl.items_per_sample,
+                                                    pl.ipx, pl.total_items);
+  DS_LAUNCH_OK("chan_stats_kernel");
+  return DS_OK;
+}
+
+extern "C" int ds_groupnorm_apply(const void* x1, const double* stats1, int C1, const void* x2, const double* stats2,
+                                  int C2, void* y, const float* gamma, const float* beta, int B, int HW, int groups,
+                                  float eps, int apply_silu, void* stream) {
+  using namespace ds;
+  DS_REQUIRE(x1 && stats1 && y && gamma && beta, "ds_groupnorm_apply: NULL pointer");
+  DS_REQUIRE((x2 == nullptr) == (C2 == 0) && (x2 == nullptr) == (stats2 == nullptr),
+             "ds_groupnorm_apply: x2 / stats2 / C2 must be given together");
+  const int C = C1 + C2;
+  DS_REQUIRE(B > 0 && HW > 0 && C1 > 0 && C2 >= 0 && groups > 0 && groups <= 64, "ds_groupnorm_apply: bad shape");
+  DS_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && C % groups == 0 && C <= 8192,
+             "ds_groupnorm_apply: C1, C2 must be multiples of 8 and C1 + C2 (%d) a multiple of groups (%d)", C, groups);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  DS_REQUIRE(al16(x1) && al16(y) && al16(stats1) && (!x2 || (al16(x2) && al16(stats2))),
+             "ds_groupnorm_apply: x / y / stats must be 16-byte aligned");
+  DeviceInfo dev;
+  if (!get_device(&dev)) return DS_ERR_CUDA;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const int tt = gn_env("DS_GN_THREADS", 256, 64, 1024);
+  static const int unroll = gn_env("DS_GN_UNROLL", 8, 4, 8);
+  static const int max_occ = gn_env("DS_GN_OCC", 8, 1, 16);
+  GnPlan pl;
+  DS_REQUIRE(gn_plan(B, HW, C, tt, unroll, &pl), "ds_groupnorm_apply: tensor too large");
+  const size_t smem = static_cast<size_t>(C) * 2 * sizeof(double) + static_cast<size_t>(groups) * 2 * sizeof(float);
+  const void* fn;
+  if (unroll == 8)
+    fn = apply_silu ? reinterpret_cast<const void*>(gn_apply2_kernel<true, 8>)
+                    : reinterpret_cast<const void*>(gn_apply2_kernel<false, 8>);
+  else
+    fn = apply_silu ? reinterpret_cast<const void*>(gn_apply2_kernel<true, 4>)
+                    : reinterpret_cast<const void*>(gn_apply2_kernel<false, 4>);
+  static size_t attr[kMaxDevices][4] = {};
+  size_t& a = attr[device_slot()][(unroll == 8 ? 2 : 0) + (apply_silu ? 1 : 0)];
+  if (smem > 48 * 1024 && smem > a) {
+    DS_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    a = smem;
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl.threads, smem) != cudaSuccess || occ < 1) {
+    (void)cudaGetLastError();
+    occ = 1;
+  }
+  if (occ > max_occ) occ = max_occ;
+  const long long g = static_cast<long long>(occ) * dev.num_sms;
+  const int grid = static_cast<int>(g < pl.total_items ? g : pl.total_items);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(pl.threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  const uint4* a1 = static_cast<const uint4*>(x1);
+  const uint4* a2 = static_cast<const uint4*>(x2);
+  uint4* yp = static_cast<uint4*>(y);
+#define DS_GN_LAUNCH(S, U)                                                                                         \
+  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_apply2_kernel<S, U>, a1, a2, yp, stats1, stats2, gamma, beta, HW, C1, C2, \
+                                groups, eps, pl.items_per_sample, pl.ipx, pl.total_items))
+  if (unroll == 8) {
+    if (apply_silu) DS_GN_LAUNCH(true, 8); else DS_GN_LAUNCH(false, 8);
+  } else {
+    if (apply_silu) DS_GN_LAUNCH(true, 4); else DS_GN_LAUNCH(false, 4);
+  }
+#undef DS_GN_LAUNCH
+  DS_LAUNCH_OK("gn_apply2_kernel");
+  return DS_OK;
+}
+
 extern "C" int ds_groupnorm_silu(const void* x, void* y, const float* gamma, const float* beta, float* stats, int B,
                                  int HW, int C, int groups, float eps, int apply_silu, void* stream) {
   using namespace ds;
   DS_REQUIRE(x && y && gamma && beta && stats, "ds_groupnorm_silu: NULL pointer");
   DS_REQUIRE(B > 0 && HW > 0 && C > 0 && groups > 0, "ds_groupnorm_silu: bad shape");
-  DS_REQUIRE(C % 8 == 0 && C % groups == 0, "ds_groupnorm_silu: C (%d) must be a multiple of 8 and of groups (%d)", C,
-             groups);
-  DS_REQUIRE(C <= 8192, "ds_groupnorm_silu: C (%d) > 8192 unsupported", C);
-  DS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(stats) & 7) == 0,
-             "ds_groupnorm_silu: x/y must be 16-byte and stats 8-byte aligned");
-  DeviceInfo dev;
-  if (!get_device(&dev)) return DS_ERR_CUDA;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int cv = C / 8;
-  // DS_GN_THREADS=512 (untested knob for the next tuning pass): half as many, twice as large CTAs -> half the
-  // per-(sample, group) fp64 atomics at the tail of the statistics kernel (21.7 us at 49 % DRAM throughput today)
-  static const int target_threads = [] {
-    const char* e = getenv("DS_GN_THREADS");
-    const int v = e ? atoi(e) : 256;
-    return v >= 64 && v <= 1024 ? v : 256;
-  }();
-  int rpb = target_threads / cv;
-  if (rpb < 1) rpb = 1;
-  const int threads = cv * rpb;
-  DS_REQUIRE(threads <= 1024, "ds_groupnorm_silu: C too large for one CTA row");
-  // items of 8 sweeps of the CTA's pixel rows; one resident wave of CTAs (occupancy queried once per kernel)
-  const int ipx = 8 * rpb;
-  const int items_per_sample = (HW + ipx - 1) / ipx;
-  const long long total_items_ll = static_cast<long long>(B) * items_per_sample;
-  DS_REQUIRE(total_items_ll < (1ll << 30), "ds_groupnorm_silu: tensor too large");
-  const int total_items = static_cast<int>(total_items_ll);
-  auto wave = [&](const void* fn, size_t smem) -> int {
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem) != cudaSuccess || occ < 1) {
-      (void)cudaGetLastError();
-      occ = 1;
-    }
-    const long long g = static_cast<long long>(occ) * dev.num_sms;
-    return static_cast<int>(g < total_items ? g : total_items);
-  };
-  static const int l2_hints = [] {  // DS_GN_L2HINT=0 disables the evict_last / evict_first policies (A/B timing)
-    const char* e = getenv("DS_GN_L2HINT");
-    return e ? atoi(e) : 1;
-  }();
+  DS_REQUIRE((reinterpret_cast<uintptr_t>(stats) & 15) == 0, "ds_groupnorm_silu: stats scratch must be 16-byte aligned");
+  // stand-alone form (no producer statistics): one statistics pass + the apply pass.  scratch = fp64 [B][C][2]
   double* dstats = reinterpret_cast<double*>(stats);
-  // ---- single-pass fused kernel when a sample's per-CTA slice fits a >= 2-deep shared-memory ring
-  // MEASURED (B200, (8,128,128,320), 167.8 MB algorithmic): two kernels 64.8 us; fused with fp64 global atomics
-  // 78.6 us; fused with the partials table (this version) 87.5 us — one 480-thread CTA per SM does not have the
-  // thread-level parallelism to run its statistics / reduce / normalise phases at HBM pace (each sample costs a CTA
-  // ~10 us of serial work against 3.2 us of HBM time).  Opt-in (DS_GN_FUSED=1) until it is restructured with
-  // warp-specialised producer / normalise roles; the two-kernel path stays the default.
-  static const int fused_env = [] {
-    const char* e = getenv("DS_GN_FUSED");
-    return e ? atoi(e) : 0;
-  }();
-  if (fused_env && groups <= 64 && cv <= 512 && 512 / cv * cv >= 2 * groups) {
-    const int fthreads = cv * (512 / cv);
-    const int grid = dev.num_sms;
-    const long long max_px = (static_cast<long long>(HW) + grid - 1) / grid + 1;
-    const long long slice_stride_ll = ((max_px * C * 2) + 127) / 128 * 128;
-    const int ring_budget = 215 * 1024;
-    int nbuf = static_cast<int>(ring_budget / slice_stride_ll);
-    if (nbuf > 4) nbuf = 4;
-    if (nbuf > B) nbuf = B;
-    if (nbuf >= 2 || (nbuf >= 1 && B == 1)) {
-      const int slice_stride = static_cast<int>(slice_stride_ll);
-      const size_t smem = 128 + 5760 + static_cast<size_t>(nbuf) * slice_stride;
-      const void* fn = apply_silu ? reinterpret_cast<const void*>(gn_fused_kernel<true>)
-                                  : reinterpret_cast<const void*>(gn_fused_kernel<false>);
-      static size_t attr_smem[kMaxDevices][2] = {};
-      if (smem > attr_smem[device_slot()][apply_silu ? 1 : 0]) {
-        DS_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_smem[device_slot()][apply_silu ? 1 : 0] = smem;
-      }
-      // scratch (ds_groupnorm_scratch_floats): [4*B*groups floats: fp64 sums of the two-kernel path] [2*B: arrival
-      // counters] [B][num_sms][2*groups] fp32 partials
-      unsigned int* d_arrived = reinterpret_cast<unsigned int*>(stats + static_cast<size_t>(4) * B * groups);
-      float* d_partials = stats + static_cast<size_t>(4) * B * groups + 2 * B;
-      DS_CUDA_OK(cudaMemsetAsync(d_arrived, 0, sizeof(unsigned int) * B, st));
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(grid);
-      cfg.blockDim = dim3(fthreads);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeCooperative;
-      attr[0].val.cooperative = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      const uint4* xp = static_cast<const uint4*>(x);
-      uint4* yp = static_cast<uint4*>(y);
-      if (apply_silu)
-        DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel<true>, xp, yp, d_partials, d_arrived, gamma, beta, B, HW, C,
-                                      groups, eps, nbuf, slice_stride));
-      else
-        DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_fused_kernel<false>, xp, yp, d_partials, d_arrived, gamma, beta, B, HW, C,
-                                      groups, eps, nbuf, slice_stride));
-      DS_LAUNCH_OK("gn_fused_kernel");
-      return DS_OK;
-    }
-  }
-  DS_CUDA_OK(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * B * groups, st));
-  const size_t sh = sizeof(double) * 2 * groups;
-  gn_stats_kernel<<<wave(reinterpret_cast<const void*>(gn_stats_kernel), sh), threads, sh, st>>>(
-      static_cast<const uint4*>(x), dstats, HW, C, groups, items_per_sample, ipx, total_items, l2_hints);
-  DS_LAUNCH_OK("gn_stats_kernel");
-  if (apply_silu)
-    gn_apply_kernel<true><<<wave(reinterpret_cast<const void*>(gn_apply_kernel<true>), 0), threads, 0, st>>>(
-        static_cast<const uint4*>(x), static_cast<uint4*>(y), dstats, gamma, beta, HW, C, groups, eps,
-        items_per_sample, ipx, total_items, l2_hints);
-  else
-    gn_apply_kernel<false><<<wave(reinterpret_cast<const void*>(gn_apply_kernel<false>), 0), threads, 0, st>>>(
-        static_cast<const uint4*>(x), static_cast<uint4*>(y), dstats, gamma, beta, HW, C, groups, eps,
-        items_per_sample, ipx, total_items, l2_hints);
-  DS_LAUNCH_OK("gn_apply_kernel");
-  return DS_OK;
+  DS_CUDA_OK(cudaMemsetAsync(dstats, 0, sizeof(double) * 2 * static_cast<size_t>(B) * C, static_cast<cudaStream_t>(stream)));
+  int rc = ds_channel_stats(x, dstats, B, HW, C, stream);
+  if (rc != DS_OK) return rc;
+  return ds_groupnorm_apply(x, dstats, C, nullptr, nullptr, 0, y, gamma, beta, B, HW, groups, eps, apply_silu, stream);
 }
 
-extern "C" int64_t ds_groupnorm_scratch_floats(int B, int groups) {
-  if (B <= 0 || groups <= 0) return 0;
-  int sms = 256;  // without a device: an upper bound for any sm_100 part
-  ds::DeviceInfo dev;
-  if (ds::get_device(&dev)) sms = dev.num_sms;
-  return static_cast<int64_t>(4) * B * groups + 2 * B + static_cast<int64_t>(B) * sms * 2 * groups;
+extern "C" int64_t ds_groupnorm_scratch_floats(int B, int C) {
+  if (B <= 0 || C <= 0) return 0;
+  return static_cast<int64_t>(4) * B * C;  // fp64 [B][C][2]
 }
 
 extern "C" int ds_layernorm(const void* x, void* y, const float* gamma, const float* beta, int rows, int C, float eps,

@@ -60,15 +60,68 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 # ---------------------------------------------------------------------------------------------- norms
-def groupnorm_scratch_floats(B: int, groups: int) -> int:
-    """Floats of scratch ds_groupnorm_silu needs for a [B, ..., C] tensor (include/dsengine.h)."""
-    return int(lib.ds_groupnorm_scratch_floats(int(B), int(groups)))
+def groupnorm_scratch_floats(B: int, C: int) -> int:
+    """Floats of scratch the stand-alone ds_groupnorm_silu needs for a [B, ..., C] tensor (fp64 [B][C][2])."""
+    return int(lib.ds_groupnorm_scratch_floats(int(B), int(C)))
+
+
+def channel_stats(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp64 [B, C, 2] {sum, sum of squares} per (sample, channel) of channels-last bf16 ``x`` [B, ..., C].
+    ``out`` is ACCUMULATED into (it must be zero); without it a zeroed buffer is allocated."""
+    _req(x, bf16, "channel_stats.x")
+    B, Cc = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * Cc)
+    if out is None:
+        out = torch.zeros(B, Cc, 2, dtype=torch.float64, device=x.device)
+    else:
+        _req(out, torch.float64, "channel_stats.out")
+        if out.numel() != 2 * B * Cc:
+            raise DsEngineError("channel_stats: out must hold B*C*2 doubles")
+    check(lib.ds_channel_stats(x.data_ptr(), out.data_ptr(), B, HW, Cc, _stream()), "ds_channel_stats")
+    return out
+
+
+def groupnorm_apply(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int,
+                    eps: float, silu: bool = True, x2: Optional[torch.Tensor] = None,
+                    stats2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) of [x | x2] (channel concatenation, never materialised) from per-channel statistics
+    (``channel_stats`` or the ``chan_stats`` a producing ``gemm`` / ``conv3x3`` filled): ONE pass over the data."""
+    _req(x, bf16, "groupnorm_apply.x")
+    B, C1 = x.shape[0], x.shape[-1]
+    HW = x.numel() // (B * C1)
+    _req(stats, torch.float64, "groupnorm_apply.stats")
+    C2 = 0
+    if x2 is not None:
+        _req(x2, bf16, "groupnorm_apply.x2")
+        C2 = x2.shape[-1]
+        if x2.shape[0] != B or x2.numel() // (B * C2) != HW or stats2 is None:
+            raise DsEngineError("groupnorm_apply: x2 must have the same batch / pixels as x, and needs stats2")
+        _req(stats2, torch.float64, "groupnorm_apply.stats2")
+        if stats2.numel() != 2 * B * C2:
+            raise DsEngineError("groupnorm_apply: stats2 must hold B*C2*2 doubles")
+    if stats.numel() != 2 * B * C1:
+        raise DsEngineError("groupnorm_apply: stats must hold B*C*2 doubles")
+    _req(gamma, f32, "groupnorm_apply.gamma", 1)
+    _req(beta, f32, "groupnorm_apply.beta", 1)
+    if gamma.numel() != C1 + C2 or beta.numel() != C1 + C2:
+        raise DsEngineError("groupnorm_apply: gamma/beta must have C1 + C2 elements")
+    if out is None:
+        out = torch.empty(tuple(x.shape[:-1]) + (C1 + C2,), dtype=bf16, device=x.device)
+    else:
+        _req(out, bf16, "groupnorm_apply.out")
+        if out.numel() != B * HW * (C1 + C2):
+            raise DsEngineError("groupnorm_apply: out has the wrong number of elements")
+    check(lib.ds_groupnorm_apply(x.data_ptr(), stats.data_ptr(), C1, _ptr(x2), _ptr(stats2), C2, out.data_ptr(),
+                                 gamma.data_ptr(), beta.data_ptr(), B, HW, groups, eps, int(silu), _stream()),
+          "ds_groupnorm_apply")
+    return out
 
 
 def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float,
                    silu: bool = True, out: Optional[torch.Tensor] = None,
                    stats: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """GroupNorm(+SiLU) on channels-last bf16 ``x`` of shape [B, ..., C] (everything between is 'pixels')."""
+    """Stand-alone GroupNorm(+SiLU) on channels-last bf16 ``x`` of shape [B, ..., C]: statistics pass + apply pass
+    (the engine's forward uses producer statistics + ``groupnorm_apply`` instead)."""
     _req(x, bf16, "groupnorm_silu.x")
     B, Cc = x.shape[0], x.shape[-1]
     HW = x.numel() // (B * Cc)
@@ -77,7 +130,7 @@ def groupnorm_silu(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, gro
     if gamma.numel() != Cc or beta.numel() != Cc:
         raise DsEngineError("groupnorm_silu: gamma/beta must have C elements")
     out = torch.empty_like(x) if out is None else _req(out, bf16, "groupnorm_silu.out")
-    need = groupnorm_scratch_floats(B, groups)
+    need = groupnorm_scratch_floats(B, Cc)
     if stats is None:
         stats = torch.empty(need, dtype=f32, device=x.device)
     elif stats.numel() < need:
@@ -151,7 +204,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          out: Optional[torch.Tensor] = None, out_fp32: bool = False, out_scale: float = 0.0,
          ln_stats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
          row_stats_out: Optional[torch.Tensor] = None, zero_rows: Optional[torch.Tensor] = None,
-         row_stats_zeroed: bool = False) -> torch.Tensor:
+         row_stats_zeroed: bool = False, a2: Optional[torch.Tensor] = None,
+         chan_stats: Optional[torch.Tensor] = None, stats_rows_per_sample: int = 0) -> torch.Tensor:
     """out[..., Nout] = epilogue(a[..., K] @ w[N, K]^T) on tcgen05; ``a`` may have any leading dims.
 
     LayerNorm fusion (include/dsengine.h): ``ln_stats`` [2*M] fp32 {sum, sumsq} per row of ``a`` + ``ln_colsum`` [N]
@@ -159,11 +213,22 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     [2*M] fp32 receives {sum, sumsq} of every (bf16-rounded) output row."""
     _req(a, bf16, "gemm.a")
     _req(w, bf16, "gemm.w", 2)
-    K = a.shape[-1]
-    M = a.numel() // K
+    K1 = a.shape[-1]
+    M = a.numel() // K1
+    K = K1
+    if a2 is not None:                       # [a | a2] along K, never concatenated in memory
+        _req(a2, bf16, "gemm.a2")
+        if a2.numel() // a2.shape[-1] != M:
+            raise DsEngineError("gemm: a2 must have the same rows as a")
+        K = K1 + a2.shape[-1]
     N = w.shape[0]
     if w.shape[1] != K:
         raise DsEngineError(f"gemm: a has K={K} but w is {tuple(w.shape)}")
+    if chan_stats is not None:
+        _req(chan_stats, torch.float64, "gemm.chan_stats")
+        if stats_rows_per_sample <= 0 or M % stats_rows_per_sample or \
+                chan_stats.numel() != 2 * (M // stats_rows_per_sample) * N:
+            raise DsEngineError("gemm: chan_stats must be fp64 [M / stats_rows_per_sample, N, 2]")
     n_out = N // 2 if epilogue == EPI_GEGLU else N
     if bias is not None:
         _req(bias, f32, "gemm.bias", 1)
@@ -202,19 +267,22 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
             raise DsEngineError("gemm: row_stats_out must hold 2*M floats and needs a bf16 output")
     ws = _splitk_ws()
     args = GemmArgs(a=a.data_ptr(), w=w.data_ptr(), out=out.data_ptr(), bias=_ptr(bias), rowbias=_ptr(rowbias),
-                    residual=_ptr(residual), M=M, N=N, K=K, lda=K, ldw=K, ldo=n_out, ldres=n_out,
+                    residual=_ptr(residual), M=M, N=N, K=K, lda=K1, ldw=K, ldo=n_out, ldres=n_out,
                     rows_per_batch=rows_per_batch, rowbias_ld=rowbias_ld, epilogue=epilogue, out_fp32=int(out_fp32),
                     out_scale=out_scale, ln_stats=_ptr(ln_stats), ln_colsum=_ptr(ln_colsum), ln_eps=float(ln_eps),
                     row_stats_out=_ptr(row_stats_out), zero_rows=_ptr(zero_rows),
                     row_stats_zeroed=int(bool(row_stats_zeroed)), splitk_ws=_ptr(ws),
-                    splitk_ws_bytes=0 if ws is None else ws.numel() * 4)
+                    splitk_ws_bytes=0 if ws is None else ws.numel() * 4,
+                    a2=_ptr(a2), K1=K1, lda2=0 if a2 is None else a2.shape[-1],
+                    chan_stats=_ptr(chan_stats), stats_rows_per_sample=int(stats_rows_per_sample))
     check(lib.ds_gemm_bf16(C.byref(args), _stream()), "ds_gemm_bf16")
     return out
 
 
 def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, stride: int = 1,
             rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-            out: Optional[torch.Tensor] = None, out_fp32: bool = False) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, out_fp32: bool = False,
+            chan_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """3x3 / pad 1 conv on NHWC bf16 ``x``; ``w`` is packed [Cout, 3, 3, Cin] bf16 (weights.pack_conv3x3)."""
     _req(x, bf16, "conv3x3.x", 4)
     B, H, W, Cin = x.shape
@@ -239,12 +307,16 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
         _req(residual, bf16, "conv3x3.residual")
         if residual.numel() != B * Ho * Wo * Cout:
             raise DsEngineError("conv3x3: residual must match the output shape")
+    if chan_stats is not None:
+        _req(chan_stats, torch.float64, "conv3x3.chan_stats")
+        if chan_stats.numel() != 2 * B * Cout:
+            raise DsEngineError("conv3x3: chan_stats must be fp64 [B, Cout, 2]")
     ws = _splitk_ws()
     args = Conv3x3Args(x=x.data_ptr(), w=w.data_ptr(), out=out.data_ptr(), bias=_ptr(bias), rowbias=_ptr(rowbias),
                        residual=_ptr(residual), B=B, H=H, W=W, Cin=Cin, Cout=Cout, stride=stride,
                        rowbias_ld=0 if rowbias is None else rowbias.stride(0),
                        out_fp32=int(out_fp32), out_scale=0.0, splitk_ws=_ptr(ws),
-                       splitk_ws_bytes=0 if ws is None else ws.numel() * 4)
+                       splitk_ws_bytes=0 if ws is None else ws.numel() * 4, chan_stats=_ptr(chan_stats))
     check(lib.ds_conv3x3_nhwc(C.byref(args), _stream()), "ds_conv3x3_nhwc")
     return out
 

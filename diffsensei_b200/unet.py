@@ -297,18 +297,45 @@ class UNetMangaEngine:
         return ops.gemm(ops.silu(emb), self.temb_w, self.temb_b, out_fp32=True)
 
     # ------------------------------------------------------------------------------------------ blocks
-    def _resnet(self, p: str, x: torch.Tensor, temb: torch.Tensor) -> torch.Tensor:
-        r, g = self.resnets[p], self.cfg.norm_num_groups
-        h = ops.groupnorm_silu(x, r.n1[0], r.n1[1], g, 1e-5, True)
-        h = ops.conv3x3(h, r.w1, r.b1, rowbias=temb[:, r.temb_off:r.temb_off + r.cout])
-        h = ops.groupnorm_silu(h, r.n2[0], r.n2[1], g, 1e-5, True, out=h)
-        sc = x if r.wsc is None else ops.gemm(x, r.wsc, r.bsc)
-        return ops.conv3x3(h, r.w2, r.b2, residual=sc)
+    # GroupNorm statistics travel WITH the activations: every conv / GEMM that produces an NHWC activation also
+    # accumulates its per-(sample, channel) {sum, sum of squares} in the epilogue (`chan_stats`), so each GroupNorm
+    # is a single read-x / write-y pass (ops.groupnorm_apply), and torch.cat([hidden, skip], 1) in front of the
+    # up-block resnets is never written: norm1 reads both tensors (their statistics side by side), the 1x1 shortcut
+    # reads them as two K ranges of one GEMM.  `st` = fp64 [B, C, 2] view into the per-forward pool, or None when the
+    # producer could not emit it (conv_in, token counts that are not a multiple of 128) -> ops.channel_stats.
+    class _Pool:
+        def __init__(self, B: int, cmax: int, device, slots: int = 64):
+            self.buf = torch.zeros(slots * B * cmax * 2, dtype=torch.float64, device=device)   # ONE memset per forward
+            self.off, self.B = 0, B
 
-    def _transformer(self, p: str, x: torch.Tensor, cond: Conditions) -> torch.Tensor:
+        def take(self, C: int) -> torch.Tensor:
+            n = self.B * C * 2
+            if self.off + n > self.buf.numel():
+                raise RuntimeError("UNetMangaEngine: statistics pool exhausted")
+            v = self.buf[self.off:self.off + n].view(self.B, C, 2)
+            self.off += n
+            return v
+
+    def _stats(self, x: torch.Tensor, st: Optional[torch.Tensor], pool) -> torch.Tensor:
+        return st if st is not None else ops.channel_stats(x, out=pool.take(x.shape[-1]))
+
+    def _resnet(self, p: str, x, x_st, temb, pool, skip=None, skip_st=None, want_stats: bool = True):
+        r, g = self.resnets[p], self.cfg.norm_num_groups
+        x_st = self._stats(x, x_st, pool)
+        if skip is not None:
+            skip_st = self._stats(skip, skip_st, pool)
+        h = ops.groupnorm_apply(x, x_st, r.n1[0], r.n1[1], g, 1e-5, True, x2=skip, stats2=skip_st)
+        st1 = pool.take(r.cout)
+        h = ops.conv3x3(h, r.w1, r.b1, rowbias=temb[:, r.temb_off:r.temb_off + r.cout], chan_stats=st1)
+        h = ops.groupnorm_apply(h, st1, r.n2[0], r.n2[1], g, 1e-5, True, out=h)
+        sc = x if r.wsc is None else ops.gemm(x, r.wsc, r.bsc, a2=skip)          # 1x1 shortcut on [x | skip]
+        st2 = pool.take(r.cout) if want_stats else None
+        return ops.conv3x3(h, r.w2, r.b2, residual=sc, chan_stats=st2), st2
+
+    def _transformer(self, p: str, x, x_st, cond: Conditions, pool, want_stats: bool = True):
         t, cfg = self.transformers[p], self.cfg
         B, H, W, Cc = x.shape
-        h = ops.groupnorm_silu(x, t.norm[0], t.norm[1], cfg.norm_num_groups, 1e-6, False)
+        h = ops.groupnorm_apply(x, self._stats(x, x_st, pool), t.norm[0], t.norm[1], cfg.norm_num_groups, 1e-6, False)
         M = B * H * W
         # Row statistics {sum, sum of squares} of the residual stream h: the GEMM that writes h publishes them
         # (producer k -> buffer k % 3), the next LayerNorm-folded GEMM consumes them and clears buffer (k + 2) % 3 for
@@ -339,7 +366,12 @@ class UNetMangaEngine:
             h = produce(a, blk.wo2, blk.bo2, residual=h, out=h)
             f = consume(h, blk.wff1, blk.bff1, blk.cs_ff1, epilogue=ops.EPI_GEGLU)
             h = produce(f, blk.wff2, blk.bff2, residual=h, out=h)
-        return ops.gemm(h, t.w_out, t.b_out, residual=x.view(B, H * W, Cc)).view(B, H, W, Cc)
+        # proj_out (+ the block's residual) writes an NHWC activation again: publish its channel statistics when a
+        # 128-row tile cannot straddle two samples
+        ost = pool.take(Cc) if (want_stats and (H * W) % 128 == 0) else None
+        out = ops.gemm(h, t.w_out, t.b_out, residual=x.view(B, H * W, Cc), chan_stats=ost,
+                       stats_rows_per_sample=H * W if ost is not None else 0)
+        return out.view(B, H, W, Cc), ost
 
     # ------------------------------------------------------------------------------------------ forward
     def forward_nhwc(self, x: torch.Tensor, temb: torch.Tensor, cond: Conditions,
@@ -352,37 +384,51 @@ class UNetMangaEngine:
         nlev = len(ch)
         B, H, W, _ = x.shape
         need_size = (H % (2 ** (nlev - 1)) != 0) or (W % (2 ** (nlev - 1)) != 0)       # unet.py:152-162
+        pool = self._Pool(B, max(ch), x.device)
         h = ops.conv_in(x, self.conv_in_w, self.conv_in_b)
         if dialog_bbox is not None:
             ops.dialog_embed_add_(h, self.dialog_emb, dialog_bbox, round_bf16)        # unet.py:208-210
-        skips = [h]
+        st = None                                                                     # no tensor-core producer
+        skips = [(h, st)]
         for i in range(nlev):
             for j in range(cfg.layers_per_block):
-                h = self._resnet(f"down_blocks.{i}.resnets.{j}", h, temb)
+                if st is None:                      # resolve once: the same statistics serve the skip connection
+                    st = self._stats(h, None, pool)
+                    skips[-1] = (h, st)
+                h, st = self._resnet(f"down_blocks.{i}.resnets.{j}", h, st, temb, pool)
                 if depth[i] > 0:
-                    h = self._transformer(f"down_blocks.{i}.attentions.{j}", h, cond)
-                skips.append(h)
+                    h, st = self._transformer(f"down_blocks.{i}.attentions.{j}", h, st, cond, pool)
+                skips.append((h, st))
             if i < nlev - 1:
                 w, b = self.down_convs[i]
-                h = ops.conv3x3(h, w, b, stride=2)
-                skips.append(h)
-        h = self._resnet("mid_block.resnets.0", h, temb)
-        h = self._transformer("mid_block.attentions.0", h, cond)
-        h = self._resnet("mid_block.resnets.1", h, temb)
+                st = pool.take(ch[i])
+                h = ops.conv3x3(h, w, b, stride=2, chan_stats=st)
+                skips.append((h, st))
+        h, st = self._resnet("mid_block.resnets.0", h, st, temb, pool)
+        h, st = self._transformer("mid_block.attentions.0", h, st, cond, pool)
+        h, st = self._resnet("mid_block.resnets.1", h, st, temb, pool)
         rdepth = list(reversed(depth))
+        rch = list(reversed(ch))
         for i in range(nlev):
-            for j in range(cfg.layers_per_block + 1):
-                h = self._resnet(f"up_blocks.{i}.resnets.{j}", ops.concat_channels(h, skips.pop()), temb)
-                if rdepth[i] > 0:
-                    h = self._transformer(f"up_blocks.{i}.attentions.{j}", h, cond)
+            nres = cfg.layers_per_block + 1
+            for j in range(nres):
+                sk, sk_st = skips.pop()
+                feeds_gn = not (j == nres - 1 and i < nlev - 1)       # the block's last output only feeds the upsampler
+                has_attn = rdepth[i] > 0
+                h, st = self._resnet(f"up_blocks.{i}.resnets.{j}", h, st, temb, pool, skip=sk, skip_st=sk_st,
+                                     want_stats=feeds_gn or has_attn)
+                if has_attn:
+                    h, st = self._transformer(f"up_blocks.{i}.attentions.{j}", h, st, cond, pool, want_stats=feeds_gn)
             if i < nlev - 1:
                 if need_size:
-                    Ho, Wo = skips[-1].shape[1:3]                                     # unet.py:312-313
+                    Ho, Wo = skips[-1][0].shape[1:3]                                  # unet.py:312-313
                 else:
                     Ho, Wo = 2 * h.shape[1], 2 * h.shape[2]
                 w, b = self.up_convs[i]
-                h = ops.conv3x3(ops.upsample_nearest(h, Ho, Wo), w, b)
-        h = ops.groupnorm_silu(h, self.norm_out[0], self.norm_out[1], cfg.norm_num_groups, 1e-5, True, out=h)
+                st = pool.take(rch[i])
+                h = ops.conv3x3(ops.upsample_nearest(h, Ho, Wo), w, b, chan_stats=st)
+        h = ops.groupnorm_apply(h, self._stats(h, st, pool), self.norm_out[0], self.norm_out[1], cfg.norm_num_groups,
+                                1e-5, True, out=h)
         return ops.conv3x3(h, self.conv_out_w, self.conv_out_b, out=out)
 
     def _conditions_for(self, ehs: torch.Tensor, bbox: torch.Tensor, aspect_ratio: float) -> Conditions:

@@ -39,19 +39,27 @@ uint64_t ds_launch_count(void);
  * GroupNorm (+ optional SiLU), NHWC bf16.                     [HBM-bound]
  * Replaces diffusers ResnetBlock2D.norm1/norm2 + nonlinearity (GroupNorm(32, eps=1e-5) -> SiLU),
  * Transformer2DModel.norm (eps=1e-6, no SiLU) and conv_norm_out+conv_act reached from
- * src/models/unet.py:251-261,281-290,316-338.
- *   x, y      : [B][HW][C] bf16 (y may alias x)
- *   gamma/beta: [C] fp32
- *   stats     : scratch of ds_groupnorm_scratch_floats(B, groups) floats, 8-byte aligned; zeroed, written and read
- *               by the call itself.  Layout: 2*B*groups doubles (per-(sample, group) sum / sum of squares of the
- *               two-kernel path) | 2*B arrival counters | [B][num_SMs][2*groups] fp32 per-CTA partial statistics.
- * Per-thread partial sums are fp32, cross-CTA accumulation is fp64; normalisation + affine + SiLU run in fp32 with
- * one rounding to bf16.  Default: a statistics kernel (x marked evict_last in L2) followed by an apply kernel.
- * DS_GN_FUSED=1 selects an experimental single cooperative kernel that keeps every sample's per-SM pixel slice in a
- * shared-memory ring and reads x once (per-CTA partials go through the table in the scratch, one arrival counter
- * per sample; deterministic).  Measured slower so far (87 us vs 65 us at (8,128,128,320)), hence opt-in.
+ * src/models/unet.py:251-261,281-290,316-338 — and the torch.cat([hidden, skip], 1) in front of every up-block
+ * ResnetBlock2D (:316-332), which is never materialised.
+ *
+ * Statistics are per (sample, CHANNEL): fp64 [B][C][2] {sum, sum of squares} of the bf16 tensor.  They normally
+ * come from the epilogue of the ds_gemm_bf16 / ds_conv3x3_nhwc call that produced the tensor (`chan_stats`), so the
+ * GroupNorm itself is ONE pass: read x, write y (the algorithmic 4 B/element).  Per-channel sums compose: the
+ * statistics of a channel concatenation are the two tensors' statistics side by side.
+ *   ds_channel_stats   : statistics of a tensor that has no such producer; ACCUMULATES into `stats` (caller zeroes).
+ *   ds_groupnorm_apply : y[B][HW][C1+C2] = act(GroupNorm([x1 | x2])) from stats1 [B][C1][2] / stats2 [B][C2][2];
+ *                        x2 / stats2 NULL and C2 = 0 for a single source.  The channel sums are folded into the
+ *                        `groups` group statistics in shared memory in a fixed order; normalisation, affine and SiLU
+ *                        in fp32, one rounding to bf16.  y must not alias x1 / x2 when C2 > 0.
+ *   ds_groupnorm_silu  : stand-alone form = zero scratch + ds_channel_stats + ds_groupnorm_apply (two passes over x).
+ *                        `stats`: scratch of ds_groupnorm_scratch_floats(B, C) floats, 16-byte aligned.
+ * All pointers 16-byte aligned; C, C1, C2 multiples of 8; (C1 + C2) % groups == 0; groups <= 64.
  * --------------------------------------------------------------------------------------------- */
-int64_t ds_groupnorm_scratch_floats(int B, int groups);
+int ds_channel_stats(const void* x, double* stats, int B, int HW, int C, void* stream);
+int ds_groupnorm_apply(const void* x1, const double* stats1, int C1, const void* x2, const double* stats2, int C2,
+                       void* y, const float* gamma, const float* beta, int B, int HW, int groups, float eps,
+                       int apply_silu, void* stream);
+int64_t ds_groupnorm_scratch_floats(int B, int C);
 int ds_groupnorm_silu(const void* x, void* y, const float* gamma, const float* beta, float* stats, int B, int HW,
                       int C, int groups, float eps, int apply_silu, void* stream);
 
@@ -112,6 +120,11 @@ int ds_ip_mask(const float* bbox, float* mask, int B, int N, double aspect_ratio
  *   finished by whichever slice arrives last.  The caller provides a 16-byte aligned workspace that is ALL ZERO on
  *   entry (ds_gemm_splitk_ws_bytes() bytes cover every shape; the kernel leaves it all zero again) and must not be
  *   shared by GEMMs running concurrently on different streams.  NULL simply disables the feature.
+ * Tail launch (default on, DS_GEMM_TAIL=0 disables): when the last round of the persistent schedule would fill
+ *   less than ~45 % of the CTA pairs, the call covers the M range with TWO launches of the same kernel — 256-wide
+ *   tiles for the m-rows of the full rounds, 128-wide tiles (twice as many, half as long) for the remaining m-rows —
+ *   instead of paying a whole round for a handful of tiles.  Results are bit-identical to one launch (same K order
+ *   per output element).
  * Constraints: K % 8 == 0, lda % 8 == 0 (16-byte TMA strides). M, N, K tails are handled by TMA
  * zero-fill and masked stores.
  * --------------------------------------------------------------------------------------------- */
@@ -142,6 +155,17 @@ typedef struct {
   int32_t row_stats_zeroed; /* 1: row_stats_out is already 0, skip the memset  */
   void* splitk_ws;        /* split-K workspace (see below) or NULL             */
   int64_t splitk_ws_bytes;
+  /* second A operand (optional): the GEMM reads [a | a2] along K without the concatenation ever being written —
+   * the 1x1 shortcut of an up-block ResnetBlock2D on torch.cat([hidden, skip], 1) (src/models/unet.py:316-332).
+   * a2: bf16 [M][lda2], its K2 = K - K1 columns follow a's K1 columns; K1 % 64 == 0.  NULL: off (K1 ignored). */
+  const void* a2;
+  int32_t K1, lda2;
+  /* producer-side GroupNorm statistics (optional): fp64 [M/stats_rows_per_sample][N][2] (sum, sum of squares) per
+   * (sample, output channel) of the bf16-rounded outputs, ACCUMULATED with atomics (the caller zeroes it) — read by
+   * ds_groupnorm_apply, so the GroupNorm that follows needs no statistics pass over the tensor.  Needs the bf16
+   * TMA epilogue (16-byte rows), no GEGLU, stats_rows_per_sample % 128 == 0.  NULL: off. */
+  double* chan_stats;
+  int32_t stats_rows_per_sample;
 } ds_gemm_args;
 
 int ds_gemm_bf16(const ds_gemm_args* args, void* stream);
@@ -174,6 +198,7 @@ typedef struct {
   float out_scale;
   void* splitk_ws;    /* as in ds_gemm_args */
   int64_t splitk_ws_bytes;
+  double* chan_stats; /* fp64 [B][Cout][2] producer-side GroupNorm statistics, as in ds_gemm_args; NULL: off */
 } ds_conv3x3_args;
 
 int ds_conv3x3_nhwc(const ds_conv3x3_args* args, void* stream);

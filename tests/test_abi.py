@@ -64,8 +64,8 @@ def test_scratch_size_queries_work_without_a_gpu():
     """ds_groupnorm_scratch_floats / ds_gemm_splitk_ws_bytes are pure host arithmetic (they fall back to an upper
     bound on the SM count when no device is present), so callers can size buffers before touching CUDA."""
     from diffsensei_b200 import _lib
-    n = _lib.lib.ds_groupnorm_scratch_floats(8, 32)
-    assert n >= 4 * 8 * 32 + 2 * 8 + 8 * 100 * 64            # sums + counters + partials for >= 100 SMs
+    n = _lib.lib.ds_groupnorm_scratch_floats(8, 320)
+    assert n == 4 * 8 * 320                                   # fp64 [B][C][2] channel sums
     assert _lib.lib.ds_groupnorm_scratch_floats(0, 32) == 0
     b = _lib.lib.ds_gemm_splitk_ws_bytes()
     assert b >= 1024 + 64 * 256 * 256 * 4 and b % 16 == 0    # counter header + >= 64 fp32 tiles of 256 x 256
@@ -76,3 +76,5 @@ def test_new_gemm_fields_default_to_off():
     a = _lib.GemmArgs()
     assert not a.ln_stats and not a.ln_colsum and not a.row_stats_out and not a.zero_rows and not a.splitk_ws
     assert a.row_stats_zeroed == 0 and a.splitk_ws_bytes == 0
+    assert not a.a2 and not a.chan_stats and a.K1 == 0 and a.stats_rows_per_sample == 0
+    assert not _lib.Conv3x3Args().chan_stats

@@ -303,3 +303,106 @@ def test_full_size_properties_cfg2(ops):
     w = pack_conv3x3(torch.randn(640, 640, 3, 3, device=DEV) * (9 * 640) ** -0.5)
     y1, y2 = ops.conv3x3(xc, w, out_fp32=True), ops.conv3x3(xc * 2, w, out_fp32=True)
     assert rel_l2(y2, 2 * y1) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- round-2 kernels
+def _chan_stats_ref(t):          # t: [B, ..., C] -> fp64 [B, C, 2]
+    B, C = t.shape[0], t.shape[-1]
+    v = t.double().reshape(B, -1, C)
+    return torch.stack([v.sum(1), (v * v).sum(1)], dim=-1)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 24, 64), (3, 7, 9, 320), (1, 64, 64, 1280), (2, 33, 17, 2560)])
+def test_channel_stats(ops, B, H, W, C):
+    x = _r(B, H, W, C, seed=5) * 1.5 + 0.25
+    got = ops.channel_stats(x.to(DEV)).cpu()
+    want = _chan_stats_ref(x)
+    assert got.shape == (B, C, 2)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-3)       # fp32 partials over <= a few hundred pixels
+    again = ops.channel_stats(x.to(DEV)).cpu()
+    assert torch.equal(again, got)                               # fixed-order partials + exact fp64 sums
+
+
+@pytest.mark.parametrize("B,H,W,C1,C2,silu,eps", [(2, 16, 24, 64, 0, True, 1e-5), (2, 9, 7, 640, 320, True, 1e-5),
+                                                 (1, 32, 32, 1280, 640, True, 1e-5), (2, 8, 8, 1280, 1280, True, 1e-5),
+                                                 (3, 5, 3, 320, 0, False, 1e-6), (2, 64, 64, 320, 320, True, 1e-5)])
+def test_groupnorm_apply_two_sources(ops, B, H, W, C1, C2, silu, eps):
+    """GroupNorm(+SiLU) of torch.cat([x1, x2], channel) from per-channel statistics, without the concatenation:
+    group boundaries of the result (e.g. 60 channels per group at 1280 + 640) straddle the two tensors."""
+    x1 = _r(B, H, W, C1, seed=1) * 1.7 + 0.3
+    x2 = (_r(B, H, W, C2, seed=2) * 0.6 - 0.2) if C2 else None
+    C = C1 + C2
+    gamma, beta = torch.randn(C) * 0.2 + 1, torch.randn(C) * 0.1
+    xc = x1 if x2 is None else torch.cat([x1, x2], dim=-1)
+    want = F.group_norm(xc.float().permute(0, 3, 1, 2), 32, gamma, beta, eps)
+    want = (F.silu(want) if silu else want).permute(0, 2, 3, 1)
+    s1 = ops.channel_stats(x1.to(DEV))
+    s2 = ops.channel_stats(x2.to(DEV)) if C2 else None
+    got = ops.groupnorm_apply(x1.to(DEV), s1, gamma.to(DEV), beta.to(DEV), 32, eps, silu,
+                              x2=None if x2 is None else x2.to(DEV), stats2=s2)
+    assert got.shape == (B, H, W, C) and rel_l2(got.float(), want) < 6e-3
+
+
+@pytest.mark.parametrize("M,N,K1,K2", [(512, 320, 640, 320), (1024, 640, 1280, 640), (300, 1280, 2560 - 1280, 1280)])
+def test_gemm_two_operand_k_concat(ops, M, N, K1, K2):
+    """The 1x1 shortcut of an up-block resnet on torch.cat([hidden, skip], 1): [a | a2] along K from two tensors."""
+    a, a2 = _r(M, K1, seed=3), _r(M, K2, seed=4)
+    w = _r(N, K1 + K2, seed=5, scale=(K1 + K2) ** -0.5)
+    bias = torch.randn(N) * 0.1
+    want = F.linear(torch.cat([a, a2], 1).float(), w.float(), bias)
+    got = ops.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), a2=a2.to(DEV))
+    ref = ops.gemm(torch.cat([a, a2], 1).to(DEV), w.to(DEV), bias.to(DEV))
+    assert rel_l2(got.float(), want) < 6e-3 and torch.equal(got, ref)      # same K order -> bit-identical
+
+
+@pytest.mark.parametrize("B,HW,N,K,res", [(2, 1024, 1280, 256, True), (3, 128, 320, 128, False), (8, 1024, 1280, 64, True),
+                                          (2, 256, 640, 192, True)])
+def test_gemm_producer_channel_stats(ops, B, HW, N, K, res):
+    """chan_stats from the GEMM epilogue == statistics of the bf16 output it wrote (incl. the tail-launch split at
+    M = 8192, N = 1280 where the last m-rows run as BN = 128 tiles)."""
+    a = _r(B * HW, K, seed=6)
+    w = _r(N, K, seed=7, scale=K ** -0.5)
+    bias = torch.randn(N) * 0.1
+    r = _r(B * HW, N, seed=8) if res else None
+    st = torch.zeros(B, N, 2, dtype=torch.float64, device=DEV)
+    out = ops.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), residual=None if r is None else r.to(DEV), chan_stats=st,
+                   stats_rows_per_sample=HW)
+    want = F.linear(a.float(), w.float(), bias) + (0 if r is None else r.float())
+    assert rel_l2(out.float(), want) < 6e-3
+    ref = _chan_stats_ref(out.cpu().view(B, HW, N))
+    assert torch.allclose(st.cpu(), ref, rtol=1e-5, atol=1e-3)
+    plain = ops.gemm(a.to(DEV), w.to(DEV), bias.to(DEV), residual=None if r is None else r.to(DEV))
+    assert torch.equal(plain, out)                                # the statistics epilogue does not change the output
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 16, 16, 64, 64, 1), (2, 18, 27, 128, 320, 1), (1, 33, 20, 64, 128, 2),
+                                                  (8, 32, 32, 128, 1280, 1)])
+def test_conv_producer_channel_stats(ops, B, H, W, Cin, Cout, stride):
+    """chan_stats from the conv epilogue on ragged maps: pixels of partial 8x16 patches must not be counted."""
+    x = _r(B, H, W, Cin, seed=9)
+    w = _r(Cout, Cin, 3, 3, seed=10, scale=(9 * Cin) ** -0.5)
+    bias = torch.randn(Cout) * 0.1
+    from diffsensei_b200.weights import pack_conv3x3
+    st = torch.zeros(B, Cout, 2, dtype=torch.float64, device=DEV)
+    out = ops.conv3x3(x.to(DEV), pack_conv3x3(w.float()).to(DEV), bias.to(DEV), stride=stride, chan_stats=st)
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, stride=stride, padding=1).permute(0, 2, 3, 1)
+    assert rel_l2(out.float(), want) < 6e-3
+    assert torch.allclose(st.cpu(), _chan_stats_ref(out.cpu()), rtol=1e-5, atol=1e-3)
+
+
+def test_gemm_tail_launch_is_bit_identical_to_wide_tiles(ops):
+    """M 8192 x N 1280 is 160 wide tiles on 74 CTA pairs: the call runs the last m-rows as BN=128 tiles in a second
+    launch (ds_gemm_bf16 'tail launch').  Every output element accumulates the same k-blocks in the same order, so
+    those rows must equal the same rows computed on their own (15 wide tiles, no split)."""
+    M, N, K = 8192, 1280, 640
+    a = _r(M, K, seed=11).to(DEV)
+    w = _r(N, K, seed=12, scale=K ** -0.5).to(DEV)
+    bias = (torch.randn(N) * 0.1).to(DEV)
+    r = _r(M, N, seed=13).to(DEV)
+    full = ops.gemm(a, w, bias, residual=r)
+    want = F.linear(a.float(), w.float(), bias) + r.float()
+    assert rel_l2(full.float(), want) < 6e-3
+    tail = ops.gemm(a[M - 768:].contiguous(), w, bias, residual=r[M - 768:].contiguous())
+    assert torch.equal(full[M - 768:], tail)
+    head = ops.gemm(a[:2048].contiguous(), w, bias, residual=r[:2048].contiguous())
+    assert torch.equal(full[:2048], head)

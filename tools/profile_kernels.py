@@ -2,7 +2,7 @@
 """The kernels behind bench.py's roofline objects, one launch each after a warm-up, for `ncu --set full`:
   ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/kernels \
       python tools/profile_kernels.py
-Launch order inside the profiled range: gn_stats, gn_apply, gemm<256> FF1/GEGLU, gemm<128> (N=640 out-proj with
+Launch order inside the profiled range: chan_stats, gn_apply2 (two-pass form), gn_apply2 (in-step form), gemm<256> FF1/GEGLU, gemm<128> (N=640 out-proj with
 residual), gemm M8192 N1280 K1280 + residual, conv3x3 (8,64,64,640->640), flash_attn (B8 N4096 h10), cross_ip_attn (B8 N4096 h10), layernorm."""
 import os
 import sys
@@ -18,7 +18,7 @@ dev = torch.device("cuda:0")
 bf = torch.bfloat16
 r = lambda *s: torch.randn(*s, device=dev).to(bf)
 x = r(8, 128, 128, 320)
-ga, be, st = torch.ones(320, device=dev), torch.zeros(320, device=dev), torch.empty(ops.groupnorm_scratch_floats(8, 32), device=dev)
+ga, be, st = torch.ones(320, device=dev), torch.zeros(320, device=dev), torch.empty(ops.groupnorm_scratch_floats(8, 320), device=dev)
 a1, w1, b1 = r(8192, 1280), r(10240, 1280) * 0.03, torch.zeros(10240, device=dev)
 a2, w2, b2, res2 = r(32768, 640), r(640, 640) * 0.04, torch.zeros(640, device=dev), r(32768, 640)
 a3, w3, b3, res3 = r(8192, 1280), r(1280, 1280) * 0.03, torch.zeros(1280, device=dev), r(8192, 1280)
@@ -30,12 +30,18 @@ bbox = torch.tensor([[[0.0] * 4] * 4] * 4 + [[[.05, .10, .50, .95], [.50, .15, .
 ln_g, ln_b = torch.ones(640, device=dev), torch.zeros(640, device=dev)
 
 
+cst = ops.channel_stats(x)
+cst_conv = torch.zeros(8, 640, 2, dtype=torch.float64, device=dev)
+
+
 def run():
-    ops.groupnorm_silu(x, ga, be, 32, 1e-5, True, stats=st)
+    ops.groupnorm_silu(x, ga, be, 32, 1e-5, True, stats=st)           # chan_stats_kernel + gn_apply2_kernel
+    ops.groupnorm_apply(x, cst, ga, be, 32, 1e-5, True)               # the in-step form: apply only
     ops.gemm(a1, w1, b1, epilogue=ops.EPI_GEGLU)
     ops.gemm(a2, w2, b2, residual=res2)
     ops.gemm(a3, w3, b3, residual=res3)
     ops.conv3x3(xc, wc, bc, rowbias=temb, residual=xc)
+    ops.conv3x3(xc, wc, bc, rowbias=temb, residual=xc, chan_stats=cst_conv)   # with the statistics epilogue
     ops.attention_self(qkv, 10)
     ops.attention_cross_ip(q, kvt, kvi, bbox, 10, 1.0, 0.6, 16, 16)
     ops.layernorm(a2, ln_g, ln_b)

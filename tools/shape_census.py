@@ -30,6 +30,8 @@ def attention_cross_ip(q, *a, out=None, **k):
     B, N, C = q.shape; rec("attn_cross", (B, N, C), 4.0 * N * 157 * C * B); return E(B, N, C)
 ops.gemm, ops.conv3x3, ops.attention_self, ops.attention_cross_ip = gemm, conv3x3, attention_self, attention_cross_ip
 ops.groupnorm_silu = lambda x, g, b, G, eps, silu=True, out=None, stats=None: same(x)
+ops.groupnorm_apply = lambda x, st, g, b, G, eps, silu=True, x2=None, stats2=None, out=None: same(x) if x2 is None else E(*x.shape[:-1], x.shape[-1] + x2.shape[-1])
+ops.channel_stats = lambda x, out=None: None
 ops.layernorm = lambda x, g, b, eps=1e-5, out=None: same(x)
 ops.conv_in = lambda x, w, b, out=None: E(*x.shape[:3], w.shape[0])
 ops.concat_channels = lambda a, b, out=None: E(*a.shape[:-1], a.shape[-1] + b.shape[-1])
