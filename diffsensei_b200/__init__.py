@@ -4,6 +4,7 @@ Public surface (mirrors the reference's):
     UNetMangaEngine        <- src/models/unet.py            UNetMangaModel
     AttnProcessor2_0, MaskedIPAttnProcessor2_0  <- src/models/attention_processor.py
     ResamplerEngine        <- src/models/resampler.py       Resampler
+    VaeDecoderEngine       <- diffusers AutoencoderKL.decode as used by pipeline_diffsensei.py:339-363
     DiffSenseiPipeline     <- src/pipelines/pipeline_diffsensei.py  (denoise loop)
     ops                    -- tensor-level wrappers over the C ABI in include/dsengine.h
 
@@ -13,10 +14,12 @@ missing, and nothing in here falls back to PyTorch compute or to the test oracle
 from . import _lib  # noqa: F401  (loads libdsengine.so or raises ImportError)
 from . import ops  # noqa: F401
 from .attention_processor import AttnProcessor2_0, MaskedIPAttnProcessor2_0  # noqa: F401
-from .config import RESAMPLER, RESAMPLER_TINY, SDXL_MANGA, TINY, ResamplerConfig, UNetConfig  # noqa: F401
+from .config import (RESAMPLER, RESAMPLER_TINY, SDXL_MANGA, SDXL_VAE, TINY, TINY_VAE, ResamplerConfig, UNetConfig,  # noqa: F401
+                     VaeConfig)
 from .pipeline import DiffSenseiPipeline  # noqa: F401
 from .resampler import ResamplerEngine  # noqa: F401
 from .scheduler import DDIMScheduler  # noqa: F401
 from .unet import UNet2DConditionOutput, UNetMangaEngine  # noqa: F401
+from .vae import VaeDecoderEngine  # noqa: F401
 
 __version__ = "0.1.0"

@@ -74,6 +74,9 @@ SIGNATURES = {
     "ds_timestep_embedding": [_vp, _vp, _i, _i, _vp],
     "ds_cfg_ddim_step": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp],
     "ds_resampler_attn": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "ds_latent_pointwise": [_vp, _vp, _vp, _vp, _f, _i, _i, _vp],
+    "ds_softmax_rows": [_vp, _vp, _i, _i, _i64, _i64, _f, _vp],
+    "ds_image_postprocess": [_vp, _vp, _i, _i, _i, _vp],
 }
 OTHER_EXPORTS = ("ds_version", "ds_last_error", "ds_launch_count", "ds_groupnorm_scratch_floats",
                  "ds_gemm_splitk_ws_bytes")

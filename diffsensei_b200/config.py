@@ -69,3 +69,20 @@ class ResamplerConfig:
 RESAMPLER = ResamplerConfig()
 RESAMPLER_TINY = ResamplerConfig(dim=128, depth=2, heads=2, num_queries=16, num_dummy_tokens=16, embedding_dim=64,
                                  magi_embedding_dim=32, output_dim=128)
+
+
+@dataclass(frozen=True)
+class VaeConfig:
+    """AutoencoderKL (sdxl-vae ``config.json``) — the decoder half the pipeline uses after the denoise loop
+    (src/pipelines/pipeline_diffsensei.py:339-363)."""
+    latent_channels: int = 4
+    out_channels: int = 3
+    block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)
+    layers_per_block: int = 2
+    norm_num_groups: int = 32
+    scaling_factor: float = 0.13025
+    force_upcast: bool = True
+
+
+SDXL_VAE = VaeConfig()
+TINY_VAE = VaeConfig(block_out_channels=(64, 64, 128, 128))

@@ -42,6 +42,7 @@ constexpr int kGemmThreads = 384;  // 4 control warps + 8 epilogue warps
 constexpr int kABytes = kBM * kBK * 2;  // 16 KiB per stage
 constexpr int kConvTileH = 8;
 constexpr int kConvTileW = 16;
+constexpr int kNarrowBN = 128;  // width of the narrow units of the mixed-width schedule (any BN > 128 instantiation)
 
 struct GemmParams {
   const float* bias;
@@ -55,11 +56,12 @@ struct GemmParams {
   int tma_epilogue;  // 1: stage bf16 output tiles in smem and TMA-store them (residual tiles TMA-loaded)
   float out_scale;
   // LayerNorm fusion: consumer side (A rows are un-normalised; W/bias pre-folded) and producer side (row sums out)
-  const float* ln_stats;   // [M][2] {sum, sum of squares} of A's rows, or NULL
+  const double* ln_stats;  // [M][2] {sum, sum of squares} of A's rows (fp64), or NULL
   const float* ln_colsum;  // [N] sum_k W'[n][k]
   float ln_eps, ln_inv_k;
-  float* row_stats_out;    // [M][2], accumulated with atomics (zeroed by the host wrapper), or NULL
-  float* zero_rows;        // [M][2] buffer whose rows this launch resets to 0 (the statistics buffer two hops ahead)
+  double* row_stats_out;   // [M][2] fp64, accumulated with atomics (zeroed by the host wrapper), or NULL.  fp64 sums of
+                           // the <= 2 * n-tiles fp32 partials of a row are exact: the result is order-independent
+  double* zero_rows;       // [M][2] buffer whose rows this launch resets to 0 (the statistics buffer two hops ahead)
   int num_m_tiles, num_n_tiles, num_k_iters;
   // split-K tail: work items [0, tail_start) are whole 128*PAIR x BN units.  Each of the remaining `left` units (the
   // partial last wave of the persistent schedule) is cut along K into tail_parts slices that run on different CTA
@@ -68,10 +70,14 @@ struct GemmParams {
   // the tile and the counter behind it.  tail_parts = 1: off.
   int tail_start, tail_parts, total_items;
   float* ws;  // [256 uint32 counters][left][PAIR * 128][BN] fp32, all zero between launches
-  // first M tile (in units of 128*PAIR rows) of this launch: ds_gemm_bf16 / ds_conv3x3_nhwc may cover the M range
-  // with TWO launches — wide BN=256 tiles for the full waves of the persistent schedule and BN=128 tiles for the
-  // m-rows of the under-filled last wave (see run_gemm)
-  int m_pair0;
+  // Mixed-width schedule (BN = 256 instantiations only; see run_gemm): units [0, wide_units) are 256-column tiles
+  // over the m-pairs [0, wide_m_pairs); the remaining units are HALF-width (128-column) tiles over the last m-pairs,
+  // nt_narrow of them per m-pair — the m-rows of the under-filled last round of the persistent schedule are cut
+  // into twice as many, half as long units instead of costing a whole round.  Off: wide_units >= all units.
+  int wide_units, wide_m_pairs, nt_narrow;
+  // last_narrow: the LAST n-tile of every m-pair is a 128-column unit instead of a (mostly padding) BN-wide one —
+  // N = 640 runs as 256 | 256 | 128 and N = 320 as 192 | 128: no MMA work (or power) is spent on zero columns
+  int last_narrow;
   // second A operand: k-blocks [k1_iters, num_k_iters) of a plain GEMM come from tmA2 (the channel concatenation
   // [a | a2] along K is never materialised); k1_iters == num_k_iters: off
   int k1_iters;
@@ -106,7 +112,8 @@ template <int BN, int PAIR, bool STATS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                  const __grid_constant__ CUtensorMap tmA2, const GemmParams p) {
+                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                  const GemmParams p) {
   using Cfg = GemmCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::kStages;
   const uint32_t cta_rank = (PAIR == 2) ? cluster_ctarank() : 0u;  // rank inside the CTA pair; 0 = leader
@@ -140,6 +147,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (p.residual) tma_prefetch_desc(&tmR);
     }
     if (p.k1_iters < p.num_k_iters) tma_prefetch_desc(&tmA2);
+    if (p.nt_narrow > 0 || p.last_narrow) tma_prefetch_desc(&tmB2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -190,6 +198,22 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   };
 
+  // unit -> (m-pair, first weight row of its columns, tile width)
+  auto unit_geom = [&](int unit, int& m_pair, int& n_org, int& bn) {
+    if (unit < p.wide_units) {
+      m_pair = unit / p.num_n_tiles;
+      const int k = unit - m_pair * p.num_n_tiles;
+      n_org = k * BN;
+      bn = (p.last_narrow && k == p.num_n_tiles - 1) ? kNarrowBN : BN;
+    } else {
+      const int j = unit - p.wide_units;
+      const int mp = j / p.nt_narrow;
+      m_pair = p.wide_m_pairs + mp;
+      n_org = (j - mp * p.nt_narrow) * kNarrowBN;
+      bn = kNarrowBN;
+    }
+  };
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
@@ -198,8 +222,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         int unit, k0, k1, tail_idx;
         decode(tile, unit, k0, k1, tail_idx);
-        const int n_blk = unit % p.num_n_tiles;
-        const int m_blk = (p.m_pair0 + unit / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
+        int m_pair, n_org, bn;
+        unit_geom(unit, m_pair, n_org, bn);
+        const bool narrow = bn != BN;
+        const int m_blk = m_pair * PAIR + static_cast<int>(cta_rank);
+        const uint32_t stage_bytes = kABytes + (narrow ? (kNarrowBN / PAIR) * kBK * 2 : Cfg::kBBytes);
         int img = 0, x0 = 0, y0 = 0;
         if (p.conv) {
           const int per_img = p.tiles_x * p.tiles_y;
@@ -208,13 +235,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           y0 = (rem / p.tiles_x) * kConvTileH;
           x0 = (rem % p.tiles_x) * kConvTileW;
         }
-        const int b_row0 = n_blk * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
+        const int b_row0 = n_org + static_cast<int>(cta_rank) * (bn / PAIR);
+        const CUtensorMap* bm = narrow ? &tmB2 : &tmB;
         for (int kb = k0; kb < k1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (PAIR == 1) {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           } else if (leader) {
-            mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);  // both CTAs' bytes land on this barrier
+            mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);  // both CTAs' bytes land on this barrier
           } else {
             mbar_arrive_cluster(&full_bar[stage], 0);
           }
@@ -238,9 +266,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_load_2d(sA + stage * kABytes, am, &full_bar[stage], kc, m_blk * kBM);
           }
           if (PAIR == 2)
-            tma_load_2d_pair(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, b_row0);
+            tma_load_2d_pair(sB + stage * Cfg::kBBytes, bm, &full_bar[stage], kb * kBK, b_row0);
           else
-            tma_load_2d(sB + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, b_row0);
+            tma_load_2d(sB + stage * Cfg::kBBytes, bm, &full_bar[stage], kb * kBK, b_row0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -251,7 +279,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0 && leader) {  // in a pair only the leader CTA issues (for both SMs' tensor cores)
-      constexpr uint32_t idesc = make_idesc_bf16(kBM * PAIR, BN, 0, 0);
+      constexpr uint32_t idesc_wide = make_idesc_bf16(kBM * PAIR, BN, 0, 0);
+      constexpr uint32_t idesc_narrow = make_idesc_bf16(kBM * PAIR, kNarrowBN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -260,6 +289,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         decode(tile, unit, k0, k1, tail_idx);
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
+        int mp_u, n_org_u, bn_u;
+        unit_geom(unit, mp_u, n_org_u, bn_u);
+        const uint32_t idesc = bn_u == BN ? idesc_wide : idesc_narrow;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -360,9 +392,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t acc_phase = (iter >> 1) & 1;
       int unit, k0, k1, tail_idx;
       decode(tile, unit, k0, k1, tail_idx);
-      const int n_org = (unit % p.num_n_tiles) * BN;           // first weight row of the tile's columns
-      constexpr int bn_cur = BN;
-      const int m_blk = (p.m_pair0 + unit / p.num_n_tiles) * PAIR + static_cast<int>(cta_rank);
+      int m_pair, n_org, bn_cur;  // n_org: first weight row of the tile's columns; bn_cur: BN, or BN/2 (narrow unit)
+      unit_geom(unit, m_pair, n_org, bn_cur);
+      const int m_blk = m_pair * PAIR + static_cast<int>(cta_rank);
       const int r_local = wq * 32 + lane;
       const int bn_out = geglu ? bn_cur / 2 : bn_cur;          // output columns of this item
       const int no_org = geglu ? n_org / 2 : n_org;            // first output column
@@ -421,14 +453,39 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // LayerNorm-on-A: v = rstd * (acc - mean * colsum[n]) (+ folded bias); statistics of this thread's row
       float ln_mean = 0.f, ln_rstd = 1.f;
       if (p.ln_stats && row_ok) {
-        const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + orow);
-        ln_mean = st.x * p.ln_inv_k;
-        const float var = fmaxf(fmaf(st.y, p.ln_inv_k, -ln_mean * ln_mean), 0.f);
+        const double2 st = __ldg(reinterpret_cast<const double2*>(p.ln_stats) + orow);
+        const double dmean = st.x * static_cast<double>(p.ln_inv_k);
+        ln_mean = static_cast<float>(dmean);
+        const float var = fmaxf(static_cast<float>(st.y * static_cast<double>(p.ln_inv_k) - dmean * dmean), 0.f);
         ln_rstd = rsqrtf(var + p.ln_eps);
       }
       float rs_sum = 0.f, rs_sq = 0.f;  // producer side: sums over this thread's columns of the outputs
       if (p.zero_rows && n_org == 0 && half == 0 && row_ok)
-        *reinterpret_cast<float2*>(p.zero_rows + 2 * orow) = make_float2(0.f, 0.f);
+        *reinterpret_cast<double2*>(p.zero_rows + 2 * orow) = make_double2(0.0, 0.0);
+
+      // Residual prefetch: the residual tile of this thread group's FIRST 64-column block is requested before the
+      // group waits for the accumulator, so its ~1 us L2 / HBM latency overlaps the tail of the tile's MMAs instead of
+      // sitting on the epilogue's critical path (K <= 1280 linears were epilogue-latency-bound: two exposed residual
+      // round trips per tile).  Safe: the issuer issued the previous TMA store itself (wait_group.read covers it) and
+      // every thread of the group finished reading the staging tile before the issuer passed the group's last barrier.
+      bool res_prefetched = false;
+      if (p.tma_epilogue && p.residual && tail_idx < 0 && c_begin < c_end && no_org + c_begin < p.n_out) {
+        res_prefetched = true;  // group-uniform
+        if (wq == 0 && lane == 0) {
+          uint8_t* stage0 = sOut + half * (kBM * 64 * 2);
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive_expect_tx(&res_bar[half], kBM * 64 * 2);
+          if (p.conv) {
+            const int per_img = p.tiles_x * p.tiles_y;
+            const int pimg = m_blk / per_img;
+            const int rem = m_blk - pimg * per_img;
+            tma_load_4d(stage0, &tmR, &res_bar[half], no_org + c_begin, (rem % p.tiles_x) * kConvTileW,
+                        (rem / p.tiles_x) * kConvTileH, pimg);
+          } else {
+            tma_load_2d(stage0, &tmR, &res_bar[half], no_org + c_begin, m_blk * kBM);
+          }
+        }
+      }
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -532,21 +589,21 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // the previous TMA store must have finished READING the staging tile before anyone overwrites it
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          if (p.residual) {
-            if (issuer) {
-              mbar_arrive_expect_tx(&res_bar[half], kBM * 64 * 2);
-              if (p.conv)
-                tma_load_4d(stage, &tmR, &res_bar[half], no0, cx, cy, cimg);
-              else
-                tma_load_2d(stage, &tmR, &res_bar[half], no0, m_blk * kBM);
-            }
-            mbar_wait(&res_bar[half], res_phase);
-            res_phase ^= 1;
+          if (p.residual && !(res_prefetched && cb == c_begin) && issuer) {
+            mbar_arrive_expect_tx(&res_bar[half], kBM * 64 * 2);
+            if (p.conv)
+              tma_load_4d(stage, &tmR, &res_bar[half], no0, cx, cy, cimg);
+            else
+              tma_load_2d(stage, &tmR, &res_bar[half], no0, m_blk * kBM);
           }
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             float v[32];
             load_chunk(cb + cc * 32, v);
+            if (p.residual && cc == 0) {  // the TMEM load + bias math above overlapped the residual's flight
+              mbar_wait(&res_bar[half], res_phase);
+              res_phase ^= 1;
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint8_t* sp = stage + r_local * 128 + (((cc * 4 + q) ^ (r_local & 7)) << 4);
@@ -655,8 +712,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (!released) release_acc(acc);  // this column half lies entirely beyond N
         if (p.row_stats_out && row_ok) {  // columns beyond N contributed exact zeros
-          atomicAdd(p.row_stats_out + 2 * orow, rs_sum);
-          atomicAdd(p.row_stats_out + 2 * orow + 1, rs_sq);
+          atomicAdd(p.row_stats_out + 2 * orow, static_cast<double>(rs_sum));
+          atomicAdd(p.row_stats_out + 2 * orow + 1, static_cast<double>(rs_sq));
         }
         continue;
       }
@@ -760,8 +817,9 @@ static int resident_groups(int num_sms) {
 
 template <int BN, int PAIR, bool STATS>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                         const CUtensorMap& tmR, const CUtensorMap& tmA2, const GemmParams& p_in, int num_sms,
-                         cudaStream_t stream, void* splitk_ws, long long splitk_ws_bytes) {
+                         const CUtensorMap& tmR, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
+                         const GemmParams& p_in, int num_sms, cudaStream_t stream, void* splitk_ws,
+                         long long splitk_ws_bytes) {
   GemmParams p = p_in;
   using Cfg = GemmCfg<BN, PAIR>;
   const int slot = device_slot();
@@ -771,7 +829,14 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
                                     Cfg::kSmemBytes));
     attr_set[slot] = true;
   }
-  const int units = ((p.num_m_tiles + PAIR - 1) / PAIR) * p.num_n_tiles;
+  const int m_groups = (p.num_m_tiles + PAIR - 1) / PAIR;
+  const bool mixed = p.nt_narrow > 0;  // run_gemm chose the mixed-width tail (BN == 256 only)
+  if (!mixed) {
+    p.wide_units = m_groups * p.num_n_tiles;
+    p.wide_m_pairs = m_groups;
+    p.nt_narrow = 0;
+  }
+  const int units = mixed ? p.wide_units + (m_groups - p.wide_m_pairs) * p.nt_narrow : m_groups * p.num_n_tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
@@ -803,8 +868,8 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   p.tail_parts = 1;
   p.total_items = units;
   p.ws = nullptr;
-  if (splitk_env > 0 && p.num_k_iters >= splitk_env && splitk_ws && p.tma_epilogue && p.epilogue != DS_EPI_GEGLU &&
-      units > groups) {
+  if (splitk_env > 0 && !mixed && p.num_k_iters >= splitk_env && splitk_ws && p.tma_epilogue &&
+      p.epilogue != DS_EPI_GEGLU && units > groups) {
     const int full = (units / groups) * groups, left = units - full;
     if (left > 0 && left <= 128) {
       int parts = groups / left;
@@ -820,19 +885,20 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     }
   }
   cfg.gridDim = dim3(groups * PAIR);
-  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR, STATS>, tmA, tmB, tmC, tmR, tmA2, p));
+  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR, STATS>, tmA, tmB, tmC, tmR, tmA2, tmB2, p));
   DS_LAUNCH_OK("gemm_bf16_tcgen05");
   return DS_OK;
 }
 
 template <int BN, int PAIR>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                       const CUtensorMap& tmR, const CUtensorMap& tmA2, const GemmParams& p, int num_sms,
-                       cudaStream_t stream, void* splitk_ws, long long splitk_ws_bytes) {
+                       const CUtensorMap& tmR, const CUtensorMap& tmA2, const CUtensorMap& tmB2, const GemmParams& p,
+                       int num_sms, cudaStream_t stream, void* splitk_ws, long long splitk_ws_bytes) {
   // the statistics epilogue is a separate instantiation: the default one keeps its register budget
   if (p.chan_stats)
-    return launch_gemm_t<BN, PAIR, true>(tmA, tmB, tmC, tmR, tmA2, p, num_sms, stream, splitk_ws, splitk_ws_bytes);
-  return launch_gemm_t<BN, PAIR, false>(tmA, tmB, tmC, tmR, tmA2, p, num_sms, stream, splitk_ws, splitk_ws_bytes);
+    return launch_gemm_t<BN, PAIR, true>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, num_sms, stream, splitk_ws,
+                                         splitk_ws_bytes);
+  return launch_gemm_t<BN, PAIR, false>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, num_sms, stream, splitk_ws, splitk_ws_bytes);
 }
 
 static int pick_bn(int N, int epilogue) {
@@ -887,7 +953,7 @@ static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const void*
   if (p.row_stats_out) {
     DS_REQUIRE(p.tma_epilogue, "ds_gemm_bf16: row_stats_out needs a 16-byte addressable bf16 output");
     if (!row_stats_zeroed)
-      DS_CUDA_OK(cudaMemsetAsync(p.row_stats_out, 0, sizeof(float) * 2 * static_cast<size_t>(p.M), stream));
+      DS_CUDA_OK(cudaMemsetAsync(p.row_stats_out, 0, sizeof(double) * 2 * static_cast<size_t>(p.M), stream));
   }
   if (p.chan_stats) {
     DS_REQUIRE(p.tma_epilogue && p.epilogue != DS_EPI_GEGLU,
@@ -903,54 +969,71 @@ static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const void*
     if (p.residual && !make_out_map(&tmR, p.residual, p, p.ldres, conv_B)) return DS_ERR_CUDA;
   }
   p.conv_B = conv_B;
-  p.m_pair0 = 0;
-  auto launch = [&](int bn_l, const GemmParams& q) -> int {
-    CUtensorMap tmB;
-    const uint64_t dims[2] = {static_cast<uint64_t>(q.K), static_cast<uint64_t>(q.N)};
-    const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-    const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn_l / pair)};
-    if (!encode_tmap_bf16(&tmB, w, 2, dims, strides, box, nullptr)) return DS_ERR_CUDA;
-    if (pair == 2) {
-      if (bn_l == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, tmA2, q, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
-      if (bn_l == 192) return launch_gemm<192, 2>(tmA, tmB, tmC, tmR, tmA2, q, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
-      return launch_gemm<128, 2>(tmA, tmB, tmC, tmR, tmA2, q, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
-    }
-    if (bn_l == 256) return launch_gemm<256, 1>(tmA, tmB, tmC, tmR, tmA2, q, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
-    if (bn_l == 192) return launch_gemm<192, 1>(tmA, tmB, tmC, tmR, tmA2, q, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
-    return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, tmA2, q, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
-  };
   p.num_n_tiles = (p.N + bn - 1) / bn;
-  // ---- tail launch: 160 tiles on 74 CTA pairs are 2.16 rounds that cost 3.  Cover the m-rows of the full rounds with
-  // the wide tiles and the few remaining m-rows with BN=128 tiles (twice as many units, each half as long, ~0.62 of a
-  // wide round per narrow round: narrow pair tiles are shared-memory-port bound) in a second launch.
+  p.wide_units = 0;
+  p.wide_m_pairs = 0;
+  p.nt_narrow = 0;
+  // narrow last n-tile: when the last BN-wide tile of a row would hold <= 128 real columns (N = 640 -> 256|256|128,
+  // N = 320 -> 192|128, N = 1920 -> 7 x 256|128) it runs as a 128-column unit: same unit count, no padded MMAs
+  static const int narrow_env = [] {
+    const char* e = getenv("DS_GEMM_NARROW_LAST");
+    return e ? atoi(e) : 1;
+  }();
+  p.last_narrow = 0;
+  if (narrow_env && bn > kNarrowBN && p.epilogue != DS_EPI_GEGLU) {
+    const int last_cols = p.N - (p.num_n_tiles - 1) * bn;
+    if (last_cols <= kNarrowBN) p.last_narrow = 1;
+  }
+  // ---- mixed-width schedule: 160 tiles on 74 CTA pairs are 2.16 rounds that cost 3.  When the last round of the
+  // persistent schedule would fill less than ~45 % of the pairs, the m-rows that fall into it are cut into 128-column
+  // units instead (twice as many, half as long; same kernel, same launch: the MMA instruction descriptor, the B box
+  // and the epilogue's column range are per unit) and appended after the wide units, so the round-robin hands them to
+  // the pairs that would otherwise idle.  Bit-identical results (same K order per output element).
+  // MEASURED (B200): as TWO launches (wide + narrow) this LOST — N1280 K1280 linears 682 -> 528 TFLOP/s, step 59.5 ->
+  // 61.4 ms: a second launch costs ~10 us of ramp / drain, more than the saved partial round.  DS_GEMM_TAIL=0: off.
   static const int tail_env = [] {
     const char* e = getenv("DS_GEMM_TAIL");
     return e ? atoi(e) : 1;
   }();
-  if (tail_env && pair == 2 && bn == 256 && p.epilogue != DS_EPI_GEGLU) {
+  if (tail_env && pair == 2 && bn == 256 && p.epilogue != DS_EPI_GEGLU && p.N % 128 == 0 && !p.last_narrow) {
     const int G = resident_groups<256, 2>(dev.num_sms);
-    const int G128 = resident_groups<128, 2>(dev.num_sms);
     const int mp = (p.num_m_tiles + 1) / 2, nt = p.num_n_tiles;
     const int units = mp * nt;
     const int full = units / G, rem = units - full * G;
-    if (full >= 1 && rem > 0 && rem * 100 < G * 45 && G128 > 0) {
-      const int R = (full * G) / nt;                 // m-pairs the wide launch covers in exactly `full` rounds
-      const int nt128 = (p.N + 127) / 128;
-      const int units_b = (mp - R) * nt128;
-      const float cost = static_cast<float>((R * nt + G - 1) / G) + 0.62f * static_cast<float>((units_b + G128 - 1) / G128);
+    if (full >= 1 && rem > 0 && rem * 100 < G * 45) {
+      const int R = (full * G) / nt;                 // m-pairs whose wide tiles fill exactly `full` rounds
+      const int nt128 = p.N / 128;
+      const int narrow = (mp - R) * nt128;
+      // rounds in units of a wide tile: the narrow units run at ~0.6 of a wide unit each
+      const int total = R * nt + narrow;
+      const float cost = static_cast<float>(full) + 0.6f * static_cast<float>((total - full * G + G - 1) / G);
       if (R >= 1 && R < mp && cost < 0.95f * static_cast<float>(full + 1)) {
-        GemmParams qa = p, qb = p;
-        qa.num_m_tiles = R * 2;                      // rows beyond are simply not visited by this launch
-        qb.m_pair0 = R;
-        qb.num_m_tiles = p.num_m_tiles - R * 2;
-        qb.num_n_tiles = nt128;
-        const int rc = launch(256, qa);
-        if (rc != DS_OK) return rc;
-        return launch(128, qb);
+        p.wide_units = R * nt;
+        p.wide_m_pairs = R;
+        p.nt_narrow = nt128;
       }
     }
   }
-  return launch(bn, p);
+  CUtensorMap tmB, tmB2;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn / pair)};
+    if (!encode_tmap_bf16(&tmB, w, 2, dims, strides, box, nullptr)) return DS_ERR_CUDA;
+    tmB2 = tmB;
+    if (p.nt_narrow > 0 || p.last_narrow) {
+      const uint32_t box2[2] = {kBK, static_cast<uint32_t>(kNarrowBN / pair)};
+      if (!encode_tmap_bf16(&tmB2, w, 2, dims, strides, box2, nullptr)) return DS_ERR_CUDA;
+    }
+  }
+  if (pair == 2) {
+    if (bn == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+    if (bn == 192) return launch_gemm<192, 2>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+    return launch_gemm<128, 2>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+  }
+  if (bn == 256) return launch_gemm<256, 1>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+  if (bn == 192) return launch_gemm<192, 1>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
+  return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
 }
 
 }  // namespace ds
@@ -1000,18 +1083,20 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
   if (a->ln_stats) {
     DS_REQUIRE(a->ln_colsum != nullptr, "ds_gemm_bf16: ln_stats needs ln_colsum");
     DS_REQUIRE(a->rowbias == nullptr, "ds_gemm_bf16: ln_stats and rowbias are mutually exclusive");
-    DS_REQUIRE((reinterpret_cast<uintptr_t>(a->ln_stats) & 7) == 0, "ds_gemm_bf16: ln_stats must be 8-byte aligned");
+    DS_REQUIRE((reinterpret_cast<uintptr_t>(a->ln_stats) & 15) == 0, "ds_gemm_bf16: ln_stats must be 16-byte aligned");
   }
   p.ln_stats = a->ln_stats;
   p.ln_colsum = a->ln_colsum;
   p.ln_eps = a->ln_eps;
   p.ln_inv_k = 1.0f / static_cast<float>(a->K);
   p.row_stats_out = a->row_stats_out;
+  if (a->row_stats_out)
+    DS_REQUIRE((reinterpret_cast<uintptr_t>(a->row_stats_out) & 15) == 0, "ds_gemm_bf16: row_stats_out must be 16-byte aligned");
   p.zero_rows = a->zero_rows;
   if (a->zero_rows)
-    DS_REQUIRE((reinterpret_cast<uintptr_t>(a->zero_rows) & 7) == 0 && a->zero_rows != a->row_stats_out &&
+    DS_REQUIRE((reinterpret_cast<uintptr_t>(a->zero_rows) & 15) == 0 && a->zero_rows != a->row_stats_out &&
                    a->zero_rows != a->ln_stats,
-               "ds_gemm_bf16: zero_rows must be 8-byte aligned and distinct from ln_stats / row_stats_out");
+               "ds_gemm_bf16: zero_rows must be 16-byte aligned and distinct from ln_stats / row_stats_out");
   p.num_m_tiles = (a->M + kBM - 1) / kBM;
   p.num_k_iters = (a->K + kBK - 1) / kBK;
   p.k1_iters = p.num_k_iters;

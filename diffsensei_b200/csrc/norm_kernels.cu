@@ -142,7 +142,7 @@ template <bool kSilu, int kU>
 __global__ void gn_apply2_kernel(const uint4* __restrict__ x1, const uint4* __restrict__ x2, uint4* __restrict__ y,
                                  const double* __restrict__ st1, const double* __restrict__ st2,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C1, int C2,
-                                 int groups, float eps, int items_per_sample, int ipx, int total_items) {
+                                 int groups, float eps, int items_per_sample, int ipx, int total_items, int l2_hint) {
   extern __shared__ double shd[];  // [C][2] channel sums of the current sample, then [groups][2] {mean, rstd}
   const int C = C1 + C2;
   const int cv = C >> 3, cv1 = C1 >> 3;
@@ -166,7 +166,8 @@ __global__ void gn_apply2_kernel(const uint4* __restrict__ x1, const uint4* __re
     ga[j] = __ldg(gamma + cvec * 8 + j);
     be[j] = __ldg(beta + cvec * 8 + j);
   }
-  const uint64_t pol = l2_policy_evict_first();      // x is dead after this read; y stays for the consumer conv
+  // x is dead after this read (evict_first); y stays for the consumer conv.  l2_hint == 0: plain loads (A/B knob)
+  const uint64_t pol = l2_hint ? l2_policy_evict_first() : l2_policy_normal();
   // group coefficients of sample b: channel sums -> smem -> 32 threads fold cpg channels each, in order
   auto load_coeffs = [&](int b) {
     __syncthreads();                                 // previous sample's coefficients no longer in use
@@ -391,6 +392,7 @@ extern "C" int ds_groupnorm_apply(const void* x1, const double* stats1, int C1, 
   static const int tt = gn_env("DS_GN_THREADS", 256, 64, 1024);
   static const int unroll = gn_env("DS_GN_UNROLL", 8, 4, 8);
   static const int max_occ = gn_env("DS_GN_OCC", 8, 1, 16);
+  static const int l2_hint = gn_env("DS_GN_L2HINT", 0, 0, 1);  // measured: plain loads 35.4 us vs evict_first 36.1 us
   GnPlan pl;
   DS_REQUIRE(gn_plan(B, HW, C, tt, unroll, &pl), "ds_groupnorm_apply: tensor too large");
   const size_t smem = static_cast<size_t>(C) * 2 * sizeof(double) + static_cast<size_t>(groups) * 2 * sizeof(float);
@@ -425,7 +427,7 @@ extern "C" int ds_groupnorm_apply(const void* x1, const double* stats1, int C1, 
   uint4* yp = static_cast<uint4*>(y);
 #define DS_GN_LAUNCH(S, U)                                                                                         \
   DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gn_apply2_kernel<S, U>, a1, a2, yp, stats1, stats2, gamma, beta, HW, C1, C2, \
-                                groups, eps, pl.items_per_sample, pl.ipx, pl.total_items))
+                                groups, eps, pl.items_per_sample, pl.ipx, pl.total_items, l2_hint))
   if (unroll == 8) {
     if (apply_silu) DS_GN_LAUNCH(true, 8); else DS_GN_LAUNCH(false, 8);
   } else {

@@ -208,9 +208,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          chan_stats: Optional[torch.Tensor] = None, stats_rows_per_sample: int = 0) -> torch.Tensor:
     """out[..., Nout] = epilogue(a[..., K] @ w[N, K]^T) on tcgen05; ``a`` may have any leading dims.
 
-    LayerNorm fusion (include/dsengine.h): ``ln_stats`` [2*M] fp32 {sum, sumsq} per row of ``a`` + ``ln_colsum`` [N]
+    LayerNorm fusion (include/dsengine.h): ``ln_stats`` [2*M] fp64 {sum, sumsq} per row of ``a`` + ``ln_colsum`` [N]
     turn the call into LayerNorm(a) @ w_orig^T for weights folded by ``weights.fold_layernorm``; ``row_stats_out``
-    [2*M] fp32 receives {sum, sumsq} of every (bf16-rounded) output row."""
+    [2*M] fp64 receives {sum, sumsq} of every (bf16-rounded) output row."""
     _req(a, bf16, "gemm.a")
     _req(w, bf16, "gemm.w", 2)
     K1 = a.shape[-1]
@@ -251,20 +251,20 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         if residual.numel() != M * n_out:
             raise DsEngineError("gemm: residual must match the output shape")
     if ln_stats is not None:
-        _req(ln_stats, f32, "gemm.ln_stats", 1)
+        _req(ln_stats, torch.float64, "gemm.ln_stats", 1)
         if ln_colsum is None:
             raise DsEngineError("gemm: ln_stats needs ln_colsum")
         _req(ln_colsum, f32, "gemm.ln_colsum", 1)
         if ln_stats.numel() < 2 * M or ln_colsum.numel() != N:
-            raise DsEngineError("gemm: ln_stats must hold 2*M floats and ln_colsum N floats")
+            raise DsEngineError("gemm: ln_stats must hold 2*M doubles and ln_colsum N floats")
     if zero_rows is not None:
-        _req(zero_rows, f32, "gemm.zero_rows", 1)
+        _req(zero_rows, torch.float64, "gemm.zero_rows", 1)
         if zero_rows.numel() < 2 * M:
-            raise DsEngineError("gemm: zero_rows must hold 2*M floats")
+            raise DsEngineError("gemm: zero_rows must hold 2*M doubles")
     if row_stats_out is not None:
-        _req(row_stats_out, f32, "gemm.row_stats_out", 1)
+        _req(row_stats_out, torch.float64, "gemm.row_stats_out", 1)
         if row_stats_out.numel() < 2 * M or out_fp32:
-            raise DsEngineError("gemm: row_stats_out must hold 2*M floats and needs a bf16 output")
+            raise DsEngineError("gemm: row_stats_out must hold 2*M doubles and needs a bf16 output")
     ws = _splitk_ws()
     args = GemmArgs(a=a.data_ptr(), w=w.data_ptr(), out=out.data_ptr(), bias=_ptr(bias), rowbias=_ptr(rowbias),
                     residual=_ptr(residual), M=M, N=N, K=K, lda=K1, ldw=K, ldo=n_out, ldres=n_out,
@@ -460,6 +460,42 @@ def cfg_ddim_step_(noise_pred: torch.Tensor, latents: torch.Tensor, model_in: to
         raise DsEngineError("cfg_ddim_step: shape mismatch")
     check(lib.ds_cfg_ddim_step(noise_pred.data_ptr(), latents.data_ptr(), model_in.data_ptr(), coef.data_ptr(),
                                float(guidance), bs, H * W, Cc, _stream()), "ds_cfg_ddim_step")
+
+
+# ---------------------------------------------------------------------------------------------- VAE decoder helpers
+def latent_pointwise(latents: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], inv_scale: float) -> torch.Tensor:
+    """(latents * inv_scale) through a 1x1 conv 4 -> 4: fp32 NCHW [B,4,H,W] -> bf16 NHWC [B,H,W,4]."""
+    _req(latents, f32, "latent_pointwise.latents", 4)
+    B, Cc, H, W = latents.shape
+    _req(w, f32, "latent_pointwise.w", 2)
+    if Cc != 4 or tuple(w.shape) != (4, 4):
+        raise DsEngineError("latent_pointwise: latents must have 4 channels and w must be [4, 4]")
+    if bias is not None:
+        _req(bias, f32, "latent_pointwise.bias", 1)
+    out = torch.empty(B, H, W, 4, dtype=bf16, device=latents.device)
+    check(lib.ds_latent_pointwise(latents.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), float(inv_scale), B,
+                                  H * W, _stream()), "ds_latent_pointwise")
+    return out
+
+
+def softmax_rows(S: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Row-wise softmax(scale * S): fp32 [rows, n] -> bf16 [rows, n] (n <= 32768)."""
+    _req(S, f32, "softmax_rows.S", 2)
+    rows, n = S.shape
+    out = torch.empty(rows, n, dtype=bf16, device=S.device) if out is None else _req(out, bf16, "softmax_rows.out", 2)
+    if tuple(out.shape) != (rows, n):
+        raise DsEngineError("softmax_rows: out must be [rows, n]")
+    check(lib.ds_softmax_rows(S.data_ptr(), out.data_ptr(), rows, n, n, n, float(scale), _stream()), "ds_softmax_rows")
+    return out
+
+
+def image_postprocess(x: torch.Tensor) -> torch.Tensor:
+    """clamp(x / 2 + 0.5, 0, 1): bf16 NHWC [B,H,W,C] -> fp32 NCHW [B,C,H,W]."""
+    _req(x, bf16, "image_postprocess.x", 4)
+    B, H, W, Cc = x.shape
+    out = torch.empty(B, Cc, H, W, dtype=f32, device=x.device)
+    check(lib.ds_image_postprocess(x.data_ptr(), out.data_ptr(), B, H * W, Cc, _stream()), "ds_image_postprocess")
+    return out
 
 
 launch_count = _lib.launch_count

@@ -6,10 +6,10 @@ Mirrors ``src/pipelines/pipeline_diffsensei.py``:
     padded characters, Resampler(pos) and Resampler(zeros), optional paste of MLLM-adapted embeds (:143-145),
     repeat to ``num_samples``; ``prepare_dialog_bbox`` (:156-170)
   * the CFG denoise loop (:293-337) — ``denoise``: the hot path.
-Out of scope this round ("next" ring): the SDXL text encoders, CLIP / Magi image encoders and
-the VAE.  ``__call__`` keeps the reference's keyword surface but takes their OUTPUTS as tensors
-(``prompt_embeds`` ..., ``clip_image_embeds`` / ``magi_image_embeds``) and returns latents; passing a raw
-``prompt`` string without embeddings raises, it does not fall back to anything.
+  * VAE decode + image post-process (:339-363) — ``VaeDecoderEngine`` (vae.py), ``output_type`` "pt" / "np" / "pil".
+Out of scope: the SDXL text encoders and the CLIP / Magi image encoders.  ``__call__`` keeps
+the reference's keyword surface but takes their OUTPUTS as tensors (``prompt_embeds`` ..., ``clip_image_embeds`` /
+``magi_image_embeds``); passing a raw ``prompt`` string without embeddings raises, it does not fall back to anything.
 
 Loop structure on the GPU (one process per GPU, one stream):
   once per panel : K|V projections of text and IP tokens for all cross-attention layers, time-embedding
@@ -35,8 +35,9 @@ bf16, f32 = torch.bfloat16, torch.float32
 
 class DiffSenseiPipeline:
     def __init__(self, unet: UNetMangaEngine, scheduler: Optional[DDIMScheduler] = None, vae_scale_factor: int = 8,
-                 default_sample_size: int = 128):
+                 default_sample_size: int = 128, vae=None):
         self.unet = unet
+        self.vae = vae                      # VaeDecoderEngine (or None: latents out only)
         self.scheduler = scheduler or DDIMScheduler()
         self.vae_scale_factor = vae_scale_factor
         self.default_sample_size = default_sample_size
@@ -202,8 +203,10 @@ class DiffSenseiPipeline:
         if len(ip_images) > 0:
             raise NotImplementedError("image encoding (CLIP / Magi, pipeline_diffsensei.py:125-128) is outside the "
                                       "hot path this round: pass clip_image_embeds / magi_image_embeds")
-        if output_type != "latent":
-            raise NotImplementedError("VAE decode (pipeline_diffsensei.py:339-367) is outside the hot path this round")
+        if output_type not in ("latent", "pt", "np", "pil"):
+            raise ValueError(f"output_type must be one of latent / pt / np / pil, got {output_type!r}")
+        if output_type != "latent" and self.vae is None:
+            raise ValueError("output_type other than 'latent' needs a VAE decoder: DiffSenseiPipeline(..., vae=...)")
         n_real = clip_image_embeds.shape[1] if clip_image_embeds is not None else 0
         num_ips = len(ip_image_embeds) if ip_image_embeds is not None else n_real
         if num_ips != len(ip_bbox):
@@ -231,7 +234,20 @@ class DiffSenseiPipeline:
         pe = torch.cat([pe, torch.cat([neg_img, img], dim=0)], dim=1)                              # :297,303
         final = self.denoise(latents, pe, te, ti, torch.cat([neg_bbox, bbox], dim=0), aspect_ratio,
                              torch.cat([neg_db, db], dim=0), num_inference_steps, guidance_scale, use_graph=use_graph)
-        return SimpleNamespace(images=final, latents=final)
+        if output_type == "latent":
+            return SimpleNamespace(images=final, latents=final)
+        # pipeline_diffsensei.py:339-363: latents / scaling_factor -> vae.decode -> image_processor.postprocess
+        image = self.vae.decode_image(final)                                            # fp32 NCHW in [0, 1]
+        if output_type == "np":
+            image = image.permute(0, 2, 3, 1).cpu().numpy()
+        elif output_type == "pil":
+            try:
+                from PIL import Image
+            except ImportError as e:
+                raise RuntimeError("output_type='pil' needs Pillow; use 'pt' or 'np'") from e
+            arr = (image.permute(0, 2, 3, 1).cpu().numpy() * 255).round().astype("uint8")
+            image = [Image.fromarray(a) for a in arr]
+        return SimpleNamespace(images=image, latents=final)
 
 
 class DenoiseStepper:

@@ -341,7 +341,7 @@ class UNetMangaEngine:
         # (producer k -> buffer k % 3), the next LayerNorm-folded GEMM consumes them and clears buffer (k + 2) % 3 for
         # the producer two hops ahead — no stand-alone LayerNorm kernel, h is read once instead of twice, and after the
         # first two producers of a transformer (which memset their buffer) no memset node either.
-        st = [torch.empty(2 * M, dtype=f32, device=x.device) for _ in range(3)]
+        st = [torch.empty(2 * M, dtype=torch.float64, device=x.device) for _ in range(3)]
         k = 0
 
         def produce(*a, **kw):

@@ -20,7 +20,7 @@ from typing import Dict, List, Tuple
 
 import torch
 
-from .config import ResamplerConfig, UNetConfig
+from .config import ResamplerConfig, UNetConfig, VaeConfig
 
 Shape = Tuple[int, ...]
 
@@ -147,9 +147,53 @@ def resampler_param_shapes(rc: ResamplerConfig) -> Dict[str, Shape]:
     return sh
 
 
+def vae_decoder_param_shapes(vc: VaeConfig) -> Dict[str, Shape]:
+    """diffusers AutoencoderKL keys the decode path reads: ``post_quant_conv`` + ``decoder.*``."""
+    sh: Dict[str, Shape] = {}
+    ch = vc.block_out_channels
+
+    def conv(p, o, i, k):
+        sh[p + ".weight"] = (o, i, k, k)
+        sh[p + ".bias"] = (o,)
+
+    def norm(p, c):
+        sh[p + ".weight"] = (c,)
+        sh[p + ".bias"] = (c,)
+
+    def resnet(p, cin, cout):
+        norm(p + ".norm1", cin)
+        conv(p + ".conv1", cout, cin, 3)
+        norm(p + ".norm2", cout)
+        conv(p + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(p + ".conv_shortcut", cout, cin, 1)
+
+    conv("post_quant_conv", vc.latent_channels, vc.latent_channels, 1)
+    c = ch[-1]
+    conv("decoder.conv_in", c, vc.latent_channels, 3)
+    resnet("decoder.mid_block.resnets.0", c, c)
+    resnet("decoder.mid_block.resnets.1", c, c)
+    a = "decoder.mid_block.attentions.0"
+    norm(a + ".group_norm", c)
+    for nm in ("to_q", "to_k", "to_v", "to_out.0"):
+        sh[f"{a}.{nm}.weight"] = (c, c)
+        sh[f"{a}.{nm}.bias"] = (c,)
+    prev = c
+    rev = list(reversed(ch))
+    for i, co in enumerate(rev):
+        for j in range(vc.layers_per_block + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else co, co)
+        if i < len(rev) - 1:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", co, co, 3)
+        prev = co
+    norm("decoder.conv_norm_out", ch[0])
+    conv("decoder.conv_out", vc.out_channels, ch[0], 3)
+    return sh
+
+
 def _is_norm(key: str) -> bool:
     parts = key.split(".")
-    return any(p.startswith("norm") or p == "conv_norm_out" for p in parts[-2:-1]) or \
+    return any(p.startswith("norm") or p in ("conv_norm_out", "group_norm") for p in parts[-2:-1]) or \
         (len(parts) >= 2 and parts[-2] == "0" and "layers" in parts)   # Resampler FF LayerNorm "layers.i.1.0"
 
 

@@ -110,8 +110,9 @@ int ds_ip_mask(const float* bbox, float* mask, int B, int N, double aspect_ratio
  *             mean = sum/K, rstd = rsqrt(sumsq/K - mean^2 + ln_eps) from ln_stats[row] = {sum, sumsq}.
  *             Algebraically identical to LayerNorm(A) W^T + bias.
  *   producer: with row_stats_out != NULL the call zeroes it (unless row_stats_zeroed), then accumulates {sum, sum
- *             of squares} of every output row (fp32 values, before the bf16 rounding) — bf16 outputs with
- *             16-byte rows only.  zero_rows != NULL: the call also resets that [M][2] buffer (the first n-tile of
+ *             of squares} of every output row (fp32 values, before the bf16 rounding; per-tile fp32 partials are
+ *             combined with fp64 atomics, which is exact, so the statistics do not depend on the arrival order) —
+ *             bf16 outputs with 16-byte rows only.  zero_rows != NULL: the call also resets that [M][2] buffer (the first n-tile of
  *             every m-tile does it), which lets a chain of GEMMs rotate three statistics buffers without any
  *             memset node: the consumer of buffer k clears buffer k+2.
  * Split-K tail: the kernel is persistent (one CTA pair per two SMs, static round-robin over 256 x BN output tiles);
@@ -120,11 +121,10 @@ int ds_ip_mask(const float* bbox, float* mask, int B, int N, double aspect_ratio
  *   finished by whichever slice arrives last.  The caller provides a 16-byte aligned workspace that is ALL ZERO on
  *   entry (ds_gemm_splitk_ws_bytes() bytes cover every shape; the kernel leaves it all zero again) and must not be
  *   shared by GEMMs running concurrently on different streams.  NULL simply disables the feature.
- * Tail launch (default on, DS_GEMM_TAIL=0 disables): when the last round of the persistent schedule would fill
- *   less than ~45 % of the CTA pairs, the call covers the M range with TWO launches of the same kernel — 256-wide
- *   tiles for the m-rows of the full rounds, 128-wide tiles (twice as many, half as long) for the remaining m-rows —
- *   instead of paying a whole round for a handful of tiles.  Results are bit-identical to one launch (same K order
- *   per output element).
+ * Mixed-width schedule (default on, DS_GEMM_TAIL=0 disables): when the last round of the persistent schedule would
+ *   fill less than ~45 % of the CTA pairs, the m-rows that fall into it run as 128-column units (twice as many, half
+ *   as long) appended to the 256-column units of the same launch, instead of paying a whole round for a handful of
+ *   tiles.  Results are bit-identical to the plain schedule (same K order per output element).
  * Constraints: K % 8 == 0, lda % 8 == 0 (16-byte TMA strides). M, N, K tails are handled by TMA
  * zero-fill and masked stores.
  * --------------------------------------------------------------------------------------------- */
@@ -147,11 +147,11 @@ typedef struct {
   int32_t epilogue;       /* DS_EPI_*                                      */
   int32_t out_fp32;       /* 1: `out` is fp32                              */
   float out_scale;        /* 0 or 1: no scaling                            */
-  const float* ln_stats;  /* [M][2] fp32 (sum, sumsq) of A's rows, or NULL  */
+  const double* ln_stats; /* [M][2] fp64 (sum, sumsq) of A's rows, or NULL  */
   const float* ln_colsum; /* [N] fp32; required with ln_stats               */
   float ln_eps;
-  float* row_stats_out;   /* [M][2] fp32 or NULL (see "producer" above)     */
-  float* zero_rows;       /* [M][2] fp32 or NULL: rows reset to 0 by this call */
+  double* row_stats_out;  /* [M][2] fp64 or NULL (see "producer" above)     */
+  double* zero_rows;      /* [M][2] fp64 or NULL: rows reset to 0 by this call */
   int32_t row_stats_zeroed; /* 1: row_stats_out is already 0, skip the memset  */
   void* splitk_ws;        /* split-K workspace (see below) or NULL             */
   int64_t splitk_ws_bytes;
@@ -278,6 +278,23 @@ int ds_cfg_ddim_step(const void* noise_pred, float* latents, void* model_in, con
  * q and k each pre-scaled by dim_head^-0.25, fp32 softmax (src/models/resampler.py:64-74).
  *   q: bf16 [Bc][nq][C], kv: bf16 [Bc][n_kv][2*C] (k | v), out: bf16 [Bc][nq][C]; C = heads*64 */
 int ds_resampler_attn(const void* q, const void* kv, void* out, int Bc, int nq, int n_kv, int heads, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * AutoencoderKL decoder helpers (the step right after the denoise loop,
+ * src/pipelines/pipeline_diffsensei.py:339-367).  The decoder's convs / GroupNorms / linears / upsampling run on
+ * the entry points above; these cover what is specific to it.                               [HBM-bound]
+ *   ds_latent_pointwise : out[b][p][0..4) = W (latents[b][:][p] * inv_scale) + bias — `latents / scaling_factor`
+ *                         followed by AutoencoderKL.post_quant_conv (1x1, 4 -> 4).  latents fp32 NCHW [B][4][HW],
+ *                         w fp32 [4][4] (out, in), bias fp32 [4] or NULL, out bf16 NHWC [B][HW][4].
+ *   ds_softmax_rows     : P[r][:] = softmax(scale * S[r][:]), S fp32 [rows][lds], P bf16 [rows][ldp], n <= 32768
+ *                         columns — between the QK^T and PV GEMMs of the decoder's single 512-wide attention head.
+ *   ds_image_postprocess: out = clamp(x / 2 + 0.5, 0, 1), x bf16 NHWC [B][HW][C] -> out fp32 NCHW [B][C][HW]
+ *                         (VaeImageProcessor.postprocess with do_denormalize, output_type "pt").
+ * --------------------------------------------------------------------------------------------- */
+int ds_latent_pointwise(const float* latents, const float* w, const float* bias, void* out, float inv_scale, int B,
+                        int HW, void* stream);
+int ds_softmax_rows(const float* S, void* P, int rows, int n, int64_t lds, int64_t ldp, float scale, void* stream);
+int ds_image_postprocess(const void* x, float* out, int B, int HW, int C, void* stream);
 
 #ifdef __cplusplus
 }

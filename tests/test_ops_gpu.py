@@ -128,10 +128,10 @@ def test_gemm_layernorm_fusion(ops, M, N, K, geglu):
     b0, res = torch.randn(K) * 0.3, _r(M, K, seed=22) * 2 + 0.7          # row mean != 0 on purpose
     gamma, beta = torch.randn(K) * 0.2 + 1, torch.randn(K) * 0.1
     w1, b1 = _r(N, K, seed=23, scale=K ** -0.5), torch.randn(N) * 0.2
-    stats = torch.full((2 * M,), 7.0, device=DEV)                          # the call must zero it first
+    stats = torch.full((2 * M,), 7.0, device=DEV, dtype=torch.float64)     # the call must zero it first
     h = ops.gemm(a0.to(DEV), w0.to(DEV), b0.to(DEV), residual=res.to(DEV), row_stats_out=stats)
     hf = h.float().cpu()
-    st = stats.cpu().view(M, 2)
+    st = stats.cpu().view(M, 2).float()
     h32 = F.linear(a0.float(), w0.float(), b0) + res.float()   # the statistics are taken before the bf16 rounding
     assert torch.allclose(st[:, 0], h32.sum(1), rtol=1e-4, atol=2e-2)
     assert torch.allclose(st[:, 1], (h32 * h32).sum(1), rtol=1e-4, atol=2e-2)
@@ -149,13 +149,13 @@ def test_gemm_layernorm_fusion(ops, M, N, K, geglu):
         got = ops.gemm(h, wp.to(DEV), b2.to(DEV), ln_stats=stats, ln_colsum=colsum_bf16(wp).to(DEV), ln_eps=1e-5)
     assert rel_l2(got.float(), want) < 8e-3
     # buffer rotation without memsets: the consumer clears a third buffer, a later producer accumulates into it
-    third = torch.full((2 * M,), 7.0, device=DEV)
+    third = torch.full((2 * M,), 7.0, device=DEV, dtype=torch.float64)
     if not geglu:
         again = ops.gemm(h, wp.to(DEV), b2.to(DEV), ln_stats=stats, ln_colsum=colsum_bf16(wp).to(DEV), ln_eps=1e-5,
                          zero_rows=third)
         assert torch.equal(again, got) and torch.count_nonzero(third).item() == 0
         ops.gemm(a0.to(DEV), w0.to(DEV), b0.to(DEV), residual=res.to(DEV), row_stats_out=third, row_stats_zeroed=True)
-        assert torch.allclose(third, stats, rtol=1e-5, atol=1e-3)
+        assert torch.equal(third, stats)          # fp64 sums of fp32 partials: exact, hence order-independent
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(2, 16, 24, 64, 128, 1), (2, 19, 13, 128, 64, 1),
