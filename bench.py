@@ -123,6 +123,14 @@ def config_panels(name):
     return [(2, 16, 24, 2, True, False)]          # tiny: plumbing self-test only
 
 
+def shard_inputs(inp, start, end):
+    """Rows [start, end) of a CFG-concatenated global batch [neg(0..bs) ; pos(0..bs)] -> the same layout for the shard."""
+    lat, ehs, pooled, time_ids, bbox, dialog = inp
+    bs = lat.shape[0]
+    pick = lambda t: None if t is None else torch.cat([t[start:end], t[bs + start:bs + end]], 0)
+    return lat[start:end], pick(ehs), pick(pooled), pick(time_ids), pick(bbox), pick(dialog)
+
+
 def synthetic_inputs(cfg, bs, h, w, n_chars, device, dialogs=False, mllm=False):
     """SURVEY.md §8d synthetic conditions (seeds fixed); embeddings stand in for the out-of-scope encoders.
     ``mllm``: the positive image tokens of the real characters are ``0.4 g + 0.6 e`` — MLLM-adapted embeddings g
@@ -573,7 +581,15 @@ def run_ours(args):
     torch.cuda.empty_cache()
     engine.set_ip_scale(IP_SCALE)
     pipe = ds.DiffSenseiPipeline(engine)
-    inputs = [synthetic_inputs(cfg, bs, h, w, nc, dev, dialogs=dlg, mllm=ml) for bs, h, w, nc, dlg, ml in groups]
+    # N > 1 (cfg4 = bs 32 over 8 GPUs): ONE global batch of bs * world panels (every rank builds the same seeded global
+    # tensors), sharded contiguously with parallel.shard_range; the final latents are all-gathered in panel order
+    inputs, shards = [], []
+    for bs, h, w, nc, dlg, ml in groups:
+        glob = synthetic_inputs(cfg, bs * world, h, w, nc, dev, dialogs=dlg, mllm=ml)
+        s0, s1 = parallel.shard_range(bs * world, world, rank)
+        assert s1 - s0 == bs
+        shards.append((s0, s1))
+        inputs.append(shard_inputs(glob, s0, s1) if world > 1 else glob)
     steppers = [pipe.make_stepper(*inp[:5], g[1] / g[2], inp[5], T_STEPS, GUIDANCE, use_graph=True, chains=args.chains)
                 for g, inp in zip(groups, inputs)]
     stepper = steppers[0]
@@ -650,12 +666,33 @@ def run_ours(args):
         torch.cuda.synchronize()
         t_p = time.perf_counter() - t_p
         t_p = parallel.max_over_ranks(t_p, dev)
+        # ... and the step right after the loop (pipeline_diffsensei.py:339-363): latents / scaling_factor -> VAE decode
+        # -> post-process, on the SDXL-size decoder (random-init weights), per panel batch
+        vae_ms = None
+        if args.config in ("cfg2", "cfg1", "tiny"):
+            from diffsensei_b200.weights import vae_decoder_param_shapes
+            vcfg = ds.SDXL_VAE if args.config != "tiny" else ds.TINY_VAE
+            vae = ds.VaeDecoderEngine(vcfg, dev)
+            vae.load_state_dict(random_state_dict(vae_decoder_param_shapes(vcfg), seed=99, device=dev, dtype=torch.bfloat16))
+            lat_fin = stepper.latents_nchw()
+            vae.decode_image(lat_fin)
+            torch.cuda.synchronize()
+            tv = time.perf_counter()
+            img = vae.decode_image(lat_fin)
+            img_host = img.cpu()
+            vae_ms = (time.perf_counter() - tv) * 1e3
+            assert img_host.shape == (g0[0], 3, g0[1] * 8, g0[2] * 8)
+            del vae, img
+            torch.cuda.empty_cache()
         panel = {"panels_per_sec": round(world * n_pan * g0[0] / t_p, 4), "unit": "panels/s",
                  "panel_batches": n_pan, "panels_per_batch": g0[0], "steps_per_panel": T_STEPS,
                  "sec_per_panel_batch": round(t_p / n_pan, 4),
                  "setup_ms_per_panel_batch": round(t_set * 1e3, 2),
                  "setup_share": round(t_set / (t_p / n_pan), 5),
                  "first_panel_with_graph_capture_s": round(t_cap, 3),
+                 "vae_decode_ms_per_panel_batch": None if vae_ms is None else round(vae_ms, 2),
+                 "panels_per_sec_incl_vae_decode": None if vae_ms is None else
+                 round(world * n_pan * g0[0] / (t_p + n_pan * vae_ms * 1e-3), 4),
                  "how": "wall clock around DiffSenseiPipeline.denoise x panel_batches (host latents in / out, "
                         "prepare_conditions + time-embedding table + graph-buffer refill inside, CUDA graph re-used)"}
 
@@ -672,8 +709,10 @@ def run_ours(args):
         eager0 = eager0 or eager
 
     # one NCCL all-gather of the final latents (outside the timed region): the only collective of the path
-    final = parallel.gather_latents(stepper.latents_nchw(), [groups[0][0]] * world)
+    mine = stepper.latents_nchw()
+    final = parallel.gather_latents(mine, [groups[0][0]] * world)
     assert final.shape[0] == groups[0][0] * world
+    assert torch.equal(final[shards[0][0]:shards[0][1]], mine)       # gathered in global panel order
 
     extra = {}
     if rank == 0 and args.config == "cfg2" and not args.no_kernel_rooflines:
@@ -724,7 +763,9 @@ def run_ours(args):
                                        f"ip_scale {IP_SCALE}" + (", dialog boxes" if groups[0][4] else "")
                                        + (", MLLM-adapted image tokens" if groups[0][5] else ""),
                            "weights": "random-init SDXL+IP topology (2.908 B params), bf16",
-                           "parallelism": f"dp{world} (panel shards, no per-step collective)",
+                           "parallelism": f"dp{world}: one global batch of {bs_total * world} panels, contiguous shards of "
+                                          f"{bs_total} per GPU (parallel.shard_range), no per-step collective, final "
+                                          "latents all-gathered in panel order",
                            "l2": "working set per step (5.8 GB weights + activations) >> 126 MB L2; no explicit flush",
                            "hoisted": "text/IP K|V projections (0.86 TFLOP/step) and time embeddings are computed "
                                       "once per panel, outside the timed step (inside the measured `panel` leg)"},

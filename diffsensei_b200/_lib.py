@@ -64,6 +64,7 @@ SIGNATURES = {
     "ds_gemm_bf16": [C.POINTER(GemmArgs), _vp],
     "ds_conv3x3_nhwc": [C.POINTER(Conv3x3Args), _vp],
     "ds_conv_in_3x3": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "ds_im2col_latent": [_vp, _vp, _i, _i, _i, _vp],
     "ds_attention_self": [_vp, _vp, _i, _i, _i, _vp],
     "ds_attention_cross_ip": [C.POINTER(CrossIpArgs), _vp],
     "ds_nchw_to_nhwc": [_vp, _i, _vp, _i, _i, _i, _i, _vp],

@@ -1,36 +1,16 @@
 // attn_tcgen05.cu — fused attention for head_dim 64 on tcgen05 tensor cores (sm_100a).
 //
-// Kernels in this file (defaults first; the older variants stay selectable for A/B timing and as fallbacks):
-//   flash_attn_v5_kernel     self-attention / Resampler attention, DEFAULT (DS_FLASH=5): two independent
-//                            online-softmax streams per CTA, S / O / P all in TMEM (section 1d)
-//   flash_attn_kernel        the round-1 self-attention kernel (DS_FLASH=2): P through shared memory (section 1)
-//   cross_ip_attn_v2_kernel  text + bbox-masked IP cross-attention, DEFAULT: persistent, two softmax warp groups,
-//                            P in TMEM (section 2b)
-//   cross_ip_attn_kernel     one-tile-per-CTA version (DS_CROSS=1, and the fallback when the padded key counts do
-//                            not fit v2's TMEM layout) (section 2)
-//
-// (1) flash_attn_kernel — softmax(Q K^T * scale) V with an online softmax, no mask (self-attention of
-//     AttnProcessor2_0, src/models/attention_processor.py:69-81; also used for the Resampler's perceiver
-//     attention, src/models/resampler.py:64-74).  One CTA = one 128-query tile of one (batch, head);
-//     two CTAs are co-resident per SM so one CTA's softmax overlaps the other's MMAs.
-//       warp 0   TMA producer : Q once, then K_j / V_j (128 x 64 tiles, 128-B swizzle) through a 3-slot ring
-//       warp 1   MMA issuer   : S = Q K_j^T (M128 N128 K64) into TMEM; O (+)= P_j V_j (M128 N64 K128),
-//                               V consumed MN-major straight from its [kv][d] TMA tile
-//       warp 2   TMEM allocator (256 columns: S 0..127, O 128..191)
-//       warps 4-11 softmax    : 2 threads per query row (64 key columns each).  tcgen05.ld S, running max in the
-//                               log2 domain with LAZY rescaling (O/l are only rescaled when the row max grows by
-//                               > 2^8), exp2, P_j -> bf16 into swizzled shared memory as the next MMA's A operand.
-//                               O never leaves TMEM until the final 1/l normalisation.
-//     Q/K/V are addressed by 3-D tensor maps {columns, tokens, batch} over the fused projection output, so
-//     the head split/transposes of the reference (:69-72,80) are never materialised.
-//
-// (2) cross_ip_attn_kernel — out = softmax(Q Kt^T/8) Vt + scale * softmax(Q Kip^T/8 + M(bbox)) Vip
-//     (MaskedIPAttnProcessor2_0, src/models/attention_processor.py:231-258) in ONE pass: text and IP keys are
-//     concatenated along the key axis in shared memory (<= 192 keys), one S = Q [Kt;Kip]^T MMA chain, two
-//     independent softmaxes per row (unnormalised P in smem, two passes over S), two PV chains into separate
-//     TMEM accumulators (O_ip re-uses the dead S columns), and 1/l_text, scale/l_ip applied in the epilogue.
-//     The additive bbox mask M in {0,-10000} (:115-169) is evaluated in registers from the 4 boxes with the
-//     reference's closed-interval / derived-(H',W') semantics (ip_mask.cuh) and never touches memory.
+// Kernels in this file:
+//   flash_attn_v5_kernel     self-attention (AttnProcessor2_0, src/models/attention_processor.py:69-81) and the
+//                            Resampler's perceiver attention (src/models/resampler.py:64-74): softmax(Q K^T * scale) V,
+//                            no mask.  Two independent online-softmax streams per CTA, S / O / P all in TMEM (section 1).
+//                            Q/K/V are addressed by 3-D tensor maps {columns, tokens, batch} over the fused projection
+//                            output, so the head split / transposes of the reference are never materialised.
+//   cross_ip_attn_v2_kernel  out = softmax(Q Kt^T/8) Vt + scale * softmax(Q Kip^T/8 + M(bbox)) Vip
+//                            (MaskedIPAttnProcessor2_0, :231-258) in ONE pass: persistent, two softmax warp groups,
+//                            P in TMEM; the additive bbox mask M in {0,-10000} (:115-169) is evaluated in registers
+//                            with the reference's closed-interval / derived-(H',W') semantics (ip_mask.cuh) (section 2).
+// The round-1 kernels these replaced (P through shared memory; one tile per CTA) are in git history (commit 8e22d8c).
 #include <cstdlib>
 
 #include "ds_common.cuh"
@@ -39,12 +19,10 @@
 
 namespace ds {
 
-constexpr int kAttnThreads = 256;
 constexpr int kTile = 128;            // query rows per CTA == kv rows per tile
 constexpr int kHd = 64;               // head dim
 constexpr int kTileBytes = kTile * kHd * 2;  // 16 KiB
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kRescaleThreshold = 8.0f;  // log2 domain
 
 // swizzled (SWIZZLE_128B) byte offset of 16-byte chunk `q16` (0..7) of row `r` inside a [rows][64 bf16] atom
 __device__ __forceinline__ uint32_t sw128_off(int r, int q16) { return r * 128 + ((q16 ^ (r & 7)) << 4); }
@@ -81,303 +59,9 @@ struct FlashParams {
 };
 
 // =================================================================================================
-// (1) flash attention
-// =================================================================================================
-constexpr int kFlashThreads = 384;  // 4 control warps + 8 softmax warps (2 threads per query row)
-
-__global__ void __launch_bounds__(kFlashThreads, 2)
-flash_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
-  constexpr int RING = 3;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
-  uint8_t* sRing = sQ + kTileBytes;          // RING x 16 KiB, K_0 V_0 K_1 V_1 ...
-  uint8_t* sP = sRing + RING * kTileBytes;   // 2 atoms x 16 KiB: P[128][128] bf16, K-major
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kTileBytes);
-  uint64_t* q_full = bars;
-  uint64_t* full = bars + 1;           // [RING]
-  uint64_t* empty = full + RING;       // [RING]
-  uint64_t* s_full = empty + RING;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* s_xchg = reinterpret_cast<float*>(tmem_slot + 2);  // [2][128] per-row exchange between the two column halves
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTile;
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int num_kv_tiles = (p.Nkv + kTile - 1) / kTile;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < RING; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
-    mbar_init(o_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, 256);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;        // columns [0,128)
-  const uint32_t tO = tmem_base + 128;  // columns [128,192)
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kTileBytes);
-      tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + head * kHd, q0, batch);
-      int slot = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < num_kv_tiles; ++j) {
-        for (int which = 0; which < 2; ++which) {  // K_j then V_j
-          mbar_wait(&empty[slot], ph ^ 1);
-          mbar_arrive_expect_tx(&full[slot], kTileBytes);
-          tma_load_3d(sRing + slot * kTileBytes, which == 0 ? &tmK : &tmV, &full[slot],
-                      (which == 0 ? p.k_col0 : p.v_col0) + head * kHd, j * kTile, batch);
-          if (++slot == RING) {
-            slot = 0;
-            ph ^= 1;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = make_idesc_bf16(kTile, kTile, 0, 0);  // M128 N128, both K-major
-      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);    // M128 N64, B (=V) MN-major
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t p_addr = smem_u32(sP);
-      int slot = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < num_kv_tiles; ++j) {
-        // ---- S = Q K_j^T
-        mbar_wait(&full[slot], ph);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sRing + slot * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kHd / 16; ++k)
-          umma_ss(tS, make_sw128_desc(q_addr + k * 32, 1024, 16), make_sw128_desc(k_addr + k * 32, 1024, 16),
-                  idesc_qk, k != 0 ? 1u : 0u);
-        umma_commit(&empty[slot]);
-        umma_commit(s_full);
-        if (++slot == RING) {
-          slot = 0;
-          ph ^= 1;
-        }
-        // ---- O (+)= P_j V_j
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        mbar_wait(&full[slot], ph);
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(sRing + slot * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kTile / 16; ++k) {
-          const uint64_t adesc = make_sw128_desc(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 1024, 16);
-          const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048, 1024, 1024);
-          umma_ss(tO, adesc, bdesc, idesc_pv, (j | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&empty[slot]);
-        if (++slot == RING) {
-          slot = 0;
-          ph ^= 1;
-        }
-      }
-      umma_commit(o_full);
-    }
-  } else if (warp >= 4) {
-    // ---------------------------------------------------------------- softmax: 8 warps, 2 threads per query row.
-    // warp -> TMEM lane quadrant (warp & 3) and key-column half ((warp-4)>>2): thread (row, half) owns columns
-    // [64*half, 64*half+64) of S, i.e. exactly one 64-wide swizzle atom of P.
-    const int wq = warp & 3;
-    const int half = (warp - 4) >> 2;
-    const int row = wq * 32 + lane;
-    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t tSh = tS + lane_base + half * 64;
-    uint8_t* atom = sP + half * kTileBytes;
-    float m_ref = -INFINITY, l = 0.f;  // m_ref is identical in both threads of a row; l is this thread's partial
-
-    auto bar_softmax = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-    // CTA-wide OR over the 256 softmax threads (named barrier 2 with reduction)
-    auto any_softmax = [&](bool v) -> bool {
-      uint32_t r;
-      asm volatile(
-          "{\n"
-          ".reg .pred pin, pout;\n"
-          "setp.ne.u32 pin, %1, 0;\n"
-          "barrier.cta.red.or.pred pout, 2, 256, pin;\n"
-          "selp.u32 %0, 1, 0, pout;\n"
-          "}\n"
-          : "=r"(r)
-          : "r"(static_cast<uint32_t>(v))
-          : "memory");
-      return r != 0;
-    };
-
-    // One sweep over this thread's 64 columns of S: P = 2^(S*scale - m) -> bf16 -> swizzled smem.  Returns the
-    // partial row sum and (via t_max) the largest exponent seen.
-    auto sweep = [&](float neg_m, int kv_valid, float& t_max) -> float {
-      const bool full_tile = kv_valid >= kTile;  // CTA-uniform
-      float lsum = 0.f, tm = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(tSh + c * 32, raw);
-        tmem_ld_wait();
-        uint32_t pk[16];
-        if (full_tile) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
-            const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
-            tm = fmaxf(tm, fmaxf(t0, t1));
-            const float e0 = ex2(t0), e1 = ex2(t1);
-            lsum += e0 + e1;
-            pk[i] = pack_bf16_alu(e0, e1);
-          }
-        } else {
-          const int col0 = half * 64 + c * 32;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float t0 = fmaf(__uint_as_float(raw[2 * i]), p.scale_log2, neg_m);
-            const float t1 = fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2, neg_m);
-            float e0 = 0.f, e1 = 0.f;
-            if (col0 + 2 * i < kv_valid) {
-              tm = fmaxf(tm, t0);
-              e0 = ex2(t0);
-            }
-            if (col0 + 2 * i + 1 < kv_valid) {
-              tm = fmaxf(tm, t1);
-              e1 = ex2(t1);
-            }
-            lsum += e0 + e1;
-            pk[i] = pack_bf16_alu(e0, e1);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          st_shared_16(atom + sw128_off(row, c * 4 + q), pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-      }
-      t_max = tm;
-      return lsum;
-    };
-
-    for (int j = 0; j < num_kv_tiles; ++j) {
-      const int kv_valid = p.Nkv - j * kTile;  // >= 128: whole tile valid
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      float lsum, t_max;
-      if (j == 0) {
-        // first tile: exact row max (each half scans its 64 columns, the two halves meet in smem)
-        float mx = -INFINITY;
-        {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(tSh, r0);
-          tmem_ld32(tSh + 32, r1);
-          tmem_ld_wait();
-          const int col0 = half * 64;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (col0 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r0[i]));
-            if (col0 + 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r1[i]));
-          }
-        }
-        s_xchg[half * kTile + row] = mx;
-        bar_softmax();
-        m_ref = fmaxf(s_xchg[row], s_xchg[kTile + row]) * p.scale_log2;
-        bar_softmax();  // s_xchg is reused below
-        lsum = sweep(-m_ref, kv_valid, t_max);
-      } else {
-        // OPTIMISTIC single sweep against the running reference max.  Correct as long as no score of this tile
-        // exceeds m_ref by more than 2^8 (P <= 256 is exact enough in bf16 and cannot overflow); otherwise the
-        // affected rows move their reference, O and l are rescaled, and the sweep is redone.
-        lsum = sweep(-m_ref, kv_valid, t_max);
-        if (any_softmax(t_max > kRescaleThreshold)) {  // CTA-uniform
-          s_xchg[half * kTile + row] = t_max;
-          bar_softmax();
-          const float row_t = fmaxf(s_xchg[row], s_xchg[kTile + row]);
-          bar_softmax();
-          float alpha = 1.0f;
-          if (row_t > kRescaleThreshold) {
-            alpha = ex2(-row_t);  // 2^(m_ref_old - m_ref_new)
-            m_ref += row_t;
-            l *= alpha;
-          }
-          if (half == 0) {  // warps 4-7 rescale their quadrant's 32 rows of O in TMEM
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t raw[32];
-              tmem_ld32(tO + lane_base + c * 32, raw);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
-              tmem_st32(tO + lane_base + c * 32, raw);
-            }
-            tmem_st_wait();
-          }
-          lsum = sweep(-m_ref, kv_valid, t_max);
-        }
-      }
-      l += lsum;
-      fence_proxy_async_smem();  // st.shared -> visible to the tensor core's async-proxy reads
-      tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    // ---- epilogue: O / l -> bf16 -> global; each thread of a row writes 32 of its 64 output columns
-    s_xchg[half * kTile + row] = l;
-    bar_softmax();
-    const float inv_l = 1.0f / (s_xchg[row] + s_xchg[kTile + row]);
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const int q_row = q0 + row;
-    __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.Nq + q_row) * p.ldo + head * kHd + half * 32;
-    uint32_t raw[32];
-    tmem_ld32(tO + lane_base + half * 32, raw);
-    tmem_ld_wait();
-    if (q_row < p.Nq) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 u;
-        u.x = pack_bf16(__uint_as_float(raw[q * 8 + 0]) * inv_l, __uint_as_float(raw[q * 8 + 1]) * inv_l);
-        u.y = pack_bf16(__uint_as_float(raw[q * 8 + 2]) * inv_l, __uint_as_float(raw[q * 8 + 3]) * inv_l);
-        u.z = pack_bf16(__uint_as_float(raw[q * 8 + 4]) * inv_l, __uint_as_float(raw[q * 8 + 5]) * inv_l);
-        u.w = pack_bf16(__uint_as_float(raw[q * 8 + 6]) * inv_l, __uint_as_float(raw[q * 8 + 7]) * inv_l);
-        reinterpret_cast<uint4*>(orow)[q] = u;
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
-
-constexpr int kFlashSmemBytes = kTileBytes * (1 + 3 + 2) + 1024 + 128 + 2 * kTile * 4;
-
-// =================================================================================================
 // Shared by the TMEM-P flash kernels.  History of the self-attention kernel at B8 N4096 h10 (all measured on B200,
 // sources in git history, analysis in profiles/r01_ncu_flash_v3.md):
-//   v2 (below: P through shared memory, 2 threads per row)                                    634 us
+//   v2 (git history: P through shared memory, 2 threads per row)                              634 us
 //   v3 (P in TMEM via tcgen05.st + ts-form PV MMA, 1 thread per row, sum-bounded lazy rescale) 562 us
 //   v4 (v3 + the kv tile pipelined through the MMA warp in two 64-key halves)                  559 us
 //   v5 (two independent online-softmax streams per CTA)                                        436 us
@@ -399,7 +83,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
 }
 
 // =================================================================================================
-// (1d) flash attention v5 — two INDEPENDENT online-softmax streams per CTA.
+// (1) flash attention v5 — two INDEPENDENT online-softmax streams per CTA.
 //      ncu on v3/v4 (profiles/r01_ncu_flash_v3.md): with one softmax warp per SM sub-partition per CTA the exp
 //      loop is a single dependent instruction stream (issue: selected 33 % / fixed-latency wait 35 %), i.e. bound
 //      by per-warp issue latency, not by the MUFU or the tensor pipe — which is also why moving exponentials to
@@ -539,14 +223,25 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (more) mbar_wait(&full[kslot], (ki / RING) & 1);  // K_{j+1}
         const uint32_t v_addr = smem_u32(sRing + vslot * kTileBytes);
         const uint32_t k_addr = smem_u32(sRing + kslot * kTileBytes);
+        // serve whichever stream has its P ready first (no head-of-line blocking behind the slower stream); both
+        // streams of tile j use the same V_j / K_{j+1} slots, which are released after the second one is served
+        int first = 0;
+        for (;;) {
+          if (mbar_try_wait(&p_full[0], j & 1)) break;
+          if (mbar_try_wait(&p_full[1], j & 1)) {
+            first = 1;
+            break;
+          }
+        }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&p_full[h], j & 1);
+        for (int o = 0; o < 2; ++o) {
+          const int h = o == 0 ? first : 1 - first;
+          if (o == 1) mbar_wait(&p_full[h], j & 1);
           tc_fence_after();
           issue_pv(v_addr, h, j == 0);
-          if (h == 1) umma_commit(&empty[vslot]);
+          if (o == 1) umma_commit(&empty[vslot]);
           if (more) issue_s(k_addr, h);  // executes after PV_h(j): P_h(j) is consumed before S_h(j+1) overwrites it
-          if (more && h == 1) umma_commit(&empty[kslot]);
+          if (more && o == 1) umma_commit(&empty[kslot]);
         }
       }
       umma_commit(o_full);
@@ -716,225 +411,8 @@ struct CrossParams {
   float ip_scale;
 };
 
-__global__ void __launch_bounds__(kAttnThreads, 2)
-cross_ip_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKVt,
-                     const __grid_constant__ CUtensorMap tmKVip, const CrossParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  const int n_keys = p.nt_pad + p.nip_pad;          // multiple of 16, <= 192
-  const int kv_bytes = n_keys * 128;                // [n_keys][64] bf16
-  const int p_atoms = (n_keys + 63) / 64;
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kTileBytes;
-  uint8_t* sV = sK + ((kv_bytes + 1023) & ~1023);
-  uint8_t* sP = sV + ((kv_bytes + 1023) & ~1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + p_atoms * kTileBytes);
-  uint64_t* ld_full = bars;
-  uint64_t* s_full = bars + 1;
-  uint64_t* p_full = bars + 2;
-  uint64_t* o_full = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTile;
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmKVt);
-    tma_prefetch_desc(&tmKVip);
-  }
-  if (warp == 1 && lane == 0) {
-    mbar_init(ld_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, 256);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;        // columns [0, n_keys)
-  const uint32_t tO = tmem_base + 192;  // columns [192, 256)
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(ld_full, kTileBytes + 2 * kv_bytes);
-      tma_load_3d(sQ, &tmQ, ld_full, head * kHd, q0, batch);
-      // keys: [text | ip] stacked along the key axis; values likewise (V = second half of the kv columns)
-      tma_load_3d(sK, &tmKVt, ld_full, head * kHd, 0, batch);
-      tma_load_3d(sK + p.nt_pad * 128, &tmKVip, ld_full, head * kHd, 0, batch);
-      tma_load_3d(sV, &tmKVt, ld_full, p.C + head * kHd, 0, batch);
-      tma_load_3d(sV + p.nt_pad * 128, &tmKVip, ld_full, p.C + head * kHd, 0, batch);
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_qk = make_idesc_bf16(kTile, n_keys, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);
-      mbar_wait(ld_full, 0);
-      tc_fence_after();
-      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
-#pragma unroll
-      for (int k = 0; k < kHd / 16; ++k)
-        umma_ss(tS, make_sw128_desc(q_addr + k * 32, 1024, 16), make_sw128_desc(k_addr + k * 32, 1024, 16), idesc_qk,
-                k != 0 ? 1u : 0u);
-      umma_commit(s_full);
-      mbar_wait(p_full, 0);
-      tc_fence_after();
-      // two accumulators: O_text (columns 192..255) and O_ip (columns 0..63: S is dead once P is in smem)
-      const int kt = p.nt_pad / 16;
-      for (int k = 0; k < n_keys / 16; ++k) {
-        const uint64_t adesc = make_sw128_desc(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 1024, 16);
-        const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048, 1024, 1024);
-        if (k < kt)
-          umma_ss(tO, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
-        else
-          umma_ss(tS, adesc, bdesc, idesc_pv, k != kt ? 1u : 0u);
-      }
-      umma_commit(o_full);
-    }
-  } else if (warp >= 4) {
-    const int wq = warp & 3;
-    const int row = wq * 32 + lane;
-    const int q_row = q0 + row;
-    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t bits =
-        ip_inside_bits(p.bbox + static_cast<size_t>(batch) * p.num_ips * 4, p.num_ips, min(q_row, p.N - 1), p.Hd, p.Wd);
-    // log2-domain scores: t = s * (1/8) * log2(e) + M * log2(e),  M in {0, -10000} (reference :142,162-163)
-    constexpr float kS2 = 0.125f * kLog2e;
-    constexpr float kMask2 = -10000.0f * kLog2e;
-    const int chunks = n_keys / 16;
-    const int t_chunks = p.nt_pad / 16;
-    // chunk-uniform masks when the 16-column chunks line up with the per-character key blocks (SDXL: 16/16)
-    const bool uniform = (p.tokens_per_ip % 16 == 0) && (p.num_dummy % 16 == 0);
-
-    // additive term of column i of chunk c, and number of valid (non-padding) columns in the chunk
-    auto chunk_valid = [&](int c) -> int {
-      const int v = (c < t_chunks) ? p.n_text - c * 16 : p.n_ip - (c - t_chunks) * 16;
-      return v < 0 ? 0 : (v > 16 ? 16 : v);
-    };
-    auto chunk_add = [&](int c) -> float {  // only meaningful when `uniform`
-      if (c < t_chunks) return 0.0f;
-      return ip_key_open(bits, (c - t_chunks) * 16, p.tokens_per_ip, p.num_dummy) ? 0.0f : kMask2;
-    };
-    auto elem_add = [&](int c, int i) -> float {  // general path
-      if (c < t_chunks) return 0.0f;
-      return ip_key_open(bits, (c - t_chunks) * 16 + i, p.tokens_per_ip, p.num_dummy) ? 0.0f : kMask2;
-    };
-
-    mbar_wait(s_full, 0);
-    tc_fence_after();
-    // ---- pass 1: the two row maxima
-    float m_t = -INFINITY, m_i = -INFINITY;
-    for (int c = 0; c < chunks; ++c) {
-      uint32_t raw[16];
-      tmem_ld16(tS + lane_base + c * 16, raw);
-      tmem_ld_wait();
-      const int nv = chunk_valid(c);
-      float mx = -INFINITY;
-      if (uniform && nv == 16) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
-        mx = fmaf(mx, kS2, chunk_add(c));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < nv) mx = fmaxf(mx, fmaf(__uint_as_float(raw[i]), kS2, uniform ? chunk_add(c) : elem_add(c, i)));
-      }
-      if (c < t_chunks)
-        m_t = fmaxf(m_t, mx);
-      else
-        m_i = fmaxf(m_i, mx);
-    }
-    // ---- pass 2: unnormalised P = 2^(t - m) -> bf16 -> swizzled smem; row sums
-    float l_t = 0.f, l_i = 0.f;
-    for (int c = 0; c < chunks; ++c) {
-      uint32_t raw[16];
-      tmem_ld16(tS + lane_base + c * 16, raw);
-      tmem_ld_wait();
-      const int nv = chunk_valid(c);
-      const float m = c < t_chunks ? m_t : m_i;
-      uint32_t pk[8];
-      float sum = 0.f;
-      if (uniform && nv == 16) {
-        const float off = chunk_add(c) - m;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), kS2, off));
-          const float e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), kS2, off));
-          sum += e0 + e1;
-          pk[i] = pack_bf16_alu(e0, e1);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float e0 = 0.f, e1 = 0.f;
-          if (2 * i < nv)
-            e0 = ex2(fmaf(__uint_as_float(raw[2 * i]), kS2, (uniform ? chunk_add(c) : elem_add(c, 2 * i)) - m));
-          if (2 * i + 1 < nv)
-            e1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), kS2, (uniform ? chunk_add(c) : elem_add(c, 2 * i + 1)) - m));
-          sum += e0 + e1;
-          pk[i] = pack_bf16_alu(e0, e1);
-        }
-      }
-      if (c < t_chunks)
-        l_t += sum;
-      else
-        l_i += sum;
-      uint8_t* atom = sP + (c >> 2) * kTileBytes;
-      st_shared_16(atom + sw128_off(row, (c & 3) * 2), pk[0], pk[1], pk[2], pk[3]);
-      st_shared_16(atom + sw128_off(row, (c & 3) * 2 + 1), pk[4], pk[5], pk[6], pk[7]);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    mbar_arrive(p_full);
-
-    // ---- epilogue: out = O_text / l_t + scale * O_ip / l_i      (blend BEFORE to_out, reference :258)
-    const float w_t = 1.0f / l_t, w_i = p.ip_scale / l_i;
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.N + q_row) * p.C + head * kHd;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t rt[32], ri[32];
-      tmem_ld32(tO + lane_base + c * 32, rt);
-      tmem_ld32(tS + lane_base + c * 32, ri);
-      tmem_ld_wait();
-      if (q_row < p.N) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            o[e] = fmaf(__uint_as_float(rt[q * 8 + e]), w_t, __uint_as_float(ri[q * 8 + e]) * w_i);
-          uint4 u;
-          u.x = pack_bf16(o[0], o[1]);
-          u.y = pack_bf16(o[2], o[3]);
-          u.z = pack_bf16(o[4], o[5]);
-          u.w = pack_bf16(o[6], o[7]);
-          reinterpret_cast<uint4*>(orow + c * 32)[q] = u;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
-  }
-}
-
 // =================================================================================================
-// (2b) cross_ip_attn_v2_kernel — same arithmetic as cross_ip_attn_kernel, restructured because the one-tile-per-CTA
+// (2) cross_ip_attn_v2_kernel — restructured in round 1 because the one-tile-per-CTA
 //      version was latency-bound (one serial load -> S -> softmax -> PV -> store chain per CTA lifetime; 4-7x off its
 //      HBM floor, profiles/r01_ncu_summary.md):
 //        * persistent: 2 CTAs per SM, CTA c owns a contiguous range of (batch, head, q-tile) items, so K|V of a
@@ -1158,8 +636,9 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       };
       {
         // single register buffer: the 4 softmax warps per SM sub-partition (2 groups x 2 CTAs) hide the TMEM load
-        // latency; a second buffer pushed the kernel over its 96-register budget and the spill reloads (local
-        // memory = L2 round trips, the L1 carve-out is nearly all shared memory) sat on the per-tile critical path
+        // latency.  MEASURED (round 2): software-pipelining the loads one chunk ahead through a second 16-register
+        // buffer costs 3 spilled registers at the kernel's 96-register budget and LOSES: 57.0 -> 65.5 us at B8 N4096
+        // h10, 33.4 -> 36.9 us at B8 N1024 h20 (spill reloads are L2 round trips: the L1 carve-out is all shared memory)
         uint32_t ra[16];
 #pragma unroll 1
         for (int c = 0; c < chunks; ++c) {
@@ -1242,11 +721,6 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
   if (!make_tok_map(&tmQ, q, q_cols, ldq, Nq, B, kTile)) return DS_ERR_CUDA;
   if (!make_tok_map(&tmK, k, kv_cols, ldkv, Nkv, B, kTile)) return DS_ERR_CUDA;
   if (!make_tok_map(&tmV, v, kv_cols, ldkv, Nkv, B, kTile)) return DS_ERR_CUDA;
-  static bool attr_set[kMaxDevices] = {};
-  if (!attr_set[device_slot()]) {
-    DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlashSmemBytes));
-    attr_set[device_slot()] = true;
-  }
   FlashParams p;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.Nq = Nq;
@@ -1257,22 +731,12 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
   p.v_col0 = v_col0;
   p.scale_log2 = scale * kLog2e;
   dim3 grid((Nq + kTile - 1) / kTile, heads, B);
-  // DS_FLASH=2 selects the round-1 kernel (P through shared memory, 2 threads per row) for A/B timing;
-  // DS_FLASH_POLY=n sends n of every 8 exponentials to the FMA pipe (v5)
-  static const int flash_ver = [] {
-    const char* e = getenv("DS_FLASH");
-    return e ? atoi(e) : 5;
-  }();
+  // DS_FLASH_POLY=n sends n of every 8 exponentials to the FMA pipe (measured neutral: profiles/r02_attn_sweep.log)
   static const int flash_poly = [] {
     const char* e = getenv("DS_FLASH_POLY");
     return e ? atoi(e) : 0;
   }();
-  if (flash_ver == 2) {
-    flash_attn_kernel<<<grid, kFlashThreads, kFlashSmemBytes, st>>>(tmQ, tmK, tmV, p);
-    DS_LAUNCH_OK("flash_attn_kernel");
-    return DS_OK;
-  }
-  if (flash_ver >= 5 || flash_ver <= 0) {
+  {
     static const int flash_f2 = [] {  // DS_FLASH_F2=0: scalar FFMA/FADD instead of the packed fp32x2 forms
       const char* e = getenv("DS_FLASH_F2");
       return e ? atoi(e) : 1;
@@ -1306,8 +770,6 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
     DS_LAUNCH_OK("flash_attn_v5_kernel");
     return DS_OK;
   }
-  set_error("ds_attention: DS_FLASH=%d is not built (2 = shared-memory-P kernel, 5 = default)", flash_ver);
-  return DS_ERR_INVALID;
 }
 
 }  // namespace ds
@@ -1363,13 +825,10 @@ extern "C" int ds_attention_cross_ip(const ds_cross_ip_args* a, void* stream) {
   if (!make_tok_map(&tmI, a->kv_ip, 2 * C, 2 * C, a->n_ip, a->B, nip_pad)) return DS_ERR_CUDA;
   const int n_keys = nt_pad + nip_pad;
   const int kv_bytes = ((n_keys * 128) + 1023) & ~1023;
-  const int smem = kTileBytes + 2 * kv_bytes + ((n_keys + 63) / 64) * kTileBytes + 1024 + 128;
-  static int attr_smem_dev[kMaxDevices] = {};
-  int& attr_smem = attr_smem_dev[device_slot()];
-  if (smem > attr_smem) {
-    DS_CUDA_OK(cudaFuncSetAttribute(cross_ip_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  // TMEM layout of the kernel: P_ip must end below column 128 (77 text + 80 IP keys: 80 + 40 = 120)
+  DS_REQUIRE(nt_pad + nip_pad / 2 <= 128,
+             "ds_attention_cross_ip: padded key counts (%d text, %d ip) do not fit the kernel's TMEM layout "
+             "(text + ip/2 <= 128)", nt_pad, nip_pad);
   CrossParams p;
   p.out = static_cast<__nv_bfloat16*>(a->out);
   p.bbox = a->bbox;
@@ -1385,12 +844,7 @@ extern "C" int ds_attention_cross_ip(const ds_cross_ip_args* a, void* stream) {
   p.Hd = Hd;
   p.Wd = Wd;
   p.ip_scale = a->ip_scale;
-  // DS_CROSS=1 selects the round-1 one-tile-per-CTA kernel (A/B timing); default: persistent v2
-  static const int cross_ver = [] {
-    const char* e = getenv("DS_CROSS");
-    return e ? atoi(e) : 2;
-  }();
-  if (cross_ver != 1 && nt_pad + nip_pad / 2 <= 128) {  // v2's TMEM layout needs P_ip to end below column 128
+  {
     const int q_tiles = (a->N + kTile - 1) / kTile;
     const long long total_ll = static_cast<long long>(a->B) * a->heads * q_tiles;
     DS_REQUIRE(total_ll < (1ll << 30), "ds_attention_cross_ip: too many tiles");
@@ -1422,8 +876,4 @@ extern "C" int ds_attention_cross_ip(const ds_cross_ip_args* a, void* stream) {
     DS_LAUNCH_OK("cross_ip_attn_v2_kernel");
     return DS_OK;
   }
-  dim3 grid((a->N + kTile - 1) / kTile, a->heads, a->B);
-  cross_ip_attn_kernel<<<grid, kAttnThreads, smem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmT, tmI, p);
-  DS_LAUNCH_OK("cross_ip_attn_kernel");
-  return DS_OK;
 }

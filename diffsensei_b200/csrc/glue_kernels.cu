@@ -220,6 +220,38 @@ extern "C" int ds_conv_in_3x3(const void* x, const float* w, const float* bias, 
   return DS_OK;
 }
 
+// im2col of the 4-channel latent for a 3x3 / pad 1 conv: A[b*HW + p][tap*4 + c] = x[b][y+r-1][x+s-1][c] (zero outside
+// the image), taps 0..8 = (r, s) row-major, columns 36..63 zero -> one K = 64 block of the tcgen05 GEMM.  16 threads
+// per pixel, 8 bytes each: every 128-byte row of A is one coalesced store.
+__global__ void im2col_latent_kernel(const uint2* __restrict__ x, uint2* __restrict__ a, int H, int W, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // (pixel, tap slot)
+  if (i >= total) return;
+  const int tap = static_cast<int>(i & 15);
+  const long long pix = i >> 4;
+  uint2 v = make_uint2(0u, 0u);
+  if (tap < 9) {
+    const int HW = H * W;
+    const long long b = pix / HW;
+    const int p = static_cast<int>(pix - b * HW);
+    const int y = p / W + tap / 3 - 1, xx = p % W + tap % 3 - 1;
+    if (y >= 0 && y < H && xx >= 0 && xx < W) v = __ldg(x + b * HW + static_cast<long long>(y) * W + xx);
+  }
+  a[i] = v;
+}
+
+extern "C" int ds_im2col_latent(const void* x, void* a, int B, int H, int W, void* stream) {
+  DS_REQUIRE(x && a && B > 0 && H > 0 && W > 0, "ds_im2col_latent: bad arguments");
+  DS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(a) & 7) == 0,
+             "ds_im2col_latent: pointers must be 8-byte aligned");
+  DeviceInfo dev;
+  if (!get_device(&dev)) return DS_ERR_CUDA;
+  const long long total = static_cast<long long>(B) * H * W * 16;
+  im2col_latent_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint2*>(x), static_cast<uint2*>(a), H, W, total);
+  DS_LAUNCH_OK("im2col_latent_kernel");
+  return DS_OK;
+}
+
 extern "C" int ds_nchw_to_nhwc(const void* src, int src_is_fp32, void* dst, int B, int C, int H, int W, void* stream) {
   DS_REQUIRE(src && dst && B > 0 && C > 0 && H > 0 && W > 0, "ds_nchw_to_nhwc: bad arguments");
   DeviceInfo dev;

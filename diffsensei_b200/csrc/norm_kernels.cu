@@ -73,6 +73,8 @@ __global__ void chan_stats_kernel(const uint4* __restrict__ x, double* __restric
   const int prow = threadIdx.x / cv;
   int i0, i1;
   gn_item_range(total_items, i0, i1);
+  pdl_launch_dependents();  // programmatic dependent launch: our launch latency overlapped the producer's tail ...
+  pdl_wait();               // ... and nothing of the producer's output is touched before it has completed
   if (i0 >= i1) return;
   float s[8], q[8];
   auto reset = [&]() {
@@ -154,7 +156,11 @@ __global__ void gn_apply2_kernel(const uint4* __restrict__ x1, const uint4* __re
   float* sh_coef = reinterpret_cast<float*>(shd + 2 * static_cast<size_t>(C));  // [groups][2]
   int i0, i1;
   gn_item_range(total_items, i0, i1);
-  if (i0 >= i1) return;
+  pdl_launch_dependents();
+  if (i0 >= i1) {
+    pdl_wait();
+    return;
+  }
   // this thread's source: its 8 channels live entirely in x1 or entirely in x2 (C1 % 8 == 0)
   const bool second = cvec >= cv1;
   const uint4* xsrc = second ? x2 : x1;
@@ -163,9 +169,10 @@ __global__ void gn_apply2_kernel(const uint4* __restrict__ x1, const uint4* __re
   float ga[8], be[8], sc[8], sf[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    ga[j] = __ldg(gamma + cvec * 8 + j);
+    ga[j] = __ldg(gamma + cvec * 8 + j);   // parameters: not written by the predecessor kernel
     be[j] = __ldg(beta + cvec * 8 + j);
   }
+  pdl_wait();  // x and the statistics come from the predecessor
   // x is dead after this read (evict_first); y stays for the consumer conv.  l2_hint == 0: plain loads (A/B knob)
   const uint64_t pol = l2_hint ? l2_policy_evict_first() : l2_policy_normal();
   // group coefficients of sample b: channel sums -> smem -> 32 threads fold cpg channels each, in order
@@ -366,8 +373,19 @@ extern "C" int ds_channel_stats(const void* x, double* stats, int B, int HW, int
   if (occ > 2) occ = 2;  // few, fat CTAs: every CTA ends with 2*C fp64 atomics per sample it touched
   const long long g = static_cast<long long>(occ) * dev.num_sms;
   const int grid = static_cast<int>(g < pl.total_items ? g : pl.total_items);
-  chan_stats_kernel<<<grid, pl.threads, smem, st>>>(static_cast<const uint4*>(x), stats, HW, C, pl.items_per_sample,
-                                                    pl.ipx, pl.total_items);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(pl.threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    pdl_attr(&attr[0]);
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DS_CUDA_OK(cudaLaunchKernelEx(&cfg, chan_stats_kernel, static_cast<const uint4*>(x), stats, HW, C,
+                                  pl.items_per_sample, pl.ipx, pl.total_items));
+  }
   DS_LAUNCH_OK("chan_stats_kernel");
   return DS_OK;
 }
@@ -422,6 +440,10 @@ extern "C" int ds_groupnorm_apply(const void* x1, const double* stats1, int C1, 
   cfg.blockDim = dim3(pl.threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
+  cudaLaunchAttribute lattr[1];
+  pdl_attr(&lattr[0]);
+  cfg.attrs = lattr;
+  cfg.numAttrs = 1;
   const uint4* a1 = static_cast<const uint4*>(x1);
   const uint4* a2 = static_cast<const uint4*>(x2);
   uint4* yp = static_cast<uint4*>(y);

@@ -337,6 +337,18 @@ def conv_in(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out:
     return out
 
 
+def im2col_latent(x: torch.Tensor) -> torch.Tensor:
+    """3x3 / pad 1 patches of the 4-channel latent: NHWC bf16 [B,H,W,4] -> [B*H*W, 64] bf16 (36 real columns), the A
+    operand of conv_in as a K = 64 tcgen05 GEMM against ``weights.pack_conv_in``."""
+    _req(x, bf16, "im2col_latent.x", 4)
+    B, H, W, Cin = x.shape
+    if Cin != 4:
+        raise DsEngineError("im2col_latent: the latent must have 4 channels")
+    out = torch.empty(B * H * W, 64, dtype=bf16, device=x.device)
+    check(lib.ds_im2col_latent(x.data_ptr(), out.data_ptr(), B, H, W, _stream()), "ds_im2col_latent")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- attention
 def attention_self(qkv: torch.Tensor, heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(QK^T/8)V from the fused projection ``qkv`` [B, N, 3*heads*64] -> [B, N, heads*64]."""

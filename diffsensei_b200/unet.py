@@ -26,8 +26,8 @@ import torch
 
 from . import ops
 from .config import UNetConfig
-from .weights import (bf, colsum_bf16, fold_layernorm, fp, pack_conv3x3, pack_geglu, resnet_io, transformer_sites,
-                      unet_param_shapes)
+from .weights import (bf, colsum_bf16, fold_layernorm, fp, pack_conv3x3, pack_conv_in, pack_geglu, resnet_io,
+                      transformer_sites, unet_param_shapes)
 
 bf16, f32 = torch.bfloat16, torch.float32
 
@@ -144,7 +144,7 @@ class UNetMangaEngine:
         def W(k):
             return sd[k].to(dev)
 
-        self.conv_in_w = fp(W("conv_in.weight").permute(0, 2, 3, 1))      # [Cout,3,3,4] fp32
+        self.conv_in_w = pack_conv_in(W("conv_in.weight"))                 # [Cout, 64] bf16 (K = 36 padded to 64)
         self.conv_in_b = fp(W("conv_in.bias"))
         self.dialog_emb = fp(W("dialog_bbox_embedding").to(bf16))          # parameter lives in the unet dtype
         self.te = [(bf(W(f"time_embedding.linear_{i}.weight")), fp(W(f"time_embedding.linear_{i}.bias")))
@@ -385,10 +385,15 @@ class UNetMangaEngine:
         B, H, W, _ = x.shape
         need_size = (H % (2 ** (nlev - 1)) != 0) or (W % (2 ** (nlev - 1)) != 0)       # unet.py:152-162
         pool = self._Pool(B, max(ch), x.device)
-        h = ops.conv_in(x, self.conv_in_w, self.conv_in_b)
+        # conv_in on the tensor cores: im2col of the 4-channel latent (K = 36 -> 64) + one GEMM whose epilogue also
+        # takes the GroupNorm statistics — unless the dialog embedding is added afterwards (it changes them)
+        st = None
+        if dialog_bbox is None and (H * W) % 128 == 0:
+            st = pool.take(ch[0])
+        h = ops.gemm(ops.im2col_latent(x), self.conv_in_w, self.conv_in_b, chan_stats=st,
+                     stats_rows_per_sample=H * W if st is not None else 0).view(B, H, W, ch[0])
         if dialog_bbox is not None:
             ops.dialog_embed_add_(h, self.dialog_emb, dialog_bbox, round_bf16)        # unet.py:208-210
-        st = None                                                                     # no tensor-core producer
         skips = [(h, st)]
         for i in range(nlev):
             for j in range(cfg.layers_per_block):

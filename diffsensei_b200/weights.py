@@ -232,6 +232,15 @@ def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     return w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
 
 
+def pack_conv_in(w: torch.Tensor) -> torch.Tensor:
+    """conv_in OIHW [Cout, 4, 3, 3] -> [Cout, 64] bf16: column tap*4 + c (taps row-major), columns 36..63 zero — the
+    B operand matching ``ops.im2col_latent``."""
+    cout = w.shape[0]
+    p = torch.zeros(cout, 64, dtype=torch.float32, device=w.device)
+    p[:, :36] = w.float().permute(0, 2, 3, 1).reshape(cout, 36)
+    return p.to(torch.bfloat16).contiguous()
+
+
 def pack_geglu(w: torch.Tensor, b: torch.Tensor, block: int = 128):
     """diffusers GEGLU.proj rows are [value(4C) ; gate(4C)]; DS_EPI_GEGLU wants per 2*block rows
     [block value rows ; the matching block gate rows] so one 256-wide output tile holds both halves."""

@@ -208,6 +208,11 @@ int ds_conv3x3_nhwc(const ds_conv3x3_args* args, void* stream);
  * Replaces UNet2DConditionModel.conv_in (src/models/unet.py:206).                       [HBM-bound] */
 int ds_conv_in_3x3(const void* x, const float* w, const float* bias, void* out, int B, int H, int W, int Cout,
                    void* stream);
+/* The same conv on the tensor cores: ds_im2col_latent writes A[B*H*W][64] bf16 (column tap*4 + c, taps row-major over
+ * the 3x3 window, zero padding outside the image, columns 36..63 zero) and ds_gemm_bf16 with the weights packed as
+ * [Cout][64] (weights.pack_conv_in) does the rest — bias, GroupNorm statistics of the output (chan_stats) and the
+ * coalesced TMA store in its epilogue.  x: NHWC bf16 [B][H][W][4].                        [HBM-bound] */
+int ds_im2col_latent(const void* x, void* a, int B, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused self-attention, head_dim 64, no mask: softmax(Q K^T / 8) V.              [tensor-bound]

@@ -406,3 +406,18 @@ def test_gemm_tail_launch_is_bit_identical_to_wide_tiles(ops):
     assert torch.equal(full[M - 768:], tail)
     head = ops.gemm(a[:2048].contiguous(), w, bias, residual=r[:2048].contiguous())
     assert torch.equal(full[:2048], head)
+
+
+@pytest.mark.parametrize("B,H,W,Cout", [(2, 16, 24, 64), (1, 17, 9, 320), (2, 32, 32, 512)])
+def test_conv_in_as_im2col_gemm(ops, B, H, W, Cout):
+    """conv_in (Cin = 4) on the tensor cores: ds_im2col_latent + ds_gemm_bf16 with weights.pack_conv_in."""
+    from diffsensei_b200.weights import pack_conv_in
+    g = torch.Generator().manual_seed(31)
+    x = _r(B, H, W, 4, seed=30)
+    w = (torch.randn(Cout, 4, 3, 3, generator=g) / 6).to(bf16).float()
+    b = torch.randn(Cout, generator=g) * 0.1
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1)
+    a = ops.im2col_latent(x.to(DEV))
+    assert a.shape == (B * H * W, 64) and torch.count_nonzero(a[:, 36:]).item() == 0
+    got = ops.gemm(a, pack_conv_in(w).to(DEV), b.to(DEV)).view(B, H, W, Cout)
+    assert rel_l2(got.float(), want) < 6e-3

@@ -56,3 +56,20 @@ def _worker(rank, world, port, total):
 def test_world_size_2_gloo_gather_and_max():
     port = _free_port()
     mp.spawn(_worker, args=(2, port, 5), nprocs=2, join=True)      # 5 panels -> shards of 3 and 2
+
+
+def test_bench_shards_one_global_batch_over_the_ranks():
+    """bench.py --gpus N: every rank builds the same seeded global batch (bs * N panels, CFG-concatenated) and keeps the
+    contiguous rows parallel.shard_range gives it; the shards must tile the global batch in panel order."""
+    import torch
+    import bench
+    from diffsensei_b200 import parallel
+    from oracle.config import TINY
+    world, bs = 4, 2
+    glob = bench.synthetic_inputs(TINY, bs * world, 8, 8, 2, "cpu", dialogs=True)
+    parts = [bench.shard_inputs(glob, *parallel.shard_range(bs * world, world, r)) for r in range(world)]
+    assert torch.equal(torch.cat([p[0] for p in parts]), glob[0])                      # latents, panel order
+    for k in (1, 2, 3, 4, 5):                                                           # CFG halves stay paired
+        neg = torch.cat([p[k][:bs] for p in parts])
+        pos = torch.cat([p[k][bs:] for p in parts])
+        assert torch.equal(torch.cat([neg, pos]), glob[k])

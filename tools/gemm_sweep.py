@@ -37,16 +37,18 @@ for (M, N, K, res, geglu) in GEMMS:
     b = torch.zeros(N, device=dev)
     ms = timed([(lambda s=s: ops.gemm(s[0], s[1], b, residual=s[2], out=s[3], epilogue=ops.EPI_GEGLU if geglu else 0)) for s in sets])
     out.append("gemm M%%d N%%d K%%d%%s %%.1fus %%.0fTF" %% (M, N, K, "+res" if res else "", ms * 1e3, 2.0 * M * N * K / ms / 1e9))
-CONVS = [(8, 128, 128, 320, 320, True), (8, 128, 128, 640, 320, False), (8, 64, 64, 640, 640, True), (8, 32, 32, 1280, 1280, True),
-         (8, 128, 128, 640, 640, False)]
-for (B, H, W, Ci, Co, res) in CONVS:
+CONVS = [(8, 128, 128, 320, 320, True, False), (8, 128, 128, 640, 320, False, False), (8, 64, 64, 640, 640, True, False),
+         (8, 32, 32, 1280, 1280, True, False), (8, 128, 128, 640, 640, False, False), (8, 128, 128, 960, 320, False, True),
+         (8, 128, 128, 640, 320, False, True), (8, 128, 128, 320, 320, True, True)]
+for (B, H, W, Ci, Co, res, stats) in CONVS:
     nset = max(2, int(300e6 // (B * H * W * (Ci + Co * (2 if res else 1)) * 2)) + 1)
     w = pack_conv3x3(torch.randn(Co, Ci, 3, 3, device=dev) * (9 * Ci) ** -0.5)
     b = torch.zeros(Co, device=dev)
     rb = torch.randn(B, Co, device=dev)
     sets = [(r(B, H, W, Ci), r(B, H, W, Co) if res else None, torch.empty(B, H, W, Co, dtype=bf, device=dev)) for _ in range(min(nset, 6))]
-    ms = timed([(lambda s=s: ops.conv3x3(s[0], w, b, rowbias=rb, residual=s[1], out=s[2])) for s in sets])
-    out.append("conv %%dx%%d %%d->%%d%%s %%.1fus %%.0fTF" %% (H, W, Ci, Co, "+res" if res else "", ms * 1e3, 2.0 * 9 * Ci * Co * B * H * W / ms / 1e9))
+    cst = torch.zeros(B, Co, 2, dtype=torch.float64, device=dev) if stats else None
+    ms = timed([(lambda s=s: ops.conv3x3(s[0], w, b, rowbias=rb, residual=s[1], out=s[2], chan_stats=cst)) for s in sets])
+    out.append("conv %%dx%%d %%d->%%d%%s%%s %%.1fus %%.0fTF" %% (H, W, Ci, Co, "+res" if res else "", "+stats" if stats else "", ms * 1e3, 2.0 * 9 * Ci * Co * B * H * W / ms / 1e9))
 print("\n    ".join(out))
 ''' % ROOT
 variants = sys.argv[1:] or ["", "DS_GEMM_TAIL=0", "DS_GEMM_BN=256", "DS_PDL=0"]

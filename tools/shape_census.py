@@ -34,6 +34,8 @@ ops.groupnorm_apply = lambda x, st, g, b, G, eps, silu=True, x2=None, stats2=Non
 ops.channel_stats = lambda x, out=None: None
 ops.layernorm = lambda x, g, b, eps=1e-5, out=None: same(x)
 ops.conv_in = lambda x, w, b, out=None: E(*x.shape[:3], w.shape[0])
+ops.im2col_latent = lambda x: E(x.shape[0] * x.shape[1] * x.shape[2], 64)
+unet_mod.pack_conv_in = lambda w: E(w.shape[0], 64)
 ops.concat_channels = lambda a, b, out=None: E(*a.shape[:-1], a.shape[-1] + b.shape[-1])
 ops.upsample_nearest = lambda x, Ho, Wo, out=None: E(x.shape[0], Ho, Wo, x.shape[3])
 
