@@ -192,6 +192,10 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
   } else if (warp == 1) {
+    // MMA issue: ONE lane in a divergent region.  MEASURED (round 2): running this warp converged with elect.sync-
+    // predicated tcgen05 instructions (as the cross-attention kernel does) removes ptxas' ELECT / BRA.U.ANY waterfall
+    // around every MMA (~50 issue cycles each) but made this kernel SLOWER (433 -> 474 us at B8 N4096 h10, 70 -> 75 us
+    // at B8 N1024 h20): the MUFU-bound softmax warps of the same SM sub-partition lose issue slots to 32 polling lanes.
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(kTile, kHalf, 0, 0);  // M128 N64, both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);    // M128 N64, A from TMEM, B (=V) MN-major
@@ -522,7 +526,7 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // converged MMA-issue warp (elected lane issues; see umma_ss_e)
       const uint32_t idesc_qk = make_idesc_bf16(kTile, n_keys, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
@@ -543,21 +547,21 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const uint32_t q_addr = smem_u32(sQ + slot * kTileBytes);
 #pragma unroll
         for (int k = 0; k < kHd / 16; ++k)
-          umma_ss(tS, make_sw128_desc(q_addr + k * 32, 1024, 16), make_sw128_desc(k_addr + k * 32, 1024, 16), idesc_qk,
+          umma_ss_e(tS, make_sw128_desc(q_addr + k * 32, 1024, 16), make_sw128_desc(k_addr + k * 32, 1024, 16), idesc_qk,
                   k != 0 ? 1u : 0u);
-        umma_commit(&q_empty[slot]);
-        umma_commit(s_full);
+        umma_commit_e(&q_empty[slot]);
+        umma_commit_e(s_full);
         mbar_wait(p_full, n & 1);
         tc_fence_after();
         for (int k = 0; k < n_keys / 16; ++k) {
           const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048, 1024, 1024);
           if (k < kt)
-            umma_ts(tOt, tS + k * 8, bdesc, idesc_pv, k != 0 ? 1u : 0u);
+            umma_ts_e(tOt, tS + k * 8, bdesc, idesc_pv, k != 0 ? 1u : 0u);
           else
-            umma_ts(tOi, tS + p.nt_pad + (k - kt) * 8, bdesc, idesc_pv, k != kt ? 1u : 0u);
+            umma_ts_e(tOi, tS + p.nt_pad + (k - kt) * 8, bdesc, idesc_pv, k != kt ? 1u : 0u);
         }
-        umma_commit(o_full);
-        if (n + 1 < n_items && (item + 1) / q_tiles != bh) umma_commit(kv_empty);
+        umma_commit_e(o_full);
+        if (n + 1 < n_items && (item + 1) / q_tiles != bh) umma_commit_e(kv_empty);
       }
     }
   } else {
