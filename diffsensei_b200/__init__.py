@@ -5,6 +5,8 @@ Public surface (mirrors the reference's):
     AttnProcessor2_0, MaskedIPAttnProcessor2_0  <- src/models/attention_processor.py
     ResamplerEngine        <- src/models/resampler.py       Resampler
     VaeDecoderEngine       <- diffusers AutoencoderKL.decode as used by pipeline_diffsensei.py:339-363
+    ClipTextEncoderEngine, ClipVisionEncoderEngine, VitMaeEncoderEngine  <- transformers CLIP / ViT-MAE encoders as
+                              used by encode_prompt (:232-245) and prepare_ip_image_embeds (:125-128)
     DiffSenseiPipeline     <- src/pipelines/pipeline_diffsensei.py  (denoise loop)
     ops                    -- tensor-level wrappers over the C ABI in include/dsengine.h
 
@@ -16,6 +18,8 @@ from . import ops  # noqa: F401
 from .attention_processor import AttnProcessor2_0, MaskedIPAttnProcessor2_0  # noqa: F401
 from .config import (RESAMPLER, RESAMPLER_TINY, SDXL_MANGA, SDXL_VAE, TINY, TINY_VAE, ResamplerConfig, UNetConfig,  # noqa: F401
                      VaeConfig)
+from .encoders import (CLIP_L_TEXT, CLIP_VIT_H, MAGI_VIT_MAE, OPENCLIP_BIGG_TEXT, ClipTextEncoderEngine,  # noqa: F401
+                       ClipVisionEncoderEngine, EncoderConfig, VitMaeEncoderEngine)
 from .pipeline import DiffSenseiPipeline  # noqa: F401
 from .resampler import ResamplerEngine  # noqa: F401
 from .scheduler import DDIMScheduler  # noqa: F401

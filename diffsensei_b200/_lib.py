@@ -48,7 +48,7 @@ class CrossIpArgs(C.Structure):
                 ("aspect_ratio", C.c_double), ("ip_scale", C.c_float)]
 
 
-EPI_NONE, EPI_GEGLU, EPI_GELU, EPI_SILU = 0, 1, 2, 3
+EPI_NONE, EPI_GEGLU, EPI_GELU, EPI_SILU, EPI_QUICKGELU = 0, 1, 2, 3, 4
 
 _vp, _i, _f, _d, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_int64
 
@@ -75,6 +75,8 @@ SIGNATURES = {
     "ds_timestep_embedding": [_vp, _vp, _i, _i, _vp],
     "ds_cfg_ddim_step": [_vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp],
     "ds_resampler_attn": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "ds_attention_small": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _f, _i, _vp],
+    "ds_embed_tokens": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "ds_latent_pointwise": [_vp, _vp, _vp, _vp, _f, _i, _i, _vp],
     "ds_softmax_rows": [_vp, _vp, _i, _i, _i64, _i64, _f, _vp],
     "ds_image_postprocess": [_vp, _vp, _i, _i, _i, _vp],

@@ -566,6 +566,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         } else if (p.epilogue == DS_EPI_SILU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+        } else if (p.epilogue == DS_EPI_QUICKGELU) {  // CLIP "quick_gelu": x * sigmoid(1.702 x)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-1.702f * v[j]));
         }
       };
 
@@ -1049,7 +1052,7 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
   DS_REQUIRE((a->a2 || a->lda >= a->K) && a->ldw >= a->K, "ds_gemm_bf16: lda/ldw smaller than K");
   DS_REQUIRE((reinterpret_cast<uintptr_t>(a->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
              "ds_gemm_bf16: a and w must be 16-byte aligned");
-  DS_REQUIRE(a->epilogue >= DS_EPI_NONE && a->epilogue <= DS_EPI_SILU, "ds_gemm_bf16: bad epilogue %d", a->epilogue);
+  DS_REQUIRE(a->epilogue >= DS_EPI_NONE && a->epilogue <= DS_EPI_QUICKGELU, "ds_gemm_bf16: bad epilogue %d", a->epilogue);
   if (a->epilogue == DS_EPI_GEGLU)
     DS_REQUIRE(a->N % 256 == 0, "ds_gemm_bf16: GEGLU needs N %% 256 == 0 (128 value + 128 gate rows per block)");
   if (a->rowbias) DS_REQUIRE(a->rows_per_batch > 0, "ds_gemm_bf16: rowbias needs rows_per_batch > 0");

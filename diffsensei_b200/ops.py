@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_GEGLU, EPI_GELU, EPI_NONE, EPI_SILU, Conv3x3Args, CrossIpArgs, DsEngineError, GemmArgs,
+from ._lib import (EPI_GEGLU, EPI_GELU, EPI_NONE, EPI_QUICKGELU, EPI_SILU, Conv3x3Args, CrossIpArgs, DsEngineError, GemmArgs,
                    check, lib)
 
 bf16, f32 = torch.bfloat16, torch.float32
@@ -472,6 +472,38 @@ def cfg_ddim_step_(noise_pred: torch.Tensor, latents: torch.Tensor, model_in: to
         raise DsEngineError("cfg_ddim_step: shape mismatch")
     check(lib.ds_cfg_ddim_step(noise_pred.data_ptr(), latents.data_ptr(), model_in.data_ptr(), coef.data_ptr(),
                                float(guidance), bs, H * W, Cc, _stream()), "ds_cfg_ddim_step")
+
+
+# ---------------------------------------------------------------------------------------------- encoder helpers
+def attention_small(qkv: torch.Tensor, heads: int, causal: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(Q K^T / sqrt(d) [+ causal]) V from a fused projection ``qkv`` [B, N, 3*heads*d] (N <= 320, d % 8 == 0,
+    d <= 128) -> [B, N, heads*d].  The short-sequence attention of the CLIP / ViT-MAE encoders."""
+    _req(qkv, bf16, "attention_small.qkv", 3)
+    B, N, C3 = qkv.shape
+    if C3 % (3 * heads) != 0:
+        raise DsEngineError("attention_small: last dim must be 3 * heads * head_dim")
+    Cc = C3 // 3
+    d = Cc // heads
+    out = torch.empty(B, N, Cc, dtype=bf16, device=qkv.device) if out is None else _req(out, bf16, "attention_small.out")
+    base = qkv.data_ptr()
+    check(lib.ds_attention_small(base, base + 2 * Cc, base + 4 * Cc, out.data_ptr(), B, N, N, heads, d, C3, C3, C3, Cc,
+                                 float(d) ** -0.5, int(causal), _stream()), "ds_attention_small")
+    return out
+
+
+def embed_tokens(ids: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor) -> torch.Tensor:
+    """token_embedding[ids] + position_embedding[:L]: int32 ids [B, L] -> bf16 [B, L, C]."""
+    _req(ids, torch.int32, "embed_tokens.ids", 2)
+    _req(tok_emb, bf16, "embed_tokens.tok_emb", 2)
+    _req(pos_emb, bf16, "embed_tokens.pos_emb", 2)
+    B, L = ids.shape
+    Cc = tok_emb.shape[1]
+    if pos_emb.shape[0] < L or pos_emb.shape[1] != Cc:
+        raise DsEngineError("embed_tokens: position table must be [>= L, C]")
+    out = torch.empty(B, L, Cc, dtype=bf16, device=ids.device)
+    check(lib.ds_embed_tokens(ids.data_ptr(), tok_emb.data_ptr(), pos_emb.data_ptr(), out.data_ptr(), B, L, Cc,
+                              tok_emb.shape[0], _stream()), "ds_embed_tokens")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- VAE decoder helpers

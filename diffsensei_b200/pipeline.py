@@ -35,9 +35,12 @@ bf16, f32 = torch.bfloat16, torch.float32
 
 class DiffSenseiPipeline:
     def __init__(self, unet: UNetMangaEngine, scheduler: Optional[DDIMScheduler] = None, vae_scale_factor: int = 8,
-                 default_sample_size: int = 128, vae=None):
+                 default_sample_size: int = 128, vae=None, text_encoder=None, text_encoder_2=None, image_encoder=None):
         self.unet = unet
         self.vae = vae                      # VaeDecoderEngine (or None: latents out only)
+        self.text_encoder = text_encoder    # ClipTextEncoderEngine (CLIP-L) / (OpenCLIP bigG, with projection)
+        self.text_encoder_2 = text_encoder_2
+        self.image_encoder = image_encoder  # ClipVisionEncoderEngine (ViT-H/14)
         self.scheduler = scheduler or DDIMScheduler()
         self.vae_scale_factor = vae_scale_factor
         self.default_sample_size = default_sample_size
@@ -78,6 +81,37 @@ class DiffSenseiPipeline:
 
     def set_ip_scale(self, scale):
         self.unet.set_ip_scale(scale)
+
+    @torch.no_grad()
+    def encode_prompt_ids(self, input_ids, input_ids_2, negative_input_ids=None, negative_input_ids_2=None):
+        """``encode_prompt`` (pipeline_diffsensei.py:232-245; diffusers StableDiffusionXLPipeline) from TOKEN IDS — the
+        two tokenizers' vocabulary files are host-side assets outside the hot path.  Both encoders are read at
+        ``hidden_states[-2]`` and concatenated (768 + 1280 = 2048 features); the pooled embedding is the second
+        encoder's projected EOS feature.  No negative ids: zeros (SDXL-base ``force_zeros_for_empty_prompt``)."""
+        if self.text_encoder is None or self.text_encoder_2 is None:
+            raise ValueError("encode_prompt_ids needs text_encoder and text_encoder_2 engines")
+
+        def enc(a, b):
+            o1, o2 = self.text_encoder(a, output_hidden_states=True), self.text_encoder_2(b, output_hidden_states=True)
+            return torch.cat([o1.hidden_states[-2], o2.hidden_states[-2]], dim=-1), o2[0]
+        pe, pp = enc(input_ids, input_ids_2)
+        if negative_input_ids is None:
+            npe, npp = torch.zeros_like(pe), torch.zeros_like(pp)
+        else:
+            npe, npp = enc(negative_input_ids, negative_input_ids_2 if negative_input_ids_2 is not None
+                           else negative_input_ids)
+        return pe, npe, pp, npp
+
+    @torch.no_grad()
+    def encode_ip_images(self, clip_pixel_values: torch.Tensor, magi_pixel_values: torch.Tensor):
+        """The encoder half of ``prepare_ip_image_embeds`` (:125-128) from the image processors' ``pixel_values``
+        ([n, 3, 224, 224] each, n real characters): CLIP ViT-H ``hidden_states[-2]`` -> (1, n, 257, 1280) and the Magi
+        ViT-MAE CLS row -> (1, n, 768).  Characters beyond n are zero embeddings either way (:131-132)."""
+        if self.image_encoder is None or self.magi_image_encoder is None:
+            raise ValueError("encode_ip_images needs image_encoder and magi_image_encoder engines")
+        clip = self.image_encoder(clip_pixel_values, output_hidden_states=True).hidden_states[-2].unsqueeze(0)
+        magi = self.magi_image_encoder(magi_pixel_values).last_hidden_state[:, 0].unsqueeze(0)
+        return clip, magi
 
     def prepare_ip_image_embeds(self, clip_image_embeds: torch.Tensor, magi_image_embeds: torch.Tensor,
                                 ip_image_embeds: Optional[torch.Tensor], ip_bbox: List[List[float]], num_samples: int):
@@ -189,20 +223,30 @@ class DiffSenseiPipeline:
                  pooled_prompt_embeds: Optional[torch.Tensor] = None,
                  negative_pooled_prompt_embeds: Optional[torch.Tensor] = None,
                  clip_image_embeds: Optional[torch.Tensor] = None, magi_image_embeds: Optional[torch.Tensor] = None,
-                 latents: Optional[torch.Tensor] = None, output_type: str = "latent", use_graph: bool = True):
+                 latents: Optional[torch.Tensor] = None, output_type: str = "latent", use_graph: bool = True,
+                 # ... or the INPUTS of those encoders, when the engines are registered (token ids / pixel values):
+                 prompt_input_ids=None, prompt_input_ids_2=None, negative_prompt_input_ids=None,
+                 negative_prompt_input_ids_2=None, clip_pixel_values=None, magi_pixel_values=None):
         height = height or self.default_sample_size * self.vae_scale_factor
         width = width or self.default_sample_size * self.vae_scale_factor
         original_size = original_size or (height, width)
         target_size = target_size or (height, width)
+        if prompt_embeds is None and prompt_input_ids is not None:
+            prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds = \
+                self.encode_prompt_ids(prompt_input_ids, prompt_input_ids_2 if prompt_input_ids_2 is not None
+                                       else prompt_input_ids, negative_prompt_input_ids, negative_prompt_input_ids_2)
+        if clip_image_embeds is None and clip_pixel_values is not None:
+            clip_image_embeds, magi_image_embeds = self.encode_ip_images(clip_pixel_values, magi_pixel_values)
         if prompt_embeds is None:
             self.check_inputs(prompt, prompt_2, list(ip_images), ip_image_embeds, list(ip_bbox))
             raise NotImplementedError(
-                "text encoding (encode_prompt, pipeline_diffsensei.py:232-245) is outside the B200 hot path this "
-                "round: pass prompt_embeds / negative_prompt_embeds / pooled_prompt_embeds / "
-                "negative_pooled_prompt_embeds")
+                "raw prompt strings need the CLIP tokenizers' vocabulary files (host-side assets, not part of the engine): "
+                "pass prompt_input_ids (+ prompt_input_ids_2) with the text-encoder engines registered, or "
+                "prompt_embeds / negative_prompt_embeds / pooled_prompt_embeds / negative_pooled_prompt_embeds")
         if len(ip_images) > 0:
-            raise NotImplementedError("image encoding (CLIP / Magi, pipeline_diffsensei.py:125-128) is outside the "
-                                      "hot path this round: pass clip_image_embeds / magi_image_embeds")
+            raise NotImplementedError("PIL images need the CLIP / Magi image processors (host-side resize + normalise): "
+                                      "pass clip_pixel_values / magi_pixel_values with the image-encoder engines "
+                                      "registered, or clip_image_embeds / magi_image_embeds")
         if output_type not in ("latent", "pt", "np", "pil"):
             raise ValueError(f"output_type must be one of latent / pt / np / pil, got {output_type!r}")
         if output_type != "latent" and self.vae is None:

@@ -101,7 +101,7 @@ int ds_ip_mask(const float* bbox, float* mask, int B, int N, double aspect_ratio
  *                 rows (see diffsensei_b200.weights.pack_geglu); out[:, j] = v_val * gelu_erf(v_gate),
  *                 Nout = N/2.  gelu_erf(x) = x * Phi(x) is evaluated as x * sigmoid(2k(x + a x^3 + b x^5)) with
  *                 (k, a, b) fitted to Phi: |abs err| <= 2.6e-5 for all x (the bf16 output rounding is >= 10x larger).
- *   DS_EPI_GELU / DS_EPI_SILU : v = act(v)
+ *   DS_EPI_GELU / DS_EPI_SILU / DS_EPI_QUICKGELU : v = act(v)
  *   then v += residual[row][n] (bf16) and v *= out_scale (if != 0).
  * LayerNorm fusion (diffusers BasicTransformerBlock.norm1/2/3 -> the linears on either side of them):
  *   consumer: with ln_stats != NULL, A holds the UN-normalised rows and the caller passes pre-folded weights
@@ -132,6 +132,7 @@ int ds_ip_mask(const float* bbox, float* mask, int B, int N, double aspect_ratio
 #define DS_EPI_GEGLU 1
 #define DS_EPI_GELU 2
 #define DS_EPI_SILU 3
+#define DS_EPI_QUICKGELU 4 /* v * sigmoid(1.702 v): CLIP-L text encoder MLP (hidden_act "quick_gelu") */
 
 typedef struct {
   const void* a;        /* bf16 [M][lda]                                  */
@@ -300,6 +301,24 @@ int ds_latent_pointwise(const float* latents, const float* w, const float* bias,
                         int HW, void* stream);
 int ds_softmax_rows(const float* S, void* P, int rows, int n, int64_t lds, int64_t ldp, float scale, void* stream);
 int ds_image_postprocess(const void* x, float* out, int B, int HW, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Conditioning-encoder helpers (CLIP ViT-H / Magi ViT-MAE image encoders,
+ * src/pipelines/pipeline_diffsensei.py:125-128, and the two SDXL CLIP text encoders of encode_prompt, :232-245).
+ * Their linears run on ds_gemm_bf16 and their LayerNorms on ds_layernorm.                    [latency-bound]
+ *   ds_attention_small : out = softmax(scale * Q K^T [+ causal mask]) V for short sequences (Nk <= 320) and any
+ *                        head_dim that is a multiple of 8 up to 128 (80 for ViT-H, outside the flash kernel's 64).
+ *                        q/k/v/out: bf16 [B][N][ld*] with head h at columns [h*head_dim, (h+1)*head_dim); the row
+ *                        strides ld* are in elements, so q/k/v may point into one fused [B][N][3C] projection.
+ *                        causal != 0: key j visible from query i iff j <= i (CLIP text), needs Nq == Nk.
+ *   ds_embed_tokens    : out[b][t][:] = tok_emb[ids[b][t]][:] + pos_emb[t][:], bf16, ids int32 [B][L] (clamped to
+ *                        the vocabulary) — CLIPTextEmbeddings.
+ * --------------------------------------------------------------------------------------------- */
+int ds_attention_small(const void* q, const void* k, const void* v, void* out, int B, int Nq, int Nk, int heads,
+                       int head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, int causal,
+                       void* stream);
+int ds_embed_tokens(const int* ids, const void* tok_emb, const void* pos_emb, void* out, int B, int L, int C, int vocab,
+                    void* stream);
 
 #ifdef __cplusplus
 }

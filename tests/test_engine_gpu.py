@@ -171,7 +171,7 @@ def test_pipeline_call_surface(tiny):
     with pytest.raises(ValueError, match="same length as `ip_bbox`"):
         pipe(prompt="x", prompt_embeds=pe, negative_prompt_embeds=npe, pooled_prompt_embeds=pp,
              negative_pooled_prompt_embeds=npp, clip_image_embeds=clip, magi_image_embeds=magi, ip_bbox=[[0, 0, 1, 1]])
-    with pytest.raises(NotImplementedError, match="text encoding"):
+    with pytest.raises(NotImplementedError, match="tokenizers"):
         pipe(prompt="x", ip_bbox=[])
 
 
