@@ -404,16 +404,18 @@ def run_reference(args):
     log = lambda *a: print(*a, file=sys.stderr)
     tiny = os.environ.get("DS_BENCH_TINY") == "1"          # plumbing self-test only; never a bench number
     ref = CpuReference(log, tiny)
-    cfg1 = ref.cfg1_step(steps=3, warmup=1)
+    # warm-up: the W untimed iterations run the cfg1-size loop step (same modules, threads and allocator; 2.9 s each on
+    # the box instead of 13.5 s for a cfg2 row), the last 3 of them are also the timed cfg1 measurement
+    cfg1 = ref.cfg1_step(steps=3, warmup=max(1, args.warmup - 3))
     log(f"[reference] cfg1 as stated (B=2, 64x64 latent): {cfg1['sec_per_step']} s/step")
-    times, fl, (h, w) = ref.cfg2_rows(args.steps, args.warmup)
+    times, fl, (h, w) = ref.cfg2_rows(args.steps, 0)
     t_row = sum(times) / max(len(times), 1)
     rows_per_step = 8
     value = 1.0 / (rows_per_step * t_row)
     sample = (f"one 'step' of this arm = ONE of the {rows_per_step} batch rows of a cfg2 step (UNet batch 1, latent "
               f"{h}x{w}, 2 character refs, fp32, {fl / 1e12:.3f} TFLOP): every op on the path is per-sample, so "
               f"steps/s = 1 / ({rows_per_step} x seconds per row) — a count of identical rows, no FLOP model; "
-              f"{args.warmup} warm-up + {args.steps} timed rows")
+              f"{args.steps} timed rows after {max(4, args.warmup)} untimed cfg1-size loop iterations (the warm-up)")
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 6), "unit": UNIT,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(t_row * 1e3, 1), "ms_per_step_is": "one bounded sample (1/8 of a cfg2 step)",
