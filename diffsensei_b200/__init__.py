@@ -21,7 +21,7 @@ from .config import (RESAMPLER, RESAMPLER_TINY, SDXL_MANGA, SDXL_VAE, TINY, TINY
 from .encoders import (CLIP_L_TEXT, CLIP_VIT_H, MAGI_VIT_MAE, OPENCLIP_BIGG_TEXT, ClipTextEncoderEngine,  # noqa: F401
                        ClipVisionEncoderEngine, EncoderConfig, VitMaeEncoderEngine)
 from .pipeline import DiffSenseiPipeline  # noqa: F401
-from .resampler import ResamplerEngine  # noqa: F401
+from .resampler import QwenResamplerEngine, ResamplerEngine  # noqa: F401
 from .scheduler import DDIMScheduler  # noqa: F401
 from .unet import UNet2DConditionOutput, UNetMangaEngine  # noqa: F401
 from .vae import VaeDecoderEngine  # noqa: F401

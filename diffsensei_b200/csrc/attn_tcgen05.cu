@@ -121,7 +121,7 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
 constexpr int kFlash5Threads = 320;  // warp 0: TMA + TMEM alloc, warp 1: MMA issue, warps 2-9: two softmax streams
 constexpr int kFlash5SmemBytes = kTileBytes * (1 + kFlash3Ring) + 1024 + 256 + 2 * kTile * 2 * 4;
 
-template <int POLY, bool F2>
+template <int POLY, bool F2, bool ELECT>
 __global__ void __launch_bounds__(kFlash5Threads, 2)
 flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
@@ -192,11 +192,70 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // MMA issue: ONE lane in a divergent region.  MEASURED (round 2): running this warp converged with elect.sync-
-    // predicated tcgen05 instructions (as the cross-attention kernel does) removes ptxas' ELECT / BRA.U.ANY waterfall
-    // around every MMA (~50 issue cycles each) but made this kernel SLOWER (433 -> 474 us at B8 N4096 h10, 70 -> 75 us
-    // at B8 N1024 h20): the MUFU-bound softmax warps of the same SM sub-partition lose issue slots to 32 polling lanes.
-    if (lane == 0) {
+    if (ELECT) {
+      // MMA issue warp, CONVERGED: lane 0 alone polls the mbarriers (32 polling lanes made this variant slower:
+      // 433 -> 474 us), the warp re-converges with __syncwarp and one elected lane issues every tcgen05 instruction
+      // with uniform operands — no ELECT / BRA.U.ANY waterfall around each MMA (~50 issue cycles each)
+      auto wait1 = [&](uint64_t* bar, uint32_t ph) {
+        if (lane == 0) mbar_wait(bar, ph);
+        __syncwarp();
+      };
+      constexpr uint32_t idesc_qk = make_idesc_bf16(kTile, kHalf, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_s = [&](uint32_t k_addr, int h) {
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k)
+          umma_ss_e(tS + h * kHalf, make_sw128_desc(q_addr + k * 32, 1024, 16),
+                    make_sw128_desc(k_addr + h * (kHalf * 128) + k * 32, 1024, 16), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit_e(&s_full[h]);
+      };
+      auto issue_pv = [&](uint32_t v_addr, int h, bool first) {
+#pragma unroll
+        for (int k = 0; k < kHalf / 16; ++k)
+          umma_ts_e(tO + h * kHd, tS + h * kHalf + k * 8,
+                    make_sw128_desc(v_addr + h * (kHalf * 128) + k * 2048, 1024, 1024), idesc_pv,
+                    (first && k == 0) ? 0u : 1u);
+      };
+      wait1(q_full, 0);
+      wait1(&full[0], 0);
+      tc_fence_after();
+      issue_s(smem_u32(sRing), 0);
+      issue_s(smem_u32(sRing), 1);
+      umma_commit_e(&empty[0]);
+      for (int j = 0; j < num_kv_tiles; ++j) {
+        const int vi = 2 * j + 1, vslot = vi % RING;
+        const int ki = 2 * j + 2, kslot = ki % RING;
+        const bool more = j + 1 < num_kv_tiles;
+        wait1(&full[vslot], (vi / RING) & 1);
+        if (more) wait1(&full[kslot], (ki / RING) & 1);
+        const uint32_t v_addr = smem_u32(sRing + vslot * kTileBytes);
+        const uint32_t k_addr = smem_u32(sRing + kslot * kTileBytes);
+        int first = 0;
+        if (lane == 0) {
+          for (;;) {
+            if (mbar_try_wait(&p_full[0], j & 1)) break;
+            if (mbar_try_wait(&p_full[1], j & 1)) {
+              first = 1;
+              break;
+            }
+          }
+        }
+        first = __shfl_sync(0xffffffffu, first, 0);
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const int h = o == 0 ? first : 1 - first;
+          if (o == 1) wait1(&p_full[h], j & 1);
+          tc_fence_after();
+          issue_pv(v_addr, h, j == 0);
+          if (o == 1) umma_commit_e(&empty[vslot]);
+          if (more) issue_s(k_addr, h);
+          if (more && o == 1) umma_commit_e(&empty[kslot]);
+        }
+      }
+      umma_commit_e(o_full);
+    } else if (lane == 0) {
+      // MMA issue: ONE lane in a divergent region (ptxas wraps every tcgen05.mma in an ELECT / BRA.U.ANY waterfall)
       constexpr uint32_t idesc_qk = make_idesc_bf16(kTile, kHalf, 0, 0);  // M128 N64, both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);    // M128 N64, A from TMEM, B (=V) MN-major
       const uint32_t q_addr = smem_u32(sQ);
@@ -745,15 +804,24 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
       const char* e = getenv("DS_FLASH_F2");
       return e ? atoi(e) : 1;
     }();
+    static const int flash_elect = [] {  // DS_FLASH_ELECT=1: converged MMA-issue warp (A/B)
+      const char* e = getenv("DS_FLASH_ELECT");
+      return e ? atoi(e) : 0;
+    }();
     static bool attr5_set_dev[kMaxDevices] = {};
     bool& attr5_set = attr5_set_dev[device_slot()];
+#define DS_F5_ATTR(P, F, E) \
+  DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<P, F, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes))
     if (!attr5_set) {
-      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
-      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
-      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
-      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
+      DS_F5_ATTR(0, true, false);
+      DS_F5_ATTR(1, true, false);
+      DS_F5_ATTR(2, true, false);
+      DS_F5_ATTR(0, false, false);
+      DS_F5_ATTR(0, true, true);
+      DS_F5_ATTR(2, true, true);
       attr5_set = true;
     }
+#undef DS_F5_ATTR
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(kFlash5Threads);
@@ -763,14 +831,20 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
     pdl_attr(&attr[0]);
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+#define DS_F5_LAUNCH(P, F, E) DS_CUDA_OK(cudaLaunchKernelEx(&cfg, flash_attn_v5_kernel<P, F, E>, tmQ, tmK, tmV, p))
     if (!flash_f2)
-      DS_CUDA_OK(cudaLaunchKernelEx(&cfg, flash_attn_v5_kernel<0, false>, tmQ, tmK, tmV, p));
+      DS_F5_LAUNCH(0, false, false);
+    else if (flash_elect && flash_poly >= 2)
+      DS_F5_LAUNCH(2, true, true);
+    else if (flash_elect)
+      DS_F5_LAUNCH(0, true, true);
     else if (flash_poly == 1)
-      DS_CUDA_OK(cudaLaunchKernelEx(&cfg, flash_attn_v5_kernel<1, true>, tmQ, tmK, tmV, p));
+      DS_F5_LAUNCH(1, true, false);
     else if (flash_poly == 2)
-      DS_CUDA_OK(cudaLaunchKernelEx(&cfg, flash_attn_v5_kernel<2, true>, tmQ, tmK, tmV, p));
+      DS_F5_LAUNCH(2, true, false);
     else
-      DS_CUDA_OK(cudaLaunchKernelEx(&cfg, flash_attn_v5_kernel<0, true>, tmQ, tmK, tmV, p));
+      DS_F5_LAUNCH(0, true, false);
+#undef DS_F5_LAUNCH
     DS_LAUNCH_OK("flash_attn_v5_kernel");
     return DS_OK;
   }

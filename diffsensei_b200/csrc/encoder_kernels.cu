@@ -129,7 +129,7 @@ extern "C" int ds_attention_small(const void* q, const void* k, const void* v, v
   DS_REQUIRE(B > 0 && Nq > 0 && Nk > 0 && heads > 0, "ds_attention_small: bad shape");
   DS_REQUIRE(Nk <= kSmallAttnMaxKeys, "ds_attention_small: at most %d keys (got %d); long sequences use ds_attention_self",
              kSmallAttnMaxKeys, Nk);
-  DS_REQUIRE(head_dim >= 8 && head_dim <= 128 && head_dim % 8 == 0, "ds_attention_small: head_dim %% 8 == 0, <= 128");
+  DS_REQUIRE(head_dim >= 8 && head_dim <= 256 && head_dim % 8 == 0, "ds_attention_small: head_dim %% 8 == 0, <= 256");
   DS_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0 && ldq >= heads * head_dim &&
                  ldk >= heads * head_dim && ldv >= heads * head_dim && ldo >= heads * head_dim,
              "ds_attention_small: row strides must cover heads*head_dim and be multiples of 8 elements");

@@ -484,7 +484,7 @@ extern "C" int ds_layernorm(const void* x, void* y, const float* gamma, const fl
   using namespace ds;
   DS_REQUIRE(x && y && gamma && beta, "ds_layernorm: NULL pointer");
   DS_REQUIRE(rows > 0 && C > 0 && C % 8 == 0, "ds_layernorm: rows>0 and C %% 8 == 0 required (rows=%d C=%d)", rows, C);
-  DS_REQUIRE(C <= 4096, "ds_layernorm: C (%d) > 4096 unsupported", C);
+  DS_REQUIRE(C <= 5120, "ds_layernorm: C (%d) > 5120 unsupported", C);
   DS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 && (reinterpret_cast<uintptr_t>(beta) & 15) == 0,
              "ds_layernorm: pointers must be 16-byte aligned");
@@ -507,7 +507,9 @@ extern "C" int ds_layernorm(const void* x, void* y, const float* gamma, const fl
     case 6: DS_LN_CASE(6); break;
     case 7:
     case 8: DS_LN_CASE(8); break;
-    default: DS_LN_CASE(16); break;
+    case 9: case 10: case 11: case 12: case 13: case 14: case 15:
+    case 16: DS_LN_CASE(16); break;
+    default: DS_LN_CASE(20); break;
   }
 #undef DS_LN_CASE
   DS_LAUNCH_OK("layernorm_kernel");

@@ -491,6 +491,26 @@ def attention_small(qkv: torch.Tensor, heads: int, causal: bool = False, out: Op
     return out
 
 
+def attention_small_qkv(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(scale * Q K^T) V with separate q [B, Nq, C] and k / v [B, Nk, C] (row-contiguous views of wider
+    projections are fine: the row strides are passed through), Nk <= 320."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == bf16 and t.dim() == 3 and t.stride(2) == 1):
+            raise DsEngineError(f"attention_small_qkv.{nm}: expected a 3-D CUDA bf16 tensor with unit channel stride")
+        _on_current_device(t, f"attention_small_qkv.{nm}")
+        if t.stride(0) != t.shape[1] * t.stride(1):
+            raise DsEngineError(f"attention_small_qkv.{nm}: batch stride must be tokens * row stride")
+    B, Nq, Cc = q.shape
+    Nk = k.shape[1]
+    d = Cc // heads
+    out = torch.empty(B, Nq, Cc, dtype=bf16, device=q.device) if out is None else _req(out, bf16, "attention_small_qkv.out")
+    check(lib.ds_attention_small(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, Nq, Nk, heads, d,
+                                 q.stride(1), k.stride(1), v.stride(1), Cc, float(d) ** -0.5 if scale is None else scale,
+                                 0, _stream()), "ds_attention_small")
+    return out
+
+
 def embed_tokens(ids: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor) -> torch.Tensor:
     """token_embedding[ids] + position_embedding[:L]: int32 ids [B, L] -> bf16 [B, L, C]."""
     _req(ids, torch.int32, "embed_tokens.ids", 2)

@@ -100,3 +100,70 @@ class ResamplerEngine:
         return torch.cat([self.dummy.unsqueeze(0).expand(bsz, -1, -1), out], dim=1)
 
     __call__ = forward
+
+
+class QwenResamplerEngine:
+    """The MLLM adaptor's resampler (first half): ``QwenResampler`` of src/models/qwen_resampler.py:87-145
+    — ``grid_size**2`` learned queries with a fixed 2-D sin-cos position embedding cross-attend ONCE over the input tokens:
+    ``kv_proj`` (no bias) -> ``ln_kv``; ``q = ln_q(query) + pos``; ``nn.MultiheadAttention(q, x + pos, x)``.
+    Used as ``input_resampler`` (image embeds (1, 64, 2048) -> (1, 64, 5120) LLM inputs, 32 heads of 160) and
+    ``output_resampler`` (LLM hidden states (n, 64, 5120) -> (n, 64, 2048) = the ``ip_image_embeds`` the pipeline pastes,
+    pipeline_diffsensei.py:143-145) around the LLaMA of src/models/mllm/seed_x.py:90-171 — the LLM itself is out of
+    scope.  Same constructor keywords and state-dict keys (``pos_embed``, ``query``, ``kv_proj.weight``,
+    ``attn.in_proj_weight/bias``, ``attn.out_proj.weight/bias``, ``ln_q.*``, ``ln_kv.*``).  The number of input tokens
+    must equal ``grid_size**2`` (the reference interpolates the position table bicubically otherwise; not needed on the
+    DiffSensei path: 64 tokens both ways)."""
+
+    def __init__(self, grid_size, embed_dim, num_heads, kv_dim=None, device="cuda"):
+        self.num_queries, self.embed_dim, self.num_heads = grid_size ** 2, embed_dim, num_heads
+        self.kv_dim = kv_dim if (kv_dim is not None and kv_dim != embed_dim) else None
+        self.out_dim = kv_dim if self.kv_dim is not None else embed_dim
+        self.device = torch.device(device)
+        self._loaded = False
+
+    def dtype(self):
+        return bf16
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        dev, E = self.device, self.embed_dim
+        W = lambda k: sd[k].to(dev)
+        want = {"pos_embed", "query", "attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight",
+                "attn.out_proj.bias", "ln_q.weight", "ln_q.bias", "ln_kv.weight", "ln_kv.bias"} | \
+            ({"kv_proj.weight"} if self.kv_dim is not None else set())
+        if strict and set(sd) != want:
+            raise KeyError(f"QwenResamplerEngine.load_state_dict: keys differ: {sorted(set(sd) ^ want)[:6]}")
+        self.pos = bf(W("pos_embed"))                                              # [nq, E]
+        self.kv_proj = bf(W("kv_proj.weight")) if self.kv_dim is not None else None
+        ipw, ipb = W("attn.in_proj_weight"), W("attn.in_proj_bias")
+        self.wq, self.bq = bf(ipw[:E]), fp(ipb[:E])
+        self.wk, self.bk = bf(ipw[E:2 * E]), fp(ipb[E:2 * E])
+        self.wv, self.bv = bf(ipw[2 * E:]), fp(ipb[2 * E:])
+        self.wo, self.bo = bf(W("attn.out_proj.weight")), fp(W("attn.out_proj.bias"))
+        self.ln_kv = (fp(W("ln_kv.weight")), fp(W("ln_kv.bias")))
+        # the query side does not depend on the input: ln_q(query) + pos -> q projection, once
+        qn = ops.layernorm(bf(W("query")), fp(W("ln_q.weight")), fp(W("ln_q.bias")), 1e-5)
+        self.q = ops.gemm((qn.float() + self.pos.float()).to(bf16).contiguous(), self.wq, self.bq)   # [nq, E]
+        self._loaded = True
+        return SimpleNamespace(missing_keys=[], unexpected_keys=[])
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, attn_mask=None) -> torch.Tensor:
+        if not self._loaded:
+            raise RuntimeError("QwenResamplerEngine.forward called before load_state_dict")
+        if attn_mask is not None:
+            raise NotImplementedError("attn_mask is None on the DiffSensei path (seed_x.py:123,160)")
+        B, L, _ = x.shape
+        if L != self.num_queries:
+            raise NotImplementedError(f"QwenResamplerEngine: {L} input tokens != grid_size**2 = {self.num_queries} "
+                                      "(bicubic interpolation of the position table is not implemented)")
+        x = x.to(device=self.device, dtype=bf16).contiguous()
+        if self.kv_proj is not None:
+            x = ops.gemm(x, self.kv_proj)
+        x = ops.layernorm(x, self.ln_kv[0], self.ln_kv[1], 1e-5)                    # [B, L, E]
+        k = ops.gemm((x.float() + self.pos.float()[None]).to(bf16).contiguous(), self.wk, self.bk)
+        v = ops.gemm(x, self.wv, self.bv)
+        q = self.q.unsqueeze(0).expand(B, -1, -1).contiguous()
+        a = ops.attention_small_qkv(q, k, v, self.num_heads)
+        return ops.gemm(a, self.wo, self.bo)
+
+    __call__ = forward

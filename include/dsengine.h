@@ -65,7 +65,7 @@ int ds_groupnorm_silu(const void* x, void* y, const float* gamma, const float* b
 
 /* LayerNorm over the last dim, bf16 in/out, fp32 affine.     [HBM-bound]
  * Replaces BasicTransformerBlock.norm1/2/3 (eps 1e-5) and Resampler LayerNorms
- * (src/models/resampler.py:14,40-41,104). rows x C, C % 8 == 0. */
+ * (src/models/resampler.py:14,40-41,104). rows x C, C % 8 == 0, C <= 5120. */
 int ds_layernorm(const void* x, void* y, const float* gamma, const float* beta, int rows, int C, float eps,
                  void* stream);
 
@@ -307,7 +307,8 @@ int ds_image_postprocess(const void* x, float* out, int B, int HW, int C, void* 
  * src/pipelines/pipeline_diffsensei.py:125-128, and the two SDXL CLIP text encoders of encode_prompt, :232-245).
  * Their linears run on ds_gemm_bf16 and their LayerNorms on ds_layernorm.                    [latency-bound]
  *   ds_attention_small : out = softmax(scale * Q K^T [+ causal mask]) V for short sequences (Nk <= 320) and any
- *                        head_dim that is a multiple of 8 up to 128 (80 for ViT-H, outside the flash kernel's 64).
+ *                        head_dim that is a multiple of 8 up to 256 (80 for ViT-H, 160 for the MLLM input resampler: outside the flash
+ *                        kernel's 64).
  *                        q/k/v/out: bf16 [B][N][ld*] with head h at columns [h*head_dim, (h+1)*head_dim); the row
  *                        strides ld* are in elements, so q/k/v may point into one fused [B][N][3C] projection.
  *                        causal != 0: key j visible from query i iff j <= i (CLIP text), needs Nq == Nk.

@@ -202,6 +202,23 @@ def test_resampler_shipped_config_matches_executed_reference():
     assert e1 < 2e-2 and e0 < 2e-2
 
 
+@pytest.mark.parametrize("name", ["tiny", "input", "output"])
+def test_qwen_resampler_matches_executed_reference(name):
+    """SURVEY §8f-4 (first half): the MLLM adaptor's QwenResampler on the engine vs the reference's own
+    qwen_resampler.py executed on the same seeded weights (tests/golden/qwen_resampler.pt); `input` has 32 heads of
+    width 160 and LayerNorms over 5120 features."""
+    import diffsensei_b200 as ds
+    from oracle.qwen_resampler import seeded_case
+    g = torch.load(os.path.join(GOLDEN, "qwen_resampler.pt"), weights_only=False)[name]
+    _m, sd, x = seeded_case(g["kwargs"], g["seed"])
+    eng = ds.QwenResamplerEngine(**g["kwargs"], device=DEV)
+    eng.load_state_dict(sd)
+    out = eng(x)
+    err = rel_l2(out.float(), g["out"])
+    print(f"QwenResampler[{name}] vs executed reference: rel-L2 {err:.3e}")
+    assert out.shape == g["out"].shape and err < 1.5e-2
+
+
 def test_smoke_entry_point():
     import __graft_entry__
     __graft_entry__.smoke()

@@ -123,3 +123,13 @@ def test_resampler_shipped_config_matches_executed_reference():
     with torch.no_grad():
         assert rel_l2(m(x, magi), g["out"]) < 1e-5
         assert rel_l2(m(torch.zeros_like(x), torch.zeros_like(magi)), g["out_zero"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["tiny", "input", "output"])
+def test_qwen_resampler_oracle_matches_executed_reference(name):
+    """MLLM adaptor resampler (src/models/qwen_resampler.py:87-145) at a tiny config and at the two shipped ones
+    (configs/model/diffsensei.yaml agent.input_resampler / output_resampler): restatement vs the executed reference."""
+    from oracle.qwen_resampler import seeded_case
+    g = _load("qwen_resampler.pt")[name]
+    m, _sd, x = seeded_case(g["kwargs"], g["seed"])
+    assert rel_l2(m(x), g["out"]) < 1e-5

@@ -195,6 +195,32 @@ def main():
     mf[0, 3:] = 0
     torch.save({"kwargs": kwf, "weight_seed": 42, "input_seed": 43, "n_real": 3, "out": full(xf, mf),
                 "out_zero": full(torch.zeros_like(xf), torch.zeros_like(mf))}, f"{OUT}/resampler_full.pt")
+    # ------------------------------------------------------------------ QwenResampler (MLLM adaptor, §8f-4)
+    # configs/model/diffsensei.yaml agent.input_resampler / output_resampler + a small one; weights / inputs are
+    # regenerated from seeds on both sides (tests/test_oracle_golden.py::qwen_case), only outputs are stored
+    qr = load_module("ref_qwen_resampler", f"{REF}/src/models/qwen_resampler.py")
+    qcases = {}
+    for name, kw in (("tiny", dict(grid_size=4, embed_dim=128, num_heads=2, kv_dim=64)),
+                     ("input", dict(grid_size=8, embed_dim=5120, num_heads=32, kv_dim=2048)),
+                     ("output", dict(grid_size=8, embed_dim=2048, num_heads=32, kv_dim=5120))):
+        m = qr.QwenResampler(**kw).eval()
+        gq = torch.Generator().manual_seed(50)
+        sdq = {}
+        for k, v in m.state_dict().items():
+            if k == "pos_embed":
+                sdq[k] = v
+            elif k.endswith("weight") and v.dim() == 1:
+                sdq[k] = (1 + 0.1 * torch.randn(v.shape, generator=gq)).to(torch.bfloat16).float()
+            elif k.endswith("bias"):
+                sdq[k] = (0.05 * torch.randn(v.shape, generator=gq)).to(torch.bfloat16).float()
+            elif k == "query":
+                sdq[k] = torch.randn(v.shape, generator=gq).to(torch.bfloat16).float()
+            else:
+                sdq[k] = (torch.randn(v.shape, generator=gq) * v.shape[-1] ** -0.5).to(torch.bfloat16).float()
+        m.load_state_dict(sdq)
+        xq = torch.randn(2, kw["grid_size"] ** 2, kw["kv_dim"], generator=gq).to(torch.bfloat16).float()
+        qcases[name] = {"kwargs": kw, "seed": 50, "out": m(xq)}
+    torch.save(qcases, f"{OUT}/qwen_resampler.pt")
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
