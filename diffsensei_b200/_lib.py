@@ -28,7 +28,7 @@ class GemmArgs(C.Structure):
                 ("row_stats_out", C.c_void_p), ("zero_rows", C.c_void_p), ("row_stats_zeroed", C.c_int32),
                 ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
                 ("a2", C.c_void_p), ("K1", C.c_int32), ("lda2", C.c_int32),
-                ("chan_stats", C.c_void_p), ("stats_rows_per_sample", C.c_int32)]
+                ("chan_stats", C.c_void_p), ("stats_rows_per_sample", C.c_int32), ("w_is_constant", C.c_int32)]
 
 
 class Conv3x3Args(C.Structure):
@@ -36,7 +36,8 @@ class Conv3x3Args(C.Structure):
                 ("rowbias", C.c_void_p), ("residual", C.c_void_p),
                 ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32),
                 ("stride", C.c_int32), ("rowbias_ld", C.c_int32), ("out_fp32", C.c_int32), ("out_scale", C.c_float),
-                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64), ("chan_stats", C.c_void_p)]
+                ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64), ("chan_stats", C.c_void_p),
+                ("upsample2", C.c_int32)]
 
 
 class CrossIpArgs(C.Structure):

@@ -71,8 +71,9 @@ def _out_proj(attn, a, residual):
     bias = None if lin.bias is None else lin.bias.detach().to(f32).contiguous()
     scale = 1.0 / float(getattr(attn, "rescale_output_factor", 1.0))
     res = residual.contiguous() if getattr(attn, "residual_connection", False) else None
+    # w_const=False: the bf16 copy of the weight may have been produced by the kernel right before this one
     return ops.gemm(a, lin.weight.detach().to(bf16).contiguous(), bias, residual=res,
-                    out_scale=0.0 if scale == 1.0 else scale)
+                    out_scale=0.0 if scale == 1.0 else scale, w_const=False)
 
 
 class AttnProcessor2_0(nn.Module):
@@ -89,7 +90,7 @@ class AttnProcessor2_0(nn.Module):
         hs = hidden_states.contiguous()
         ws = (attn.to_q.weight, attn.to_k.weight, attn.to_v.weight)
         wqkv = self._cache.get(ws, lambda: torch.cat([w.detach() for w in ws], 0).to(bf16).contiguous())
-        a = ops.attention_self(ops.gemm(hs, wqkv), attn.heads)
+        a = ops.attention_self(ops.gemm(hs, wqkv, w_const=False), attn.heads)
         return _out_proj(attn, a, hs)
 
 
@@ -123,10 +124,11 @@ class MaskedIPAttnProcessor2_0(nn.Module):
 
         def project():   # timestep-invariant: recomputed only when the conditioning tensor or weights change
             e = ehs.detach().to(bf16)
-            return (ops.gemm(e[:, :end].contiguous(), w_text), ops.gemm(e[:, end:].contiguous(), w_ip))
+            return (ops.gemm(e[:, :end].contiguous(), w_text, w_const=False),
+                    ops.gemm(e[:, end:].contiguous(), w_ip, w_const=False))
 
         kv_text, kv_ip = self._kv.get((ehs,) + wt + wi, project)
-        q = ops.gemm(hs, attn.to_q.weight.detach().to(bf16).contiguous())
+        q = ops.gemm(hs, attn.to_q.weight.detach().to(bf16).contiguous(), w_const=False)
         num_ips = bbox.shape[1]
         a = ops.attention_cross_ip(q, kv_text, kv_ip, bbox.detach().to(device=hs.device, dtype=f32).contiguous(),
                                    attn.heads, float(aspect_ratio), float(self.scale),

@@ -78,6 +78,9 @@ struct GemmParams {
   // last_narrow: the LAST n-tile of every m-pair is a 128-column unit instead of a (mostly padding) BN-wide one —
   // N = 640 runs as 256 | 256 | 128 and N = 320 as 192 | 128: no MMA work (or power) is spent on zero columns
   int last_narrow;
+  // 1: the weight operand is constant data (never written by a kernel that may still be in flight), so the producer
+  // may request its first tiles BEFORE griddepcontrol.wait.  0 (e.g. K / V^T of the VAE attention used as `w`): after.
+  int w_const;
   // second A operand: k-blocks [k1_iters, num_k_iters) of a plain GEMM come from tmA2 (the channel concatenation
   // [a | a2] along K is never materialised); k1_iters == num_k_iters: off
   int k1_iters;
@@ -87,6 +90,11 @@ struct GemmParams {
   int stats_rows_per_sample;  // GEMM mode: rows per sample (multiple of 128); conv mode: unused (tile = one image)
   // conv geometry
   int conv, stride, Ho, Wo, tiles_x, tiles_y, cin_chunks, conv_B;
+  // filter-tap geometry: taps are enumerated row-major over a taps_x-wide window whose first tap sits at input offset
+  // (off_x, off_y) from the output pixel: 3x3 / pad 1 = {3, -1, -1}; one phase of the fused nearest-x2-upsample conv =
+  // {2, -1|0, -1|0}.  out_stride: the output patch is written to every out_stride-th pixel of the output tensor map
+  // (2 for an upsample phase, whose map starts at that phase's first pixel).
+  int taps_x, off_x, off_y, out_stride;
 };
 
 // PAIR = 1: one CTA owns a 128 x BN tile.  PAIR = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) owns a
@@ -178,7 +186,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();  // everything above overlapped the previous kernel's tail; from here on we touch its outputs
+  // Everything above overlapped the previous kernel's tail; from here on we touch its outputs.  The TMA producer lane
+  // waits later: it first requests the WEIGHT tiles of its first pipeline stages (weights are never written by a
+  // predecessor kernel), so their HBM latency also hides behind the predecessor's tail.
+  const bool is_producer_lane = (warp == 0) && (lane == 0);
+  if (!is_producer_lane) pdl_wait();
 
   const int total_tiles = p.total_items;  // work items: whole units, then the K-slices of the tail units
   // item -> (unit, k-block range [k0, k1), index of the unit among the tail units or -1)
@@ -219,6 +231,22 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int pre_b = 0;  // k-blocks of the FIRST item whose weight tile was requested before griddepcontrol.wait
+      if (p.w_const && unit0 < total_tiles) {
+        int unit, k0, k1, tail_idx, m_pair, n_org, bn;
+        decode(unit0, unit, k0, k1, tail_idx);
+        unit_geom(unit, m_pair, n_org, bn);
+        const CUtensorMap* bm = (bn != BN) ? &tmB2 : &tmB;
+        const int b_row0 = n_org + static_cast<int>(cta_rank) * (bn / PAIR);
+        pre_b = (k1 - k0) < STAGES ? (k1 - k0) : STAGES;
+        for (int i = 0; i < pre_b; ++i) {  // stage i, first pass: the slot is free, its barrier is in phase 0
+          if (PAIR == 2)
+            tma_load_2d_pair(sB + i * Cfg::kBBytes, bm, &full_bar[i], (k0 + i) * kBK, b_row0);
+          else
+            tma_load_2d(sB + i * Cfg::kBBytes, bm, &full_bar[i], (k0 + i) * kBK, b_row0);
+        }
+      }
+      pdl_wait();
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         int unit, k0, k1, tail_idx;
         decode(tile, unit, k0, k1, tail_idx);
@@ -249,13 +277,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (p.conv) {
             const int tap = kb / p.cin_chunks;
             const int cc = kb - tap * p.cin_chunks;
-            const int r = tap / 3, s = tap - r * 3;
+            const int r = tap / p.taps_x, s = tap - r * p.taps_x;
             if (PAIR == 2)
-              tma_load_4d_pair(sA + stage * kABytes, &tmA, &full_bar[stage], cc * kBK, x0 * p.stride + s - 1,
-                               y0 * p.stride + r - 1, img);
+              tma_load_4d_pair(sA + stage * kABytes, &tmA, &full_bar[stage], cc * kBK, x0 * p.stride + s + p.off_x,
+                               y0 * p.stride + r + p.off_y, img);
             else
-              tma_load_4d(sA + stage * kABytes, &tmA, &full_bar[stage], cc * kBK, x0 * p.stride + s - 1,
-                          y0 * p.stride + r - 1, img);
+              tma_load_4d(sA + stage * kABytes, &tmA, &full_bar[stage], cc * kBK, x0 * p.stride + s + p.off_x,
+                          y0 * p.stride + r + p.off_y, img);
           } else {
             const bool second = kb >= p.k1_iters;  // [a | a2] along K
             const CUtensorMap* am = second ? &tmA2 : &tmA;
@@ -265,10 +293,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             else
               tma_load_2d(sA + stage * kABytes, am, &full_bar[stage], kc, m_blk * kBM);
           }
-          if (PAIR == 2)
+          if (tile == unit0 && kb - k0 < pre_b) {
+            // weight tile already in flight (requested before griddepcontrol.wait); its bytes count towards the
+            // expect_tx above — complete_tx may precede expect_tx within a phase (the tx-count is signed)
+          } else if (PAIR == 2) {
             tma_load_2d_pair(sB + stage * Cfg::kBBytes, bm, &full_bar[stage], kb * kBK, b_row0);
-          else
+          } else {
             tma_load_2d(sB + stage * Cfg::kBBytes, bm, &full_bar[stage], kb * kBK, b_row0);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -654,7 +686,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (p.conv)
               asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                                &tmC),
-                           "r"(smem_u32(stage)), "r"(no0), "r"(cx), "r"(cy), "r"(cimg)
+                           "r"(smem_u32(stage)), "r"(no0), "r"(cx * p.out_stride), "r"(cy * p.out_stride), "r"(cimg)
                            : "memory");
             else
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
@@ -760,7 +792,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       release_acc(acc);
     }
-    if (p.tma_epilogue && wq == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // the staging tile must outlive the store's READ of it; global visibility of the bulk stores is the grid's
+    // completion (what griddepcontrol.wait / stream order of the consumer waits for)
+    if (p.tma_epilogue && wq == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   // ---------------------------------------------------------------------- teardown
@@ -924,6 +958,16 @@ static int pick_bn(int N, int epilogue) {
 // Output / residual tensor maps for the TMA epilogue: plain GEMM = 2-D {n_out, M}, box {64, 128};
 // conv = 4-D NHWC {Cout, Wo, Ho, B}, box {64, 16, 8, 1} (the same 8x16 pixel patch as the M tile).
 static bool make_out_map(CUtensorMap* m, const void* base, const GemmParams& p, int ld, int conv_B) {
+  if (p.conv && p.out_stride == 2) {
+    // one phase of the fused nearest-x2 upsample: `base` points at the phase's first pixel of the FULL-resolution
+    // [B][2Ho][2Wo][C] output; the 8x16 patch lands on every second pixel in x and y (tensor-map element strides)
+    const uint64_t Wf = 2ull * p.Wo, Hf = 2ull * p.Ho;
+    const uint64_t dims[4] = {static_cast<uint64_t>(p.n_out), Wf - 1, Hf - 1, static_cast<uint64_t>(conv_B)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, Wf * ld * 2, Hf * Wf * ld * 2};
+    const uint32_t box[4] = {64, 2 * kConvTileW, 2 * kConvTileH, 1};
+    const uint32_t es[4] = {1, 2, 2, 1};
+    return encode_tmap_bf16(m, base, 4, dims, strides, box, es);
+  }
   if (p.conv) {
     const uint64_t dims[4] = {static_cast<uint64_t>(p.n_out), static_cast<uint64_t>(p.Wo), static_cast<uint64_t>(p.Ho),
                               static_cast<uint64_t>(conv_B)};
@@ -972,6 +1016,14 @@ static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const void*
     if (p.residual && !make_out_map(&tmR, p.residual, p, p.ldres, conv_B)) return DS_ERR_CUDA;
   }
   p.conv_B = conv_B;
+  // DS_GEMM_EARLY_W=1: request the first weight tiles BEFORE griddepcontrol.wait.  MEASURED neutral (isolated
+  // launches 31.6 vs 31.8 us, step 59.14 vs 59.08 ms at equal clocks), so it stays opt-in: it is only legal when `w` is
+  // constant data (w_is_constant), a constraint not worth carrying for nothing.
+  static const int early_w_env = [] {
+    const char* e = getenv("DS_GEMM_EARLY_W");
+    return e ? atoi(e) : 0;
+  }();
+  if (!early_w_env) p.w_const = 0;
   p.num_n_tiles = (p.N + bn - 1) / bn;
   p.wide_units = 0;
   p.wide_m_pairs = 0;
@@ -1104,8 +1156,11 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
   p.num_k_iters = (a->K + kBK - 1) / kBK;
   p.k1_iters = p.num_k_iters;
   p.conv = 0;
+  p.taps_x = 3;
+  p.out_stride = 1;
   p.chan_stats = a->chan_stats;
   p.stats_rows_per_sample = a->stats_rows_per_sample;
+  p.w_const = a->w_is_constant != 0;
   CUtensorMap tmA2 = tmA;
   if (a->a2) {
     DS_REQUIRE(a->K1 > 0 && a->K1 < a->K && a->K1 % kBK == 0, "ds_gemm_bf16: a2 needs 0 < K1 < K and K1 %% 64 == 0");
@@ -1133,18 +1188,10 @@ extern "C" int64_t ds_gemm_splitk_ws_bytes(void) {
   return 1024 + static_cast<int64_t>(sms / 2) * 256 * 256 * 4;
 }
 
-extern "C" int ds_conv3x3_nhwc(const ds_conv3x3_args* a, void* stream) {
-  using namespace ds;
-  DS_REQUIRE(a != nullptr, "ds_conv3x3_nhwc: args is NULL");
-  DS_REQUIRE(a->x && a->w && a->out, "ds_conv3x3_nhwc: x/w/out must be non-NULL");
-  DS_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "ds_conv3x3_nhwc: bad geometry");
-  DS_REQUIRE(a->Cin % 64 == 0, "ds_conv3x3_nhwc: Cin must be a multiple of 64 (got %d)", a->Cin);
-  DS_REQUIRE(a->stride == 1 || a->stride == 2, "ds_conv3x3_nhwc: stride must be 1 or 2 (got %d)", a->stride);
-  DS_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
-             "ds_conv3x3_nhwc: x and w must be 16-byte aligned");
-  const int Ho = (a->H - 1) / a->stride + 1;
-  const int Wo = (a->W - 1) / a->stride + 1;
-
+namespace ds {
+// one launch of the implicit-GEMM conv: `taps_y x taps_x` window at offset (off_x, off_y), weights [Cout][taps][Cin]
+static int conv_launch(const ds_conv3x3_args* a, const void* w, void* out, int Ho, int Wo, int taps_y, int taps_x,
+                       int off_x, int off_y, int out_stride, cudaStream_t stream) {
   CUtensorMap tmA;
   {
     const uint64_t dims[4] = {static_cast<uint64_t>(a->Cin), static_cast<uint64_t>(a->W),
@@ -1156,16 +1203,17 @@ extern "C" int ds_conv3x3_nhwc(const ds_conv3x3_args* a, void* stream) {
     const uint32_t es[4] = {1, static_cast<uint32_t>(a->stride), static_cast<uint32_t>(a->stride), 1};
     if (!encode_tmap_bf16(&tmA, a->x, 4, dims, strides, box, es)) return DS_ERR_CUDA;
   }
+  const int taps = taps_y * taps_x;
   GemmParams p{};
   p.bias = a->bias;
   p.rowbias = a->rowbias;
   p.residual = static_cast<const __nv_bfloat16*>(a->residual);
-  p.out = a->out;
+  p.out = out;
   p.tiles_x = (Wo + kConvTileW - 1) / kConvTileW;
   p.tiles_y = (Ho + kConvTileH - 1) / kConvTileH;
   p.M = a->B * Ho * Wo;
   p.N = a->Cout;
-  p.K = 9 * a->Cin;
+  p.K = taps * a->Cin;
   p.n_out = a->Cout;
   p.ldo = a->Cout;
   p.ldres = a->Cout;
@@ -1175,14 +1223,51 @@ extern "C" int ds_conv3x3_nhwc(const ds_conv3x3_args* a, void* stream) {
   p.out_fp32 = a->out_fp32;
   p.out_scale = a->out_scale == 1.0f ? 0.0f : a->out_scale;
   p.num_m_tiles = a->B * p.tiles_x * p.tiles_y;
-  p.num_k_iters = 9 * (a->Cin / kBK);
+  p.num_k_iters = taps * (a->Cin / kBK);
   p.conv = 1;
   p.stride = a->stride;
   p.Ho = Ho;
   p.Wo = Wo;
   p.cin_chunks = a->Cin / kBK;
+  p.taps_x = taps_x;
+  p.off_x = off_x;
+  p.off_y = off_y;
+  p.out_stride = out_stride;
   p.k1_iters = p.num_k_iters;
   p.chan_stats = a->chan_stats;
-  return run_gemm(tmA, tmA, a->w, 9 * a->Cin, p, a->B, static_cast<cudaStream_t>(stream), false, a->splitk_ws,
-                  a->splitk_ws_bytes);
+  p.w_const = 1;  // conv filters are parameters
+  return run_gemm(tmA, tmA, w, taps * a->Cin, p, a->B, stream, false, a->splitk_ws, a->splitk_ws_bytes);
+}
+}  // namespace ds
+
+extern "C" int ds_conv3x3_nhwc(const ds_conv3x3_args* a, void* stream) {
+  using namespace ds;
+  DS_REQUIRE(a != nullptr, "ds_conv3x3_nhwc: args is NULL");
+  DS_REQUIRE(a->x && a->w && a->out, "ds_conv3x3_nhwc: x/w/out must be non-NULL");
+  DS_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0 && a->Cin > 0 && a->Cout > 0, "ds_conv3x3_nhwc: bad geometry");
+  DS_REQUIRE(a->Cin % 64 == 0, "ds_conv3x3_nhwc: Cin must be a multiple of 64 (got %d)", a->Cin);
+  DS_REQUIRE(a->stride == 1 || a->stride == 2, "ds_conv3x3_nhwc: stride must be 1 or 2 (got %d)", a->stride);
+  DS_REQUIRE((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->w) & 15) == 0,
+             "ds_conv3x3_nhwc: x and w must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->upsample2) {
+    // conv3x3(nearest_x2(x)) as FOUR 2x2 convolutions of x, one per output-pixel parity (a, b): the 3x3 taps that read
+    // the same low-resolution pixel are pre-summed (weights.pack_conv3x3_up2), so the op does 16 instead of 36 MACs per
+    // (low-res pixel, Cin, Cout) and the upsampled tensor is never written.  Phase (a, b) writes pixels (2i+a, 2j+b).
+    DS_REQUIRE(a->stride == 1 && !a->residual && !a->rowbias && !a->out_fp32 && a->Cout % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(a->out) & 15) == 0,
+               "ds_conv3x3_nhwc: upsample2 needs stride 1, bf16 output with Cout %% 8 == 0, no residual / rowbias");
+    const size_t wph = static_cast<size_t>(a->Cout) * 4 * a->Cin;  // elements per phase: [Cout][2][2][Cin]
+    for (int ph = 0; ph < 4; ++ph) {
+      const int pa = ph >> 1, pb = ph & 1;
+      const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(a->w) + ph * wph;
+      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(a->out) + (static_cast<size_t>(pa) * 2 * a->W + pb) * a->Cout;
+      const int rc = conv_launch(a, w, o, a->H, a->W, 2, 2, pb ? 0 : -1, pa ? 0 : -1, 2, st);
+      if (rc != DS_OK) return rc;
+    }
+    return DS_OK;
+  }
+  const int Ho = (a->H - 1) / a->stride + 1;
+  const int Wo = (a->W - 1) / a->stride + 1;
+  return conv_launch(a, a->w, a->out, Ho, Wo, 3, 3, -1, -1, 1, st);
 }

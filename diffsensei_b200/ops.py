@@ -205,12 +205,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          ln_stats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
          row_stats_out: Optional[torch.Tensor] = None, zero_rows: Optional[torch.Tensor] = None,
          row_stats_zeroed: bool = False, a2: Optional[torch.Tensor] = None,
-         chan_stats: Optional[torch.Tensor] = None, stats_rows_per_sample: int = 0) -> torch.Tensor:
+         chan_stats: Optional[torch.Tensor] = None, stats_rows_per_sample: int = 0,
+         w_const: bool = True) -> torch.Tensor:
     """out[..., Nout] = epilogue(a[..., K] @ w[N, K]^T) on tcgen05; ``a`` may have any leading dims.
 
     LayerNorm fusion (include/dsengine.h): ``ln_stats`` [2*M] fp64 {sum, sumsq} per row of ``a`` + ``ln_colsum`` [N]
     turn the call into LayerNorm(a) @ w_orig^T for weights folded by ``weights.fold_layernorm``; ``row_stats_out``
-    [2*M] fp64 receives {sum, sumsq} of every (bf16-rounded) output row."""
+    [2*M] fp64 receives {sum, sumsq} of every (bf16-rounded) output row.
+    ``w_const=False`` when ``w`` is not a parameter but the output of a preceding kernel (it is then fetched only after
+    the programmatic-dependent-launch wait)."""
     _req(a, bf16, "gemm.a")
     _req(w, bf16, "gemm.w", 2)
     K1 = a.shape[-1]
@@ -274,7 +277,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
                     row_stats_zeroed=int(bool(row_stats_zeroed)), splitk_ws=_ptr(ws),
                     splitk_ws_bytes=0 if ws is None else ws.numel() * 4,
                     a2=_ptr(a2), K1=K1, lda2=0 if a2 is None else a2.shape[-1],
-                    chan_stats=_ptr(chan_stats), stats_rows_per_sample=int(stats_rows_per_sample))
+                    chan_stats=_ptr(chan_stats), stats_rows_per_sample=int(stats_rows_per_sample),
+                    w_is_constant=int(bool(w_const)))
     check(lib.ds_gemm_bf16(C.byref(args), _stream()), "ds_gemm_bf16")
     return out
 
@@ -282,15 +286,24 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
 def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, stride: int = 1,
             rowbias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
             out: Optional[torch.Tensor] = None, out_fp32: bool = False,
-            chan_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """3x3 / pad 1 conv on NHWC bf16 ``x``; ``w`` is packed [Cout, 3, 3, Cin] bf16 (weights.pack_conv3x3)."""
+            chan_stats: Optional[torch.Tensor] = None, upsample2: bool = False) -> torch.Tensor:
+    """3x3 / pad 1 conv on NHWC bf16 ``x``; ``w`` is packed [Cout, 3, 3, Cin] bf16 (weights.pack_conv3x3).
+    ``upsample2``: conv3x3(nearest_x2(x)) without the upsampled tensor — ``w`` is then the phase-decomposed
+    [4, Cout, 2, 2, Cin] packing of ``weights.pack_conv3x3_up2`` and the output is [B, 2H, 2W, Cout]."""
     _req(x, bf16, "conv3x3.x", 4)
     B, H, W, Cin = x.shape
-    _req(w, bf16, "conv3x3.w", 4)
-    Cout = w.shape[0]
-    if tuple(w.shape[1:]) != (3, 3, Cin):
-        raise DsEngineError(f"conv3x3: w must be [Cout,3,3,{Cin}], got {tuple(w.shape)}")
-    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if upsample2:
+        _req(w, bf16, "conv3x3.w", 5)
+        Cout = w.shape[1]
+        if tuple(w.shape) != (4, Cout, 2, 2, Cin) or stride != 1 or residual is not None or rowbias is not None or out_fp32:
+            raise DsEngineError("conv3x3(upsample2): w must be [4,Cout,2,2,Cin]; stride 1, no residual / rowbias / fp32 out")
+        Ho, Wo = 2 * H, 2 * W
+    else:
+        _req(w, bf16, "conv3x3.w", 4)
+        Cout = w.shape[0]
+        if tuple(w.shape[1:]) != (3, 3, Cin):
+            raise DsEngineError(f"conv3x3: w must be [Cout,3,3,{Cin}], got {tuple(w.shape)}")
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     if bias is not None:
         _req(bias, f32, "conv3x3.bias", 1)
     if rowbias is not None:
@@ -316,7 +329,8 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
                        residual=_ptr(residual), B=B, H=H, W=W, Cin=Cin, Cout=Cout, stride=stride,
                        rowbias_ld=0 if rowbias is None else rowbias.stride(0),
                        out_fp32=int(out_fp32), out_scale=0.0, splitk_ws=_ptr(ws),
-                       splitk_ws_bytes=0 if ws is None else ws.numel() * 4, chan_stats=_ptr(chan_stats))
+                       splitk_ws_bytes=0 if ws is None else ws.numel() * 4, chan_stats=_ptr(chan_stats),
+                       upsample2=int(bool(upsample2)))
     check(lib.ds_conv3x3_nhwc(C.byref(args), _stream()), "ds_conv3x3_nhwc")
     return out
 

@@ -26,8 +26,8 @@ import torch
 
 from . import ops
 from .config import UNetConfig
-from .weights import (bf, colsum_bf16, fold_layernorm, fp, pack_conv3x3, pack_conv_in, pack_geglu, resnet_io,
-                      transformer_sites, unet_param_shapes)
+from .weights import (bf, colsum_bf16, fold_layernorm, fp, pack_conv3x3, pack_conv3x3_up2, pack_conv_in, pack_geglu,
+                      resnet_io, transformer_sites, unet_param_shapes)
 
 bf16, f32 = torch.bfloat16, torch.float32
 
@@ -213,8 +213,11 @@ class UNetMangaEngine:
         n = len(cfg.block_out_channels)
         self.down_convs = [(pack_conv3x3(W(f"down_blocks.{i}.downsamplers.0.conv.weight")),
                             fp(W(f"down_blocks.{i}.downsamplers.0.conv.bias"))) for i in range(n - 1)]
+        # Upsample2D convs: the phase-decomposed packing for the exact x2 case (fused, no upsampled tensor) and the
+        # plain 3x3 packing for `forward_upsample_size` shapes (interpolate to the skip's size, unet.py:312-313)
         self.up_convs = [(pack_conv3x3(W(f"up_blocks.{i}.upsamplers.0.conv.weight")),
-                          fp(W(f"up_blocks.{i}.upsamplers.0.conv.bias"))) for i in range(n - 1)]
+                          fp(W(f"up_blocks.{i}.upsamplers.0.conv.bias")),
+                          pack_conv3x3_up2(W(f"up_blocks.{i}.upsamplers.0.conv.weight"))) for i in range(n - 1)]
         self.norm_out = (fp(W("conv_norm_out.weight")), fp(W("conv_norm_out.bias")))
         self.conv_out_w, self.conv_out_b = pack_conv3x3(W("conv_out.weight")), fp(W("conv_out.bias"))
         self._loaded = True
@@ -429,9 +432,12 @@ class UNetMangaEngine:
                     Ho, Wo = skips[-1][0].shape[1:3]                                  # unet.py:312-313
                 else:
                     Ho, Wo = 2 * h.shape[1], 2 * h.shape[2]
-                w, b = self.up_convs[i]
+                w, b, w_up = self.up_convs[i]
                 st = pool.take(rch[i])
-                h = ops.conv3x3(ops.upsample_nearest(h, Ho, Wo), w, b, chan_stats=st)
+                if (Ho, Wo) == (2 * h.shape[1], 2 * h.shape[2]):
+                    h = ops.conv3x3(h, w_up, b, chan_stats=st, upsample2=True)        # nearest x2 folded into the conv
+                else:
+                    h = ops.conv3x3(ops.upsample_nearest(h, Ho, Wo), w, b, chan_stats=st)
         h = ops.groupnorm_apply(h, self._stats(h, st, pool), self.norm_out[0], self.norm_out[1], cfg.norm_num_groups,
                                 1e-5, True, out=h)
         return ops.conv3x3(h, self.conv_out_w, self.conv_out_b, out=out)

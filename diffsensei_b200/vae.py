@@ -22,7 +22,7 @@ import torch
 
 from . import ops
 from .config import VaeConfig
-from .weights import bf, fp, pack_conv3x3, vae_decoder_param_shapes
+from .weights import bf, fp, pack_conv3x3, pack_conv3x3_up2, vae_decoder_param_shapes
 
 bf16, f32 = torch.bfloat16, torch.float32
 
@@ -98,7 +98,7 @@ class VaeDecoderEngine:
                                            for j in range(self.cfg.layers_per_block + 1)], up=None)
             if i < len(rev) - 1:
                 u = f"decoder.up_blocks.{i}.upsamplers.0.conv"
-                blk.up = (pack_conv3x3(W(u + ".weight")), fp(W(u + ".bias")))
+                blk.up = (pack_conv3x3_up2(W(u + ".weight")), fp(W(u + ".bias")))          # fused nearest x2 + conv
             self.ups.append(blk)
             prev = co
         self.norm_out = norm("decoder.conv_norm_out")
@@ -132,10 +132,10 @@ class VaeDecoderEngine:
         P = torch.empty(N, N, dtype=bf16, device=x.device)
         for b in range(B):
             rows = slice(b * N, (b + 1) * N)
-            ops.gemm(q[rows], k[rows], out=S, out_fp32=True)                         # S = Q K^T  (fp32)
+            ops.gemm(q[rows], k[rows], out=S, out_fp32=True, w_const=False)          # S = Q K^T  (fp32)
             ops.softmax_rows(S, C ** -0.5, out=P)
             vT = ops.nhwc_to_nchw(v[rows].view(1, N, 1, C), bf16).view(C, N)         # V^T: K-major B operand
-            ops.gemm(P, vT, out=o[rows])                                             # O = P V
+            ops.gemm(P, vT, out=o[rows], w_const=False)                              # O = P V
         ost = pool.take(C) if N % 128 == 0 else None
         out = ops.gemm(o, a.wo, a.bo, residual=x.view(B * N, C), chan_stats=ost,
                        stats_rows_per_sample=N if ost is not None else 0)
@@ -163,8 +163,7 @@ class VaeDecoderEngine:
                 x, st = self._resnet(r, x, st, pool, want_stats=not last)
             if blk.up is not None:
                 st = pool.take(x.shape[-1])
-                x = ops.conv3x3(ops.upsample_nearest(x, 2 * x.shape[1], 2 * x.shape[2]), blk.up[0], blk.up[1],
-                                chan_stats=st)
+                x = ops.conv3x3(x, blk.up[0], blk.up[1], chan_stats=st, upsample2=True)
         x = ops.groupnorm_apply(x, st, self.norm_out[0], self.norm_out[1], self.cfg.norm_num_groups, 1e-6, True, out=x)
         return ops.conv3x3(x, self.conv_out_w, self.conv_out_b)
 

@@ -232,6 +232,22 @@ def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     return w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
 
 
+def pack_conv3x3_up2(w: torch.Tensor) -> torch.Tensor:
+    """OIHW 3x3 weights of a conv that follows a nearest x2 upsample -> the four 2x2 phase kernels of the fused op,
+    [4][Cout][2][2][Cin] bf16 (phase = 2*a + b for output pixels (2i+a, 2j+b)).  Output row 2i+a reads upsampled rows
+    2i+a-1 .. 2i+a+1 = low-res rows {i-1, i, i} (a = 0) or {i, i, i+1} (a = 1): taps that land on the same low-res pixel
+    are summed (in fp32, one rounding to bf16)."""
+    wf = w.float()
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}          # parity -> (taps of window row 0, taps of window row 1)
+    out = []
+    for a in (0, 1):
+        for b in (0, 1):
+            k = torch.stack([torch.stack([wf[:, :, rows[a][u]][:, :, :, rows[b][v]].sum(dim=(2, 3)) for v in (0, 1)], dim=1)
+                             for u in (0, 1)], dim=1)                     # [Cout, 2(u), 2(v), Cin]
+            out.append(k)
+    return torch.stack(out, 0).contiguous().to(torch.bfloat16)
+
+
 def pack_conv_in(w: torch.Tensor) -> torch.Tensor:
     """conv_in OIHW [Cout, 4, 3, 3] -> [Cout, 64] bf16: column tap*4 + c (taps row-major), columns 36..63 zero — the
     B operand matching ``ops.im2col_latent``."""

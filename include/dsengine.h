@@ -167,6 +167,10 @@ typedef struct {
    * TMA epilogue (16-byte rows), no GEGLU, stats_rows_per_sample % 128 == 0.  NULL: off. */
   double* chan_stats;
   int32_t stats_rows_per_sample;
+  /* 1: `w` is constant data (model weights: never written by a kernel that can still be in flight) — the kernel may
+   * then request its first weight tiles before it waits for the preceding kernel (programmatic dependent launch).
+   * 0: `w` may have been produced by a preceding kernel (an activation used as the B operand): fetched after the wait. */
+  int32_t w_is_constant;
 } ds_gemm_args;
 
 int ds_gemm_bf16(const ds_gemm_args* args, void* stream);
@@ -200,6 +204,12 @@ typedef struct {
   void* splitk_ws;    /* as in ds_gemm_args */
   int64_t splitk_ws_bytes;
   double* chan_stats; /* fp64 [B][Cout][2] producer-side GroupNorm statistics, as in ds_gemm_args; NULL: off */
+  /* 1: out = conv3x3(nearest_x2(x)) — diffusers Upsample2D (F.interpolate(scale_factor=2, mode="nearest") + conv,
+   * reached from src/models/unet.py:335-338) — WITHOUT materialising the upsampled tensor: four 2x2 convolutions of x,
+   * one per output-pixel parity, whose taps are the pre-summed 3x3 taps that read the same input pixel (16 instead of
+   * 36 MACs per input pixel).  x: [B][H][W][Cin], out: [B][2H][2W][Cout] bf16, w: [4][Cout][2][2][Cin] bf16 from
+   * weights.pack_conv3x3_up2 (phase = 2*row_parity + col_parity).  stride 1, no residual / rowbias. */
+  int32_t upsample2;
 } ds_conv3x3_args;
 
 int ds_conv3x3_nhwc(const ds_conv3x3_args* args, void* stream);

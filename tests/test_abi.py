@@ -76,5 +76,5 @@ def test_new_gemm_fields_default_to_off():
     a = _lib.GemmArgs()
     assert not a.ln_stats and not a.ln_colsum and not a.row_stats_out and not a.zero_rows and not a.splitk_ws
     assert a.row_stats_zeroed == 0 and a.splitk_ws_bytes == 0
-    assert not a.a2 and not a.chan_stats and a.K1 == 0 and a.stats_rows_per_sample == 0
+    assert not a.a2 and not a.chan_stats and a.K1 == 0 and a.stats_rows_per_sample == 0 and a.w_is_constant == 0
     assert not _lib.Conv3x3Args().chan_stats

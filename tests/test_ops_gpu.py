@@ -421,3 +421,20 @@ def test_conv_in_as_im2col_gemm(ops, B, H, W, Cout):
     assert a.shape == (B * H * W, 64) and torch.count_nonzero(a[:, 36:]).item() == 0
     got = ops.gemm(a, pack_conv_in(w).to(DEV), b.to(DEV)).view(B, H, W, Cout)
     assert rel_l2(got.float(), want) < 6e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 8, 16, 64, 64), (1, 9, 13, 128, 320), (2, 32, 32, 640, 640), (1, 19, 5, 64, 128)])
+def test_conv3x3_fused_nearest_upsample(ops, B, H, W, Cin, Cout):
+    """Upsample2D: conv3x3(F.interpolate(x, scale_factor=2, mode='nearest')) as four 2x2 phase convolutions of x
+    (ds_conv3x3_nhwc upsample2): ragged patches, odd sizes, and the producer statistics accumulated over the 4 launches."""
+    from diffsensei_b200.weights import pack_conv3x3_up2
+    x = _r(B, H, W, Cin, seed=40)
+    w = _r(Cout, Cin, 3, 3, seed=41, scale=(9 * Cin) ** -0.5)
+    bias = torch.randn(Cout) * 0.1
+    want = F.conv2d(F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest"), w.float(), bias,
+                    padding=1).permute(0, 2, 3, 1)
+    st = torch.zeros(B, Cout, 2, dtype=torch.float64, device=DEV)
+    got = ops.conv3x3(x.to(DEV), pack_conv3x3_up2(w.float()).to(DEV), bias.to(DEV), chan_stats=st, upsample2=True)
+    assert got.shape == (B, 2 * H, 2 * W, Cout)
+    assert rel_l2(got.float(), want) < 8e-3            # + one bf16 rounding of the pre-summed taps
+    assert torch.allclose(st.cpu(), _chan_stats_ref(got.cpu()), rtol=1e-5, atol=1e-3)

@@ -36,6 +36,7 @@ ops.layernorm = lambda x, g, b, eps=1e-5, out=None: same(x)
 ops.conv_in = lambda x, w, b, out=None: E(*x.shape[:3], w.shape[0])
 ops.im2col_latent = lambda x: E(x.shape[0] * x.shape[1] * x.shape[2], 64)
 unet_mod.pack_conv_in = lambda w: E(w.shape[0], 64)
+unet_mod.pack_conv3x3_up2 = lambda w: E(4, w.shape[0], 2, 2, w.shape[1])
 ops.concat_channels = lambda a, b, out=None: E(*a.shape[:-1], a.shape[-1] + b.shape[-1])
 ops.upsample_nearest = lambda x, Ho, Wo, out=None: E(x.shape[0], Ho, Wo, x.shape[3])
 
