@@ -30,6 +30,11 @@
 // Reference arithmetic replaced: every nn.Linear / nn.Conv2d on the UNet sampling path
 // (src/models/attention_processor.py:56-84,207-261; diffusers blocks reached from src/models/unet.py:190-338).
 #include <cstdlib>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <queue>
+#include <vector>
 
 #include "ds_common.cuh"
 #include "ds_host.h"
@@ -116,12 +121,36 @@ struct GemmCfg {
       kStages * kStageBytes + kStageOutBytes + kVecBytes + kStatBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int PAIR, bool STATS>
+// One launch = 1 problem (MAXQ = 1), or a CHAIN of up to kMaxChain dependent GEMMs over the same M rows (ds_gemm_chain):
+// problem q+1 reads the output of problem q as its A operand.  The persistent CTAs walk the problems in order with
+// their pipeline state (smem ring, TMEM accumulators, barrier phases) carried across; a unit of problem q+1 on the
+// 128-row block m waits — in the TMA producer, spinning on a global counter — until all n-tiles of problem q for that
+// row block have been written (the epilogue bumps the counter after its stores have completed).  What this buys: one
+// launch + prologue + drain instead of one per GEMM (~9 us each), and the CTA pairs that run out of problem-q units
+// start on problem q+1 instead of idling through the partial last round.
+constexpr int kMaxChain = 4;
+template <int MAXQ>
+struct GemmLaunch {
+  CUtensorMap tm[MAXQ][6];  // per problem: A, B, C (output), R (residual), A2, B2 (narrow units)
+  GemmParams p[MAXQ];
+  int nq;
+  int* dep;        // [nq][dep_stride] finished n-tiles per (problem, 128-row block), all zero at launch; NULL: nq == 1
+  int dep_stride;
+  // chain schedule (host-built, see build_chain_schedule): for CTA pair g, the items of problem q are
+  // sched[sched_items + i] for i in [sched[g * (kMaxChain + 1) + q], sched[g * (kMaxChain + 1) + q + 1])
+  const int* sched;
+  int sched_items;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+
+template <int BN, int PAIR, bool STATS, int MAXQ>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                  const GemmParams p) {
+gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
   using Cfg = GemmCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::kStages;
   const uint32_t cta_rank = (PAIR == 2) ? cluster_ctarank() : 0u;  // rank inside the CTA pair; 0 = leader
@@ -148,14 +177,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    if (p.tma_epilogue) {
-      tma_prefetch_desc(&tmC);
-      if (p.residual) tma_prefetch_desc(&tmR);
+    for (int q = 0; q < (MAXQ == 1 ? 1 : L.nq); ++q) {
+      const GemmParams& pq = L.p[q];
+      tma_prefetch_desc(&L.tm[q][0]);
+      tma_prefetch_desc(&L.tm[q][1]);
+      if (pq.tma_epilogue) {
+        tma_prefetch_desc(&L.tm[q][2]);
+        if (pq.residual) tma_prefetch_desc(&L.tm[q][3]);
+      }
+      if (pq.k1_iters < pq.num_k_iters) tma_prefetch_desc(&L.tm[q][4]);
+      if (pq.nt_narrow > 0 || pq.last_narrow) tma_prefetch_desc(&L.tm[q][5]);
     }
-    if (p.k1_iters < p.num_k_iters) tma_prefetch_desc(&tmA2);
-    if (p.nt_narrow > 0 || p.last_narrow) tma_prefetch_desc(&tmB2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -192,7 +224,29 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const bool is_producer_lane = (warp == 0) && (lane == 0);
   if (!is_producer_lane) pdl_wait();
 
+  // pipeline state carried from one problem of a chain to the next (each thread plays one role)
+  int st_stage = 0, st_iter = 0;
+  uint32_t st_phase = 0, st_res_phase = 0;
+  const int nq = MAXQ == 1 ? 1 : L.nq;
+  for (int q = 0; q < nq; ++q) {
+  const GemmParams& p = L.p[q];
+  const CUtensorMap& tmA = L.tm[q][0];
+  const CUtensorMap& tmB = L.tm[q][1];
+  const CUtensorMap& tmC = L.tm[q][2];
+  const CUtensorMap& tmR = L.tm[q][3];
+  const CUtensorMap& tmA2 = L.tm[q][4];
+  const CUtensorMap& tmB2 = L.tm[q][5];
   const int total_tiles = p.total_items;  // work items: whole units, then the K-slices of the tail units
+  // this CTA (pair)'s items of the problem: round-robin over the grid, or — chain — its row of the host-built schedule
+  int it_beg = unit0, it_end = total_tiles, it_step = unit_step;
+  const int* sched_items = nullptr;
+  if (MAXQ > 1) {
+    const int* hdr = L.sched + unit0 * (kMaxChain + 1);
+    it_beg = __ldg(hdr + q);
+    it_end = __ldg(hdr + q + 1);
+    it_step = 1;
+    sched_items = L.sched + L.sched_items;
+  }
   // item -> (unit, k-block range [k0, k1), index of the unit among the tail units or -1)
   auto decode = [&](int item, int& unit, int& k0, int& k1, int& tail_idx) {
     if (item < p.tail_start) {
@@ -229,10 +283,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int& stage = st_stage;
+      uint32_t& phase = st_phase;
       int pre_b = 0;  // k-blocks of the FIRST item whose weight tile was requested before griddepcontrol.wait
-      if (p.w_const && unit0 < total_tiles) {
+      if (MAXQ == 1 && p.w_const && unit0 < total_tiles) {
         int unit, k0, k1, tail_idx, m_pair, n_org, bn;
         decode(unit0, unit, k0, k1, tail_idx);
         unit_geom(unit, m_pair, n_org, bn);
@@ -246,14 +300,27 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_2d(sB + i * Cfg::kBBytes, bm, &full_bar[i], (k0 + i) * kBK, b_row0);
         }
       }
-      pdl_wait();
-      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
+      if (q == 0) pdl_wait();
+      for (int it = it_beg; it < it_end; it += it_step) {
+        const int tile = MAXQ > 1 ? __ldg(sched_items + it) : it;
         int unit, k0, k1, tail_idx;
         decode(tile, unit, k0, k1, tail_idx);
         int m_pair, n_org, bn;
         unit_geom(unit, m_pair, n_org, bn);
         const bool narrow = bn != BN;
         const int m_blk = m_pair * PAIR + static_cast<int>(cta_rank);
+        if (MAXQ > 1 && q > 0 && L.dep != nullptr && m_blk * kBM < p.M) {
+          // chain dependency: the A rows of this unit are the output rows of ALL n-tiles of the previous problem
+          const int* cnt = L.dep + (q - 1) * L.dep_stride + m_blk;
+          const int need = 2 * L.p[q - 1].num_n_tiles;  // both column halves of every n-tile
+          if (ld_acquire_gpu(cnt) < need) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(cnt) < need) {
+              if (clock64() - t0 > 4000000000LL) __trap();  // a protocol bug becomes a launch error, not a hang
+            }
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy acquire -> async-proxy (TMA) reads
+        }
         const uint32_t stage_bytes = kABytes + (narrow ? (kNarrowBN / PAIR) * kBK * 2 : Cfg::kBBytes);
         int img = 0, x0 = 0, y0 = 0;
         if (p.conv) {
@@ -293,7 +360,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             else
               tma_load_2d(sA + stage * kABytes, am, &full_bar[stage], kc, m_blk * kBM);
           }
-          if (tile == unit0 && kb - k0 < pre_b) {
+          if (MAXQ == 1 && tile == unit0 && kb - k0 < pre_b) {
             // weight tile already in flight (requested before griddepcontrol.wait); its bytes count towards the
             // expect_tx above — complete_tx may precede expect_tx within a phase (the tx-count is signed)
           } else if (PAIR == 2) {
@@ -313,10 +380,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0 && leader) {  // in a pair only the leader CTA issues (for both SMs' tensor cores)
       constexpr uint32_t idesc_wide = make_idesc_bf16(kBM * PAIR, BN, 0, 0);
       constexpr uint32_t idesc_narrow = make_idesc_bf16(kBM * PAIR, kNarrowBN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int iter = 0;
-      for (int tile = unit0; tile < total_tiles; tile += unit_step, ++iter) {
+      int& stage = st_stage;
+      uint32_t& phase = st_phase;
+      int& iter = st_iter;
+      for (int it = it_beg; it < it_end; it += it_step, ++iter) {
+        const int tile = MAXQ > 1 ? __ldg(sched_items + it) : it;
         int unit, k0, k1, tail_idx;
         decode(tile, unit, k0, k1, tail_idx);
         const int acc = iter & 1;
@@ -406,8 +474,20 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     };
 
-    int iter = 0;
-    uint32_t res_phase = 0;
+    int& iter = st_iter;
+    uint32_t& res_phase = st_res_phase;
+    // chain: "this column half of an n-tile of row block m is written" is published one tile LATE: at the first
+    // group barrier of the group's next tile (or at the end of the problem).  By then the tile's bulk stores have long
+    // completed (the wait is free), every thread of the group is past its trailing statistics atomics (the barrier
+    // itself), and no barrier is added to the epilogue's critical path.  A consumer needs 2 * num_n_tiles per row block.
+    const bool chain_sig = MAXQ > 1 && L.dep != nullptr && q + 1 < nq;
+    const bool sig_issuer = (wq == 0) && (lane == 0);
+    int pend_blk = -1;  // row block whose signal is pending (group-uniform)
+    auto post_signal = [&]() {  // issuer thread, after a barrier of the group
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the bulk stores have been WRITTEN
+      asm volatile("fence.proxy.async;" ::: "memory");
+      asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(L.dep + q * L.dep_stride + pend_blk) : "memory");
+    };
     // hand the accumulator back to the MMA issuer (pair: the issuer lives in the leader CTA)
     auto release_acc = [&](int acc) {
       tc_fence_before();
@@ -419,7 +499,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_arrive(&tempty_bar[acc]);
       }
     };
-    for (int tile = unit0; tile < total_tiles; tile += unit_step, ++iter) {
+    for (int it = it_beg; it < it_end; it += it_step, ++iter) {
+      const int tile = MAXQ > 1 ? __ldg(sched_items + it) : it;
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       int unit, k0, k1, tail_idx;
@@ -433,6 +514,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // the item's output columns are handed to the two warp groups in 64-column blocks (192: 2 + 1, 64: 1 + 0)
       const int split = ((bn_out / 64 + 1) / 2) * 64;
       const int c_begin = half ? split : 0, c_end = half ? bn_out : (split < bn_out ? split : bn_out);
+      if (chain_sig && pend_blk >= 0 && !(c_begin < c_end && no_org + c_begin < p.n_out)) {
+        // this group has no column block in this item: no group barrier to piggy-back on
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+        if (sig_issuer) post_signal();
+        pend_blk = -1;
+      }
 
       // row -> (valid, output row index, batch index)
       bool row_ok;
@@ -484,16 +571,24 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       // LayerNorm-on-A: v = rstd * (acc - mean * colsum[n]) (+ folded bias); statistics of this thread's row
       float ln_mean = 0.f, ln_rstd = 1.f;
-      if (p.ln_stats && row_ok) {
-        const double2 st = __ldg(reinterpret_cast<const double2*>(p.ln_stats) + orow);
-        const double dmean = st.x * static_cast<double>(p.ln_inv_k);
-        ln_mean = static_cast<float>(dmean);
-        const float var = fmaxf(static_cast<float>(st.y * static_cast<double>(p.ln_inv_k) - dmean * dmean), 0.f);
-        ln_rstd = rsqrtf(var + p.ln_eps);
-      }
+      auto row_stats_io = [&]() {
+        if (p.ln_stats && row_ok) {
+          // chain: the statistics were written by an earlier problem of THIS launch -> no read-only (nc) path
+          const double2 st = MAXQ > 1 ? __ldcg(reinterpret_cast<const double2*>(p.ln_stats) + orow)
+                                      : __ldg(reinterpret_cast<const double2*>(p.ln_stats) + orow);
+          const double dmean = st.x * static_cast<double>(p.ln_inv_k);
+          ln_mean = static_cast<float>(dmean);
+          const float var = fmaxf(static_cast<float>(st.y * static_cast<double>(p.ln_inv_k) - dmean * dmean), 0.f);
+          ln_rstd = rsqrtf(var + p.ln_eps);
+        }
+        if (p.zero_rows && n_org == 0 && half == 0 && row_ok)
+          *reinterpret_cast<double2*>(p.zero_rows + 2 * orow) = make_double2(0.0, 0.0);
+      };
+      // One problem per launch: ahead of the accumulator wait, so the load's latency hides behind the MMAs.  Chain: the
+      // statistics (and the buffer to clear) belong to earlier problems of this launch — only touch them once this
+      // tile's accumulator is ready, i.e. after the producer saw the row block's dependency counter complete.
+      if (MAXQ == 1) row_stats_io();
       float rs_sum = 0.f, rs_sq = 0.f;  // producer side: sums over this thread's columns of the outputs
-      if (p.zero_rows && n_org == 0 && half == 0 && row_ok)
-        *reinterpret_cast<double2*>(p.zero_rows + 2 * orow) = make_double2(0.0, 0.0);
 
       // Residual prefetch: the residual tile of this thread group's FIRST 64-column block is requested before the
       // group waits for the accumulator, so its ~1 us L2 / HBM latency overlaps the tail of the tile's MMAs instead of
@@ -505,6 +600,19 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         res_prefetched = true;  // group-uniform
         if (wq == 0 && lane == 0) {
           uint8_t* stage0 = sOut + half * (kBM * 64 * 2);
+          if (MAXQ > 1 && q > 0 && L.dep != nullptr && m_blk * kBM < p.M) {
+            // chain: the residual may be the output of an earlier problem of the chain (same rows): same dependency
+            // as the A operand, taken here because this prefetch runs ahead of the main loop
+            const int* cnt = L.dep + (q - 1) * L.dep_stride + m_blk;
+            const int need = 2 * L.p[q - 1].num_n_tiles;
+            if (ld_acquire_gpu(cnt) < need) {
+              const long long t0 = clock64();
+              while (ld_acquire_gpu(cnt) < need) {
+                if (clock64() - t0 > 4000000000LL) __trap();
+              }
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           mbar_arrive_expect_tx(&res_bar[half], kBM * 64 * 2);
           if (p.conv) {
@@ -521,6 +629,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (MAXQ > 1) row_stats_io();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
 
       // ---- split-K tail: add this K-slice's accumulator into the unit's workspace tile; only the last slice to
@@ -624,6 +733,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // the previous TMA store must have finished READING the staging tile before anyone overwrites it
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (chain_sig && pend_blk >= 0) {  // the previous item of this group: see post_signal
+            if (issuer) post_signal();
+            pend_blk = -1;
+          }
           if (p.residual && !(res_prefetched && cb == c_begin) && issuer) {
             mbar_arrive_expect_tx(&res_bar[half], kBM * 64 * 2);
             if (p.conv)
@@ -750,6 +863,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           atomicAdd(p.row_stats_out + 2 * orow, static_cast<double>(rs_sum));
           atomicAdd(p.row_stats_out + 2 * orow + 1, static_cast<double>(rs_sq));
         }
+        if (chain_sig) pend_blk = m_blk;
         continue;
       }
 
@@ -792,10 +906,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       release_acc(acc);
     }
+    if (chain_sig && pend_blk >= 0) {  // the group's last item of this problem
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+      if (sig_issuer) post_signal();
+    }
     // the staging tile must outlive the store's READ of it; global visibility of the bulk stores is the grid's
     // completion (what griddepcontrol.wait / stream order of the consumer waits for)
     if (p.tma_epilogue && wq == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
+  }  // problems of the chain
 
   // ---------------------------------------------------------------------- teardown
   tc_fence_before();
@@ -803,6 +922,21 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch its smem / barriers
   else
     __syncthreads();
+  if (MAXQ > 1 && L.dep != nullptr && warp == 0) {
+    // the last CTA to get here (every CTA's dependency reads are behind it) hands the counters back zeroed, so the
+    // same buffer serves the next chain launch — and every replay of a captured graph — without a memset node
+    int* ticket = L.dep + kMaxChain * L.dep_stride;
+    int last = 0;
+    if (lane == 0) {
+      __threadfence();
+      last = atomicAdd(ticket, 1) == static_cast<int>(gridDim.x) - 1;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      for (int i = lane; i < (nq - 1) * L.dep_stride; i += 32) L.dep[i] = 0;
+      if (lane == 0) *ticket = 0;
+    }
+  }
   if (warp == 2) {
     tc_fence_after();
     if (PAIR == 2)
@@ -824,7 +958,7 @@ static int resident_groups(int num_sms) {
   int& g = cache[device_slot()];
   if (g == 0) {
     using Cfg = GemmCfg<BN, PAIR>;
-    (void)cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    (void)cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                Cfg::kSmemBytes);
     int n = num_sms / PAIR;
     if (PAIR == 2) {
@@ -840,7 +974,7 @@ static int resident_groups(int num_sms) {
       cfg.numAttrs = 1;
       cfg.gridDim = dim3((num_sms / PAIR) * PAIR);
       int q = 0;
-      if (cudaOccupancyMaxActiveClusters(&q, gemm_bf16_tcgen05<BN, PAIR, false>, &cfg) == cudaSuccess && q > 0)
+      if (cudaOccupancyMaxActiveClusters(&q, gemm_bf16_tcgen05<BN, PAIR, false, 1>, &cfg) == cudaSuccess && q > 0)
         n = q < n ? q : n;
       (void)cudaGetLastError();
     }
@@ -862,7 +996,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   const int slot = device_slot();
   static bool attr_set[kMaxDevices] = {};  // per device; benign race: idempotent
   if (!attr_set[slot]) {
-    DS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, STATS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes));
     attr_set[slot] = true;
   }
@@ -922,8 +1056,165 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     }
   }
   cfg.gridDim = dim3(groups * PAIR);
-  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR, STATS>, tmA, tmB, tmC, tmR, tmA2, tmB2, p));
+  GemmLaunch<1> L;
+  L.tm[0][0] = tmA;
+  L.tm[0][1] = tmB;
+  L.tm[0][2] = tmC;
+  L.tm[0][3] = tmR;
+  L.tm[0][4] = tmA2;
+  L.tm[0][5] = tmB2;
+  L.p[0] = p;
+  L.nq = 1;
+  L.dep = nullptr;
+  L.dep_stride = 0;
+  L.sched = nullptr;
+  L.sched_items = 0;
+  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR, STATS, 1>, L));
   DS_LAUNCH_OK("gemm_bf16_tcgen05");
+  return DS_OK;
+}
+
+// One prepared problem: tensor maps {A, B, C, R, A2, B2}, parameters and the tile shape run_gemm chose for it.
+struct PreparedGemm {
+  CUtensorMap tm[6];
+  GemmParams p;
+  int bn, pair;
+};
+
+// Static schedule of a chain: which CTA pair runs which units, in which order.  Round-robin per problem (what a single
+// launch does) leaves every problem's partial last round on the same low-numbered pairs; here the units of ALL
+// problems, in (problem, unit) order, go through list scheduling — each unit to the pair that becomes free first under
+// the cost model "k-blocks + alpha" — which is what a dynamic tile scheduler would do, without a per-tile atomic and a
+// cluster-wide broadcast in the kernel.  Dependencies only point to earlier problems and every pair walks the problems
+// in order, so any assignment is deadlock-free.  The table depends only on (pairs, per-problem units, k-blocks): it is
+// built once per distinct chain shape and kept in device memory (first use must be outside a graph capture).
+struct ChainSchedule {
+  int* dev = nullptr;
+  int items_off = 0;
+};
+
+static int chain_schedule(const PreparedGemm* pr, int n, int groups, cudaStream_t stream, ChainSchedule* out) {
+  static std::mutex mu;
+  static std::map<std::vector<int>, ChainSchedule> cache[kMaxDevices];
+  static const double alpha = [] {
+    const char* e = getenv("DS_CHAIN_ALPHA");
+    return e ? atof(e) : 6.0;
+  }();
+  static const int uniform = [] {  // DS_CHAIN_SCHED=rr: every unit costs the same (round-robin continued across problems)
+    const char* e = getenv("DS_CHAIN_SCHED");
+    return (e && e[0] == 'r') ? 1 : 0;
+  }();
+  std::vector<int> key = {groups, n};
+  for (int q = 0; q < n; ++q) {
+    key.push_back(pr[q].p.total_items);
+    key.push_back(pr[q].p.num_k_iters);
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  auto& tab = cache[device_slot()];
+  auto it = tab.find(key);
+  if (it != tab.end()) {
+    *out = it->second;
+    return DS_OK;
+  }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  DS_CUDA_OK(cudaStreamIsCapturing(stream, &cs));
+  DS_REQUIRE(cs == cudaStreamCaptureStatusNone,
+             "ds_gemm_chain: first use of a chain shape must happen outside a graph capture (it uploads its schedule)");
+  const int hdr = groups * (kMaxChain + 1);
+  std::vector<std::vector<int>> mine(static_cast<size_t>(groups) * kMaxChain);
+  using Slot = std::pair<double, int>;  // (time the pair becomes free, pair)
+  std::priority_queue<Slot, std::vector<Slot>, std::greater<Slot>> free_at;
+  for (int g = 0; g < groups; ++g) free_at.push({0.0, g});
+  int total = 0;
+  for (int q = 0; q < n; ++q) {
+    const double cost = uniform ? 1.0 : static_cast<double>(pr[q].p.num_k_iters) + alpha;
+    for (int u = 0; u < pr[q].p.total_items; ++u) {
+      Slot s = free_at.top();
+      free_at.pop();
+      mine[static_cast<size_t>(s.second) * kMaxChain + q].push_back(u);
+      s.first += cost;
+      free_at.push(s);
+    }
+    total += pr[q].p.total_items;
+  }
+  std::vector<int> host(static_cast<size_t>(hdr) + total);
+  int pos = 0;
+  for (int g = 0; g < groups; ++g) {
+    for (int q = 0; q < kMaxChain; ++q) {
+      host[g * (kMaxChain + 1) + q] = pos;
+      for (int u : mine[static_cast<size_t>(g) * kMaxChain + q]) host[hdr + pos++] = u;
+    }
+    host[g * (kMaxChain + 1) + kMaxChain] = pos;
+  }
+  ChainSchedule sc;
+  sc.items_off = hdr;
+  DS_CUDA_OK(cudaMalloc(&sc.dev, host.size() * sizeof(int)));
+  DS_CUDA_OK(cudaMemcpy(sc.dev, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice));
+  tab.emplace(std::move(key), sc);
+  *out = sc;
+  return DS_OK;
+}
+
+// ds_gemm_chain: n dependent GEMMs (problem q+1 reads problem q's output rows) as ONE persistent launch of
+// <256, 2> tiles; see GemmLaunch.  `dep` = kMaxChain * dep_stride + 1 zeroed ints the kernel hands back zeroed.
+static int launch_chain(PreparedGemm* pr, int n, int* dep, int dep_len, int num_sms, cudaStream_t stream) {
+  constexpr int BN = 256, PAIR = 2;
+  using Cfg = GemmCfg<BN, PAIR>;
+  const int slot = device_slot();
+  static bool attr_set[kMaxDevices] = {};
+  if (!attr_set[slot]) {
+    DS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, false, kMaxChain>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set[slot] = true;
+  }
+  GemmLaunch<kMaxChain> L;
+  const int m_groups = (pr[0].p.num_m_tiles + PAIR - 1) / PAIR;
+  int max_units = 0;
+  for (int q = 0; q < n; ++q) {
+    GemmParams& p = pr[q].p;
+    const int units = m_groups * p.num_n_tiles;
+    p.wide_units = units;
+    p.wide_m_pairs = m_groups;
+    p.nt_narrow = 0;
+    p.tail_start = units;
+    p.tail_parts = 1;
+    p.total_items = units;
+    p.ws = nullptr;
+    if (units > max_units) max_units = units;
+    for (int i = 0; i < 6; ++i) L.tm[q][i] = pr[q].tm[i];
+    L.p[q] = p;
+  }
+  for (int q = n; q < kMaxChain; ++q) {  // unused slots: defined bytes
+    for (int i = 0; i < 6; ++i) L.tm[q][i] = pr[0].tm[i];
+    L.p[q] = pr[0].p;
+  }
+  L.nq = n;
+  L.dep = dep;
+  L.dep_stride = m_groups * PAIR;
+  DS_REQUIRE(kMaxChain * L.dep_stride + 1 <= dep_len,
+             "ds_gemm_chain: dependency buffer too small (%d ints for %d row blocks)", dep_len, L.dep_stride);
+  const int max_groups = resident_groups<BN, PAIR>(num_sms);
+  const int groups = max_units < max_groups ? max_units : max_groups;
+  ChainSchedule sc;
+  const int rc = chain_schedule(pr, n, groups, stream, &sc);
+  if (rc != DS_OK) return rc;
+  L.sched = sc.dev;
+  L.sched_items = sc.items_off;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  pdl_attr(&attr[1]);
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  cfg.gridDim = dim3(groups * PAIR);
+  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR, false, kMaxChain>, L));
+  DS_LAUNCH_OK("gemm_bf16_tcgen05(chain)");
   return DS_OK;
 }
 
@@ -982,17 +1273,19 @@ static bool make_out_map(CUtensorMap* m, const void* base, const GemmParams& p, 
   return encode_tmap_bf16(m, base, 2, dims, strides, box, nullptr);
 }
 
-static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const void* w, int ldw, GemmParams& p, int conv_B,
-                    cudaStream_t stream, bool row_stats_zeroed, void* splitk_ws, long long splitk_ws_bytes) {
-  DeviceInfo dev;
-  if (!get_device(&dev)) return DS_ERR_CUDA;
-  const int bn = pick_bn(p.N, p.epilogue);
+// Everything run_gemm decides about one problem except the launch: tile shape, epilogue kind, output / residual /
+// weight tensor maps, the narrow-tile schedule.  `chain`: the problem is a link of ds_gemm_chain (<256, 2> tiles, no
+// mixed-width tail — its row blocks must all have num_n_tiles units).
+static int prepare_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const void* w, int ldw, GemmParams& p,
+                        int conv_B, cudaStream_t stream, bool row_stats_zeroed, bool chain, const DeviceInfo& dev,
+                        PreparedGemm* out) {
+  const int bn = chain ? 256 : pick_bn(p.N, p.epilogue);
   // CTA pairs (cta_group::2) whenever there are at least two M tiles to pair up; DS_GEMM_PAIR=0 forces 1-CTA tiles
   static const int pair_env = [] {
     const char* e = getenv("DS_GEMM_PAIR");
     return e ? atoi(e) : 1;
   }();
-  const int pair = (pair_env != 0 && p.num_m_tiles >= 2) ? 2 : 1;
+  const int pair = chain ? 2 : ((pair_env != 0 && p.num_m_tiles >= 2) ? 2 : 1);
   // coalesced TMA epilogue whenever the bf16 output (and residual) rows are 16-byte addressable
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.tma_epilogue = !p.out_fp32 && p.n_out % 8 == 0 && p.ldo % 8 == 0 && aligned16(p.out) &&
@@ -1050,7 +1343,7 @@ static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const void*
     const char* e = getenv("DS_GEMM_TAIL");
     return e ? atoi(e) : 1;
   }();
-  if (tail_env && pair == 2 && bn == 256 && p.epilogue != DS_EPI_GEGLU && p.N % 128 == 0 && !p.last_narrow) {
+  if (tail_env && !chain && pair == 2 && bn == 256 && p.epilogue != DS_EPI_GEGLU && p.N % 128 == 0 && !p.last_narrow) {
     const int G = resident_groups<256, 2>(dev.num_sms);
     const int mp = (p.num_m_tiles + 1) / 2, nt = p.num_n_tiles;
     const int units = mp * nt;
@@ -1081,6 +1374,29 @@ static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const void*
       if (!encode_tmap_bf16(&tmB2, w, 2, dims, strides, box2, nullptr)) return DS_ERR_CUDA;
     }
   }
+  out->tm[0] = tmA;
+  out->tm[1] = tmB;
+  out->tm[2] = tmC;
+  out->tm[3] = tmR;
+  out->tm[4] = tmA2;
+  out->tm[5] = tmB2;
+  out->p = p;
+  out->bn = bn;
+  out->pair = pair;
+  return DS_OK;
+}
+
+static int run_gemm(const CUtensorMap& tmA_in, const CUtensorMap& tmA2_in, const void* w, int ldw, GemmParams& p_in,
+                    int conv_B, cudaStream_t stream, bool row_stats_zeroed, void* splitk_ws,
+                    long long splitk_ws_bytes) {
+  DeviceInfo dev;
+  if (!get_device(&dev)) return DS_ERR_CUDA;
+  PreparedGemm g;
+  const int rc = prepare_gemm(tmA_in, tmA2_in, w, ldw, p_in, conv_B, stream, row_stats_zeroed, false, dev, &g);
+  if (rc != DS_OK) return rc;
+  const CUtensorMap &tmA = g.tm[0], &tmB = g.tm[1], &tmC = g.tm[2], &tmR = g.tm[3], &tmA2 = g.tm[4], &tmB2 = g.tm[5];
+  const GemmParams& p = g.p;
+  const int bn = g.bn, pair = g.pair;
   if (pair == 2) {
     if (bn == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
     if (bn == 192) return launch_gemm<192, 2>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
@@ -1091,10 +1407,8 @@ static int run_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const void*
   return launch_gemm<128, 1>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
 }
 
-}  // namespace ds
-
-extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
-  using namespace ds;
+// argument checks + A tensor map(s) + GemmParams of one ds_gemm_args (shared by ds_gemm_bf16 and ds_gemm_chain)
+static int build_problem(const ds_gemm_args* a, CUtensorMap* tmA_out, CUtensorMap* tmA2_out, GemmParams* p_out) {
   DS_REQUIRE(a != nullptr, "ds_gemm_bf16: args is NULL");
   DS_REQUIRE(a->a && a->w && a->out, "ds_gemm_bf16: a/w/out must be non-NULL");
   DS_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "ds_gemm_bf16: M,N,K must be positive (got %d,%d,%d)", a->M, a->N,
@@ -1112,14 +1426,15 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
   DS_REQUIRE(a->ldo >= n_out, "ds_gemm_bf16: ldo (%d) smaller than output width (%d)", a->ldo, n_out);
   if (a->residual) DS_REQUIRE(a->ldres >= n_out, "ds_gemm_bf16: ldres smaller than output width");
 
-  CUtensorMap tmA;
+  CUtensorMap& tmA = *tmA_out;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(a->K), static_cast<uint64_t>(a->M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(a->lda) * 2};
     const uint32_t box[2] = {kBK, kBM};
     if (!encode_tmap_bf16(&tmA, a->a, 2, dims, strides, box, nullptr)) return DS_ERR_CUDA;
   }
-  GemmParams p{};
+  GemmParams& p = *p_out;
+  p = GemmParams{};
   p.bias = a->bias;
   p.rowbias = a->rowbias;
   p.residual = static_cast<const __nv_bfloat16*>(a->residual);
@@ -1161,7 +1476,8 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
   p.chan_stats = a->chan_stats;
   p.stats_rows_per_sample = a->stats_rows_per_sample;
   p.w_const = a->w_is_constant != 0;
-  CUtensorMap tmA2 = tmA;
+  CUtensorMap& tmA2 = *tmA2_out;
+  tmA2 = tmA;
   if (a->a2) {
     DS_REQUIRE(a->K1 > 0 && a->K1 < a->K && a->K1 % kBK == 0, "ds_gemm_bf16: a2 needs 0 < K1 < K and K1 %% 64 == 0");
     DS_REQUIRE(a->lda >= a->K1 && a->lda2 >= a->K - a->K1 && a->lda2 % 8 == 0 &&
@@ -1176,9 +1492,48 @@ extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
     if (!encode_tmap_bf16(&tmA2, a->a2, 2, dims2, strides2, box, nullptr)) return DS_ERR_CUDA;
     p.k1_iters = a->K1 / kBK;
   }
+  return DS_OK;
+}
+
+}  // namespace ds
+
+extern "C" int ds_gemm_bf16(const ds_gemm_args* a, void* stream) {
+  using namespace ds;
+  CUtensorMap tmA, tmA2;
+  GemmParams p;
+  const int rc = build_problem(a, &tmA, &tmA2, &p);
+  if (rc != DS_OK) return rc;
   return run_gemm(tmA, tmA2, a->w, a->ldw, p, 0, static_cast<cudaStream_t>(stream), a->row_stats_zeroed != 0,
                   a->splitk_ws, a->splitk_ws_bytes);
 }
+
+extern "C" int ds_gemm_chain(const ds_gemm_args* args, int n, int* dep, int dep_len, void* stream) {
+  using namespace ds;
+  DS_REQUIRE(args != nullptr && n >= 1 && n <= kMaxChain, "ds_gemm_chain: 1..%d problems (got %d)", kMaxChain, n);
+  DS_REQUIRE(dep != nullptr && (reinterpret_cast<uintptr_t>(dep) & 3) == 0, "ds_gemm_chain: dep is NULL / unaligned");
+  DeviceInfo dev;
+  if (!get_device(&dev)) return DS_ERR_CUDA;
+  PreparedGemm pr[kMaxChain];
+  for (int q = 0; q < n; ++q) {
+    const ds_gemm_args* a = args + q;
+    CUtensorMap tmA, tmA2;
+    GemmParams p;
+    const int rc = build_problem(a, &tmA, &tmA2, &p);
+    if (rc != DS_OK) return rc;
+    DS_REQUIRE(a->M == args[0].M && a->M > kBM, "ds_gemm_chain: every problem must have the same M > 128");
+    DS_REQUIRE(!a->chan_stats && !a->out_fp32, "ds_gemm_chain: no chan_stats / fp32 outputs in a chain");
+    if (q > 0)
+      DS_REQUIRE(a->a == args[q - 1].out && a->a2 == nullptr,
+                 "ds_gemm_chain: problem %d must read problem %d's output as its A operand", q, q - 1);
+    const int rc2 = prepare_gemm(tmA, tmA2, a->w, a->ldw, p, 0, static_cast<cudaStream_t>(stream),
+                                 a->row_stats_zeroed != 0, true, dev, &pr[q]);
+    if (rc2 != DS_OK) return rc2;
+    DS_REQUIRE(pr[q].p.tma_epilogue, "ds_gemm_chain: problem %d needs a 16-byte addressable bf16 output", q);
+  }
+  return launch_chain(pr, n, dep, dep_len, dev.num_sms, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ds_gemm_chain_max(void) { return ds::kMaxChain; }
 
 extern "C" int64_t ds_gemm_splitk_ws_bytes(void) {
   int sms = 256;

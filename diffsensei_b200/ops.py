@@ -199,15 +199,87 @@ def _splitk_ws():
     return ws
 
 
-def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_NONE,
+def gemm(*a, **kw) -> torch.Tensor:
+    """out[..., Nout] = epilogue(a[..., K] @ w[N, K]^T) on tcgen05 — one launch; see ``_gemm_args`` for the
+    arguments."""
+    args, out = _gemm_args(*a, **kw)
+    check(lib.ds_gemm_bf16(C.byref(args), _stream()), "ds_gemm_bf16")
+    return out
+
+
+_CHAIN_DEP: dict = {}
+_CHAIN_ROW_BLOCKS = 512                      # M <= 65536 rows per chain
+
+
+def gemm_chain_max() -> int:
+    return int(lib.ds_gemm_chain_max())
+
+
+_CHAIN_SLOTS = 16
+
+
+def gemm_chain_prepare() -> None:
+    """Allocate (and zero, once) the dependency counters of the current device: one slot per stream that runs chains,
+    ``_CHAIN_SLOTS`` of them.  The kernel hands a slot back zeroed, so nothing is ever memset again — which is why this
+    must run once OUTSIDE any graph capture (UNetMangaEngine does it when it is built)."""
+    dev = torch.cuda.current_device()
+    if dev not in _CHAIN_DEP:
+        if torch.cuda.is_current_stream_capturing():
+            raise DsEngineError("gemm_chain: call ops.gemm_chain_prepare() once outside the graph capture")
+        n = (gemm_chain_max() * _CHAIN_ROW_BLOCKS + 1 + 31) // 32 * 32
+        _CHAIN_DEP[dev] = (torch.zeros(_CHAIN_SLOTS, n, dtype=torch.int32, device=f"cuda:{dev}"), {})
+
+
+def _chain_counters() -> torch.Tensor:
+    gemm_chain_prepare()
+    pool, slots = _CHAIN_DEP[torch.cuda.current_device()]
+    key = torch.cuda.current_stream().cuda_stream          # chains on different streams may run concurrently
+    i = slots.get(key)
+    if i is None:
+        if len(slots) >= _CHAIN_SLOTS:
+            raise DsEngineError(f"gemm_chain: more than {_CHAIN_SLOTS} streams run GEMM chains on this device")
+        i = slots[key] = len(slots)
+    return pool[i]
+
+
+def gemm_chain(calls, min_links: int = 2) -> list:
+    """Run ``calls`` — a list of ``(args, kwargs)`` of :func:`gemm`, each one reading the previous one's output as its
+    ``a`` (pass ``None`` for ``a`` to say exactly that) — as ONE persistent launch (ds_gemm_chain, include/dsengine.h).  Bit-identical to calling :func:`gemm` on
+    each; returns the outputs.  Falls back to separate launches for shapes a chain does not take (M <= 128 or more
+    than 65536 rows, fp32 outputs, channel statistics, or more links than the kernel holds).  ``min_links=1`` runs even
+    a single GEMM through the chain kernel (same tile geometry as a longer chain: what the tests compare against)."""
+    prepared = []
+    for a, kw in calls:
+        if a[0] is None:                     # "the previous link's output"
+            a = (prepared[-1][1],) + tuple(a[1:])
+        prepared.append(_gemm_args(*a, **kw))
+    M = prepared[0][0].M
+    ok = min_links <= len(prepared) <= gemm_chain_max() and 128 < M <= _CHAIN_ROW_BLOCKS * 128
+    for i, (g, _) in enumerate(prepared):
+        ok = ok and g.M == M and not g.out_fp32 and not g.chan_stats and not g.a2
+        ok = ok and (g.N // 2 if g.epilogue == EPI_GEGLU else g.N) % 8 == 0
+        if i > 0:
+            ok = ok and g.a == prepared[i - 1][0].out
+    if not ok:
+        for g, _ in prepared:
+            check(lib.ds_gemm_bf16(C.byref(g), _stream()), "ds_gemm_bf16")
+        return [o for _, o in prepared]
+    dep = _chain_counters()
+    arr = (GemmArgs * len(prepared))(*[g for g, _ in prepared])
+    check(lib.ds_gemm_chain(arr, len(prepared), dep.data_ptr(), dep.numel(), _stream()), "ds_gemm_chain")
+    return [o for _, o in prepared]
+
+
+def _gemm_args(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = EPI_NONE,
          residual: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rows_per_batch: int = 0,
          out: Optional[torch.Tensor] = None, out_fp32: bool = False, out_scale: float = 0.0,
          ln_stats: Optional[torch.Tensor] = None, ln_colsum: Optional[torch.Tensor] = None, ln_eps: float = 1e-5,
          row_stats_out: Optional[torch.Tensor] = None, zero_rows: Optional[torch.Tensor] = None,
          row_stats_zeroed: bool = False, a2: Optional[torch.Tensor] = None,
          chan_stats: Optional[torch.Tensor] = None, stats_rows_per_sample: int = 0,
-         w_const: bool = True) -> torch.Tensor:
-    """out[..., Nout] = epilogue(a[..., K] @ w[N, K]^T) on tcgen05; ``a`` may have any leading dims.
+         w_const: bool = True):
+    """Validated ds_gemm_args + the output tensor of out[..., Nout] = epilogue(a[..., K] @ w[N, K]^T); ``a`` may have
+    any leading dims.
 
     LayerNorm fusion (include/dsengine.h): ``ln_stats`` [2*M] fp64 {sum, sumsq} per row of ``a`` + ``ln_colsum`` [N]
     turn the call into LayerNorm(a) @ w_orig^T for weights folded by ``weights.fold_layernorm``; ``row_stats_out``
@@ -279,8 +351,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
                     a2=_ptr(a2), K1=K1, lda2=0 if a2 is None else a2.shape[-1],
                     chan_stats=_ptr(chan_stats), stats_rows_per_sample=int(stats_rows_per_sample),
                     w_is_constant=int(bool(w_const)))
-    check(lib.ds_gemm_bf16(C.byref(args), _stream()), "ds_gemm_bf16")
-    return out
+    return args, out
 
 
 def conv3x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, stride: int = 1,

@@ -177,6 +177,21 @@ int ds_gemm_bf16(const ds_gemm_args* args, void* stream);
 /* bytes of split-K workspace that suffice for any ds_gemm_bf16 / ds_conv3x3_nhwc call on the current device */
 int64_t ds_gemm_splitk_ws_bytes(void);
 
+/* A CHAIN of n (<= ds_gemm_chain_max()) dependent GEMMs as ONE persistent launch: args[q+1].a must be args[q].out
+ * (the BasicTransformerBlock sequences attn.to_out -> attn2.to_q and attn2.to_out -> ff.net.0 -> ff.net.2 -> next
+ * attn1.to_qkv of diffusers' BasicTransformerBlock.forward, each a torch.nn.Linear call in the reference; the
+ * LayerNorms between them are folded as in ds_gemm_bf16).  Results are bit-identical to n ds_gemm_bf16 calls: same
+ * tiles, same K order; only the schedule differs — the CTA pairs walk the problems back to back and a tile of problem
+ * q+1 on row block m starts as soon as all column tiles of problem q for those 128 rows are written (a counter per
+ * (problem, row block) in `dep`), so launch / prologue / drain are paid once and the partial last round of one
+ * problem is filled with the first tiles of the next.  Every problem: same M > 128, bf16 output with 16-byte
+ * addressable rows, no chan_stats, no split-K; residual / ln_stats / row_stats_out / zero_rows may refer to buffers
+ * written by EARLIER problems of the chain for the same rows.
+ * dep: dep_len >= ds_gemm_chain_max() * 2 * ceil(M / 256) + 1 ints, ALL ZERO on entry; the kernel leaves them all
+ *      zero again (no memset between launches or graph replays); not to be shared by chains running concurrently. */
+int ds_gemm_chain(const ds_gemm_args* args, int n, int* dep, int dep_len, void* stream);
+int ds_gemm_chain_max(void);
+
 /* ---------------------------------------------------------------------------------------------
  * 3x3 convolution, padding 1, stride 1 or 2, NHWC bf16, as an implicit GEMM on tcgen05:
  * the A operand is gathered by 4-D TMA tiles (one 8x16-pixel patch x 64 channels per filter tap;

@@ -367,3 +367,31 @@ def test_tensor_on_other_device_is_rejected(tiny):
     x = torch.zeros(1, 8, 8, 64, device="cuda:1", dtype=bf16)
     with pytest.raises(ds.ops.DsEngineError, match="current CUDA device"):
         ds.ops.silu(x)
+
+
+def test_chained_linears_do_not_change_the_unet_output(tiny, monkeypatch):
+    """DS_GEMM_CHAIN: the linears between the attention kernels of every BasicTransformerBlock as one persistent
+    launch each (ops.gemm_chain).  Same tiles, same K order -> the UNet output must be bit-identical, with fewer
+    launches."""
+    from diffsensei_b200 import unet as unet_mod
+    from diffsensei_b200._lib import launch_count
+    ds, _oracle, engine = tiny
+    lat, ehs, pooled, time_ids, bbox, dialog = _inputs(ds.TINY, 2, 32, 32)
+    x = torch.cat([lat] * 2).to(DEV)
+
+    def run():
+        n0 = launch_count()
+        out = engine.forward(x, torch.tensor(500), ehs.to(DEV, bf16),
+                             added_cond_kwargs={"text_embeds": pooled.to(DEV), "time_ids": time_ids.to(DEV)},
+                             cross_attention_kwargs={"bbox": bbox.to(DEV), "aspect_ratio": 1.0},
+                             dialog_bbox=dialog.to(DEV)).sample
+        torch.cuda.synchronize()
+        return out, launch_count() - n0
+
+    monkeypatch.setattr(unet_mod, "_CHAIN", False)
+    want, n_plain = run()
+    monkeypatch.setattr(unet_mod, "_CHAIN", True)
+    for _ in range(3):
+        got, n_chain = run()
+        assert torch.equal(got, want)
+    assert n_chain < n_plain

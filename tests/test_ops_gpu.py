@@ -10,6 +10,11 @@ import torch.nn.functional as F
 
 from conftest import GOLDEN, rel_l2
 
+
+def launch_count():
+    from diffsensei_b200._lib import launch_count as lc
+    return lc()
+
 pytestmark = pytest.mark.gpu
 
 bf16, f32 = torch.bfloat16, torch.float32
@@ -438,3 +443,88 @@ def test_conv3x3_fused_nearest_upsample(ops, B, H, W, Cin, Cout):
     assert got.shape == (B, 2 * H, 2 * W, Cout)
     assert rel_l2(got.float(), want) < 8e-3            # + one bf16 rounding of the pre-summed taps
     assert torch.allclose(st.cpu(), _chan_stats_ref(got.cpu()), rtol=1e-5, atol=1e-3)
+
+
+def _block_links(ops, C, M, seed):
+    """The linears of one BasicTransformerBlock between its attention kernels, as (args, kwargs) lists for ops.gemm:
+    attn2.to_out (+h, row stats) -> ff.net.0 (LayerNorm folded, GEGLU) -> ff.net.2 (+h, row stats) -> to_qkv (LN)."""
+    from diffsensei_b200.weights import colsum_bf16, fold_layernorm, pack_geglu
+    g = torch.Generator().manual_seed(seed)
+
+    def lin(n, k, ln=False, geglu=False):
+        w, b = torch.randn(n, k, generator=g) * k ** -0.5, torch.randn(n, generator=g) * 0.2
+        if ln:
+            w, b = fold_layernorm(w, b, torch.randn(k, generator=g) * 0.2 + 1, torch.randn(k, generator=g) * 0.1)
+        if geglu:
+            w, b = pack_geglu(w, b)
+        w = w.to(bf16)
+        return w.to(DEV), b.to(DEV), (colsum_bf16(w).to(DEV) if ln else None)
+
+    a = (torch.randn(M, C, generator=g)).to(bf16).to(DEV)
+    h0 = (torch.randn(M, C, generator=g) * 2 + 0.5).to(bf16).to(DEV)
+    wo, bo, _ = lin(C, C)
+    w1, b1, cs1 = lin(8 * C, C, ln=True, geglu=True)
+    w2, b2, _ = lin(C, 4 * C)
+    wq, bq, csq = lin(3 * C, C, ln=True)
+
+    def build():
+        h = h0.clone()
+        st = [torch.zeros(2 * M, dtype=torch.float64, device=DEV) for _ in range(3)]
+        qkv = torch.empty(M, 3 * C, dtype=bf16, device=DEV)
+        links = [((a, wo, bo), dict(residual=h, out=h, row_stats_out=st[0], row_stats_zeroed=True)),
+                 ((None, w1, b1), dict(epilogue=ops.EPI_GEGLU, ln_stats=st[0], ln_colsum=cs1, zero_rows=st[2])),
+                 ((None, w2, b2), dict(residual=h, out=h, row_stats_out=st[1], row_stats_zeroed=True)),
+                 ((None, wq, bq), dict(ln_stats=st[1], ln_colsum=csq, zero_rows=st[0], out=qkv))]
+        return links, h, st
+    return build
+
+
+@pytest.mark.parametrize("C,M", [(640, 4096), (1280, 8192), (640, 128 * 5 + 40), (320, 1024)])
+def test_gemm_chain_is_bit_identical_to_separate_launches(ops, C, M):
+    """ds_gemm_chain: attn2.to_out -> ff.net.0 -> ff.net.2 -> to_qkv as ONE persistent launch with per-row-block
+    dependency counters.  Outputs, intermediates and LayerNorm statistics must equal the four-launch sequence bit for
+    bit, launch after launch (the kernel hands its counters back zeroed), including odd row-block counts."""
+    build = _block_links(ops, C, M, seed=C + M)
+    links, h_ref, st_ref = build()
+    # the reference: the same four GEMMs as four launches of the same tile geometry (<256, 2> tiles; the row statistics
+    # are fp64 sums of per-tile fp32 partials, so they depend — in the last bit — on the tile widths)
+    prev, want = None, []
+    for args, kw in links:
+        n0 = launch_count()
+        prev = ops.gemm_chain([((prev,) + args[1:] if args[0] is None else args, kw)], min_links=1)[0]
+        assert launch_count() - n0 == 1
+        want.append(prev.clone())
+    # ... which agrees with the default schedule (mixed-width / 192-column tiles) to rounding
+    links_d, h_d, _ = build()
+    prev = None
+    for args, kw in links_d:
+        prev = ops.gemm(*((prev,) + args[1:] if args[0] is None else args), **kw)
+    assert rel_l2(prev.float(), want[3].float()) < 2e-3 and rel_l2(h_d.float(), h_ref.float()) < 2e-3
+    torch.cuda.synchronize()
+    for it in range(6):
+        links, h, st = build()
+        n0 = launch_count()
+        got = ops.gemm_chain(links)
+        assert launch_count() - n0 == 1, "the chain must be ONE launch"
+        torch.cuda.synchronize()
+        assert torch.equal(got[1], want[1]), f"ff.net.0 output differs (iteration {it})"
+        assert torch.equal(got[3], want[3]), f"to_qkv output differs (iteration {it})"
+        assert torch.equal(h, h_ref), f"residual stream differs (iteration {it})"
+        assert torch.equal(st[1], st_ref[1]) and torch.count_nonzero(st[0]).item() == 0
+    # two-link chain (attn.to_out -> attn2.to_q) through the same counters
+    links, h, st = build()
+    two = ops.gemm_chain([links[0], ((None, links[3][0][1], links[3][0][2]),
+                                     dict(ln_stats=st[0], ln_colsum=links[3][1]["ln_colsum"], zero_rows=st[2]))])
+    links, h2, st2 = build()
+    ops.gemm_chain([links[0]], min_links=1)
+    ref = ops.gemm_chain([((h2, links[3][0][1], links[3][0][2]),
+                           dict(ln_stats=st2[0], ln_colsum=links[3][1]["ln_colsum"]))], min_links=1)[0]
+    assert torch.equal(two[1], ref)
+
+
+def test_gemm_chain_falls_back_for_shapes_it_does_not_take(ops):
+    a, w = _r(64, 128, seed=1).to(DEV), _r(128, 128, seed=2, scale=128 ** -0.5).to(DEV)
+    n0 = launch_count()
+    o = ops.gemm_chain([((a, w), {}), ((None, w), {})])          # M <= 128: two ordinary launches
+    assert launch_count() - n0 == 2
+    assert torch.equal(o[1], ops.gemm(ops.gemm(a, w), w))
