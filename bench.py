@@ -495,7 +495,8 @@ def library_baseline(dev, steps=3, warmup=2, log=lambda *a: None):
 # ------------------------------------------------------------------------------------------------ our arm
 def family_roofline(ds, stepper, peaks, reps=2):
     """Time-weighted roofline of the tcgen05 GEMM family over the REAL shape census of one step: every ds_gemm_bf16 /
-    ds_conv3x3_nhwc launch of an eager step is bracketed by CUDA events; achieved = sum(2*M*N*K) / sum(time)."""
+    ds_gemm_chain / ds_conv3x3_nhwc launch of an eager step is bracketed by CUDA events; achieved = sum(2*M*N*K) /
+    sum(time)."""
     ops = ds.ops
     rec, on = [], [False]
     orig = {"gemm": ops.gemm, "conv3x3": ops.conv3x3}
@@ -529,7 +530,22 @@ def family_roofline(ds, stepper, peaks, reps=2):
                     e0, e1))
         return r
 
-    ops.gemm, ops.conv3x3 = gemm, conv3x3
+    def gemm_chain(calls, **kw):
+        if not on[0]:
+            return orig["gemm_chain"](calls, **kw)
+        a0 = calls[0][0][0]
+        M = a0.numel() // a0.shape[-1]
+        ws = [c[0][1] for c in calls]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig["gemm_chain"](calls, **kw)
+        e1.record()
+        rec.append((f"chain M{M} " + ">".join(f"N{w.shape[0]}K{w.shape[1]}" for w in ws),
+                    sum(2.0 * M * w.shape[0] * w.shape[1] for w in ws), e0, e1))
+        return r
+
+    orig["gemm_chain"] = ops.gemm_chain
+    ops.gemm, ops.conv3x3, ops.gemm_chain = gemm, conv3x3, gemm_chain
     try:
         stepper.step(0)
         torch.cuda.synchronize()
@@ -545,13 +561,14 @@ def family_roofline(ds, stepper, peaks, reps=2):
                 d[0] += 1
                 d[1] += e0.elapsed_time(e1)
     finally:
-        ops.gemm, ops.conv3x3 = orig["gemm"], orig["conv3x3"]
+        ops.gemm, ops.conv3x3, ops.gemm_chain = orig["gemm"], orig["conv3x3"], orig["gemm_chain"]
     tot_ms = sum(d[1] for d in agg.values()) / reps
     tot_fl = sum(d[0] * d[2] for d in agg.values()) / reps
     ach = tot_fl / tot_ms / 1e9
     worst = sorted(((k, d[2] / (d[1] / d[0]) / 1e9, d[1] / reps) for k, d in agg.items() if d[1] / reps > 0.25),
                    key=lambda x: x[1])[:4]
-    return {"kernel": "gemm_bf16_tcgen05 family (all ds_gemm_bf16 + ds_conv3x3_nhwc launches of one cfg2 step)",
+    return {"kernel": "gemm_bf16_tcgen05 family (all ds_gemm_bf16 / ds_gemm_chain / ds_conv3x3_nhwc launches of one "
+                      "cfg2 step)",
             "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": round(ach / peaks["bf16_tflops"], 4),
             "frac_of_sustained": round(ach / peaks["bf16_tflops_sustained"], 4),
