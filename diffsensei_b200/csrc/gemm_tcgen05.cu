@@ -86,6 +86,7 @@ struct GemmParams {
   // 1: the weight operand is constant data (never written by a kernel that may still be in flight), so the producer
   // may request its first tiles BEFORE griddepcontrol.wait.  0 (e.g. K / V^T of the VAE attention used as `w`): after.
   int w_const;
+  int l2_prefetch;  // k-blocks of weight tile the producer requests into the L2 ahead of its smem ring (0 = off)
   // second A operand: k-blocks [k1_iters, num_k_iters) of a plain GEMM come from tmA2 (the channel concatenation
   // [a | a2] along K is never materialised); k1_iters == num_k_iters: off
   int k1_iters;
@@ -148,15 +149,26 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* ptr) {
   return v;
 }
 
-template <int BN, int PAIR, bool STATS, int MAXQ>
+// QUAD (PAIR == 2 only): a cluster of 4 = TWO CTA pairs stacked along M that work on the same n-tile and k-range in
+// lockstep and SHARE the weight tile: each CTA fetches a quarter of it and TMA-multicasts that quarter to the CTA of the
+// same rank in the other pair, so the cluster reads B once from the L2 instead of twice (L2 -> SM bytes per FLOP: -25 %;
+// at 256 x 256 pair tiles the kernel asks the L2 for 64 B/clk/SM at full tensor rate, more than it delivers chip-wide).
+// A smem slot is then written by both pairs' producers: its empty barrier collects BOTH pairs' MMA commits.
+template <int BN, int PAIR, bool STATS, int MAXQ, bool QUAD = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
+  static_assert(!QUAD || (PAIR == 2 && BN == 256), "QUAD needs CTA pairs and 256-column tiles");
   using Cfg = GemmCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::kStages;
-  const uint32_t cta_rank = (PAIR == 2) ? cluster_ctarank() : 0u;  // rank inside the CTA pair; 0 = leader
+  constexpr int GRP = QUAD ? 4 : PAIR;      // CTAs per work unit (cluster size)
+  constexpr int PPG = QUAD ? 2 : 1;         // pairs per work unit
+  const uint32_t crank = (PAIR == 2) ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = crank & 1u;     // rank inside the CTA pair; 0 = leader
+  const uint32_t pair_id = QUAD ? (crank >> 1) : 0u;
+  const uint32_t leader_rank = crank & ~1u; // cluster rank of this pair's leader
   const bool leader = cta_rank == 0;
-  const int unit0 = blockIdx.x / PAIR;     // first work unit (a 128*PAIR x BN tile) of this CTA (pair)
-  const int unit_step = gridDim.x / PAIR;
+  const int unit0 = blockIdx.x / GRP;       // first work unit (a 128*GRP x BN tile) of this CTA group
+  const int unit_step = gridDim.x / GRP;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -192,7 +204,7 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], PAIR);  // pair: the leader's expect_tx arrival + the peer producer's remote arrival
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], PPG);  // one commit per pair that reads (and whose peer pair writes) the slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -286,7 +298,7 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
       int& stage = st_stage;
       uint32_t& phase = st_phase;
       int pre_b = 0;  // k-blocks of the FIRST item whose weight tile was requested before griddepcontrol.wait
-      if (MAXQ == 1 && p.w_const && unit0 < total_tiles) {
+      if (MAXQ == 1 && !QUAD && p.w_const && unit0 < total_tiles) {
         int unit, k0, k1, tail_idx, m_pair, n_org, bn;
         decode(unit0, unit, k0, k1, tail_idx);
         unit_geom(unit, m_pair, n_org, bn);
@@ -308,7 +320,7 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
         int m_pair, n_org, bn;
         unit_geom(unit, m_pair, n_org, bn);
         const bool narrow = bn != BN;
-        const int m_blk = m_pair * PAIR + static_cast<int>(cta_rank);
+        const int m_blk = (m_pair * PPG + static_cast<int>(pair_id)) * PAIR + static_cast<int>(cta_rank);
         if (MAXQ > 1 && q > 0 && L.dep != nullptr && m_blk * kBM < p.M) {
           // chain dependency: the A rows of this unit are the output rows of ALL n-tiles of the previous problem
           const int* cnt = L.dep + (q - 1) * L.dep_stride + m_blk;
@@ -330,16 +342,32 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
           y0 = (rem / p.tiles_x) * kConvTileH;
           x0 = (rem % p.tiles_x) * kConvTileW;
         }
-        const int b_row0 = n_org + static_cast<int>(cta_rank) * (bn / PAIR);
+        // QUAD: this CTA fetches rows [pair_id * bn/4, +bn/4) of its half and multicasts them to both pairs
+        const int b_sub = QUAD ? static_cast<int>(pair_id) * (bn / 4) : 0;
+        const int b_row0 = n_org + static_cast<int>(cta_rank) * (bn / PAIR) + b_sub;
+        const uint16_t b_mask = static_cast<uint16_t>(0x5u << cta_rank);  // the CTAs of this rank in pair 0 and pair 1
         const CUtensorMap* bm = narrow ? &tmB2 : &tmB;
+        if (p.l2_prefetch > 0 && it + it_step < it_end) {
+          // the first weight blocks of this CTA's NEXT item: first touched from HBM by whichever CTA gets there first —
+          // ask the L2 for them a whole item early, so the smem ring only ever has to cover L2-hit latency
+          const int nxt = MAXQ > 1 ? __ldg(sched_items + it + it_step) : it + it_step;
+          int u2, k02, k12, t2, mp2, no2, bn2;
+          decode(nxt, u2, k02, k12, t2);
+          unit_geom(u2, mp2, no2, bn2);
+          const CUtensorMap* bm2 = (bn2 != BN) ? &tmB2 : &tmB;
+          const int row2 = no2 + static_cast<int>(cta_rank) * (bn2 / PAIR) + (QUAD ? static_cast<int>(pair_id) * (bn2 / 4) : 0);
+          const int npf = (k12 - k02) < p.l2_prefetch ? (k12 - k02) : p.l2_prefetch;
+          for (int i = 0; i < npf; ++i) tma_prefetch_2d(bm2, (k02 + i) * kBK, row2);
+        }
         for (int kb = k0; kb < k1; ++kb) {
+          if (p.l2_prefetch > 0 && kb + p.l2_prefetch < k1) tma_prefetch_2d(bm, (kb + p.l2_prefetch) * kBK, b_row0);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (PAIR == 1) {
             mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
           } else if (leader) {
             mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);  // both CTAs' bytes land on this barrier
           } else {
-            mbar_arrive_cluster(&full_bar[stage], 0);
+            mbar_arrive_cluster(&full_bar[stage], leader_rank);
           }
           if (p.conv) {
             const int tap = kb / p.cin_chunks;
@@ -363,6 +391,9 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
           if (MAXQ == 1 && tile == unit0 && kb - k0 < pre_b) {
             // weight tile already in flight (requested before griddepcontrol.wait); its bytes count towards the
             // expect_tx above — complete_tx may precede expect_tx within a phase (the tx-count is signed)
+          } else if (QUAD) {
+            tma_load_2d_pair_mc(sB + stage * Cfg::kBBytes + b_sub * (kBK * 2), bm, &full_bar[stage], kb * kBK, b_row0,
+                                b_mask);
           } else if (PAIR == 2) {
             tma_load_2d_pair(sB + stage * Cfg::kBBytes, bm, &full_bar[stage], kb * kBK, b_row0);
           } else {
@@ -383,6 +414,10 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
       int& stage = st_stage;
       uint32_t& phase = st_phase;
       int& iter = st_iter;
+#ifdef DS_GEMM_TRACE
+      long long tr_full = 0, tr_tempty = 0, tr_t0 = clock64();
+      int tr_tiles = 0;
+#endif
       for (int it = it_beg; it < it_end; it += it_step, ++iter) {
         const int tile = MAXQ > 1 ? __ldg(sched_items + it) : it;
         int unit, k0, k1, tail_idx;
@@ -392,11 +427,24 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
         int mp_u, n_org_u, bn_u;
         unit_geom(unit, mp_u, n_org_u, bn_u);
         const uint32_t idesc = bn_u == BN ? idesc_wide : idesc_narrow;
+#ifdef DS_GEMM_TRACE
+        long long tr_a = clock64();
+#endif
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+#ifdef DS_GEMM_TRACE
+        tr_tempty += clock64() - tr_a;
+        ++tr_tiles;
+#endif
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = k0; kb < k1; ++kb) {
+#ifdef DS_GEMM_TRACE
+          tr_a = clock64();
+#endif
           mbar_wait(&full_bar[stage], phase);
+#ifdef DS_GEMM_TRACE
+          tr_full += clock64() - tr_a;
+#endif
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * kABytes);
           const uint32_t b_addr = smem_u32(sB + stage * Cfg::kBBytes);
@@ -410,7 +458,9 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
               umma_ss(d_tmem, adesc, bdesc, idesc, (kb != k0 || k != 0) ? 1u : 0u);
           }
           // stage reusable (in both CTAs) once these MMAs have read it
-          if (PAIR == 2)
+          if (QUAD)
+            umma_commit_mask(&empty_bar[stage], 0xF);  // all four CTAs: the other pair's producers write this slot too
+          else if (PAIR == 2)
             umma_commit_pair(&empty_bar[stage]);
           else
             umma_commit(&empty_bar[stage]);
@@ -419,11 +469,19 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
             phase ^= 1;
           }
         }
-        if (PAIR == 2)  // accumulator complete: wake the epilogue warps of both CTAs
+        if (QUAD)
+          umma_commit_mask(&tfull_bar[acc], static_cast<uint16_t>(0x3u << (2 * pair_id)));
+        else if (PAIR == 2)  // accumulator complete: wake the epilogue warps of both CTAs
           umma_commit_pair(&tfull_bar[acc]);
         else
           umma_commit(&tfull_bar[acc]);
       }
+#ifdef DS_GEMM_TRACE
+      if ((blockIdx.x % 37) == 0 && tr_tiles > 2)
+        printf("[trace] blk %d K%d N%d tiles %d: loop %lld clk, wait full %lld, wait tempty %lld, rest (issue) %lld\n",
+               blockIdx.x, p.K, p.N, tr_tiles, clock64() - tr_t0, tr_full, tr_tempty,
+               clock64() - tr_t0 - tr_full - tr_tempty);
+#endif
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: 8 warps = 4 TMEM lane quadrants
@@ -494,7 +552,7 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
       __syncwarp();
       if (lane == 0) {
         if (PAIR == 2)
-          mbar_arrive_cluster(&tempty_bar[acc], 0);
+          mbar_arrive_cluster(&tempty_bar[acc], leader_rank);
         else
           mbar_arrive(&tempty_bar[acc]);
       }
@@ -507,7 +565,7 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
       decode(tile, unit, k0, k1, tail_idx);
       int m_pair, n_org, bn_cur;  // n_org: first weight row of the tile's columns; bn_cur: BN, or BN/2 (narrow unit)
       unit_geom(unit, m_pair, n_org, bn_cur);
-      const int m_blk = m_pair * PAIR + static_cast<int>(cta_rank);
+      const int m_blk = (m_pair * PPG + static_cast<int>(pair_id)) * PAIR + static_cast<int>(cta_rank);
       const int r_local = wq * 32 + lane;
       const int bn_out = geglu ? bn_cur / 2 : bn_cur;          // output columns of this item
       const int no_org = geglu ? n_org / 2 : n_org;            // first output column
@@ -952,41 +1010,42 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
 // Co-resident CTA groups (pairs or singles) of gemm_bf16_tcgen05<BN, PAIR, *> on the current device.  The schedule
 // is persistent with a static stride, so every CTA (pair) must be co-resident: a pair needs both SMs of one TPC, and
 // not every TPC of a 148-SM part has two enabled SMs — ask the runtime how many clusters fit.  Cached per device.
-template <int BN, int PAIR>
+template <int BN, int PAIR, bool QUAD = false>
 static int resident_groups(int num_sms) {
   static int cache[kMaxDevices] = {};
   int& g = cache[device_slot()];
   if (g == 0) {
     using Cfg = GemmCfg<BN, PAIR>;
-    (void)cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    constexpr int GRP = QUAD ? 4 : PAIR;
+    (void)cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, false, 1, QUAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                Cfg::kSmemBytes);
-    int n = num_sms / PAIR;
+    int n = num_sms / GRP;
     if (PAIR == 2) {
       cudaLaunchConfig_t cfg = {};
       cfg.blockDim = dim3(kGemmThreads);
       cfg.dynamicSmemBytes = Cfg::kSmemBytes;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = PAIR;
+      attr[0].val.clusterDim.x = GRP;
       attr[0].val.clusterDim.y = 1;
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      cfg.gridDim = dim3((num_sms / PAIR) * PAIR);
+      cfg.gridDim = dim3((num_sms / GRP) * GRP);
       int q = 0;
-      if (cudaOccupancyMaxActiveClusters(&q, gemm_bf16_tcgen05<BN, PAIR, false, 1>, &cfg) == cudaSuccess && q > 0)
+      if (cudaOccupancyMaxActiveClusters(&q, gemm_bf16_tcgen05<BN, PAIR, false, 1, QUAD>, &cfg) == cudaSuccess && q > 0)
         n = q < n ? q : n;
       (void)cudaGetLastError();
     }
     g = n;
     if (getenv("DS_DEBUG"))
       fprintf(stderr, "[dsengine] gemm<%d,%d>: %d co-resident CTA %s of %d SMs\n", BN, PAIR, g,
-              PAIR == 2 ? "pairs" : "singles", num_sms);
+              QUAD ? "quads" : (PAIR == 2 ? "pairs" : "singles"), num_sms);
   }
   return g;
 }
 
-template <int BN, int PAIR, bool STATS>
+template <int BN, int PAIR, bool STATS, bool QUAD = false>
 static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                          const CUtensorMap& tmR, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
                          const GemmParams& p_in, int num_sms, cudaStream_t stream, void* splitk_ws,
@@ -996,11 +1055,12 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   const int slot = device_slot();
   static bool attr_set[kMaxDevices] = {};  // per device; benign race: idempotent
   if (!attr_set[slot]) {
-    DS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, STATS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::kSmemBytes));
+    DS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, STATS, 1, QUAD>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set[slot] = true;
   }
-  const int m_groups = (p.num_m_tiles + PAIR - 1) / PAIR;
+  constexpr int GRP = QUAD ? 4 : PAIR;
+  const int m_groups = (p.num_m_tiles + GRP - 1) / GRP;
   const bool mixed = p.nt_narrow > 0;  // run_gemm chose the mixed-width tail (BN == 256 only)
   if (!mixed) {
     p.wide_units = m_groups * p.num_n_tiles;
@@ -1014,13 +1074,13 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR;
+  attr[0].val.clusterDim.x = GRP;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   pdl_attr(&attr[1]);
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  const int max_groups = resident_groups<BN, PAIR>(num_sms);
+  const int max_groups = resident_groups<BN, PAIR, QUAD>(num_sms);
   const int groups = units < max_groups ? units : max_groups;
   // split-K tail (see GemmParams): the units of the partial last wave are cut along K so that every CTA pair gets
   // a slice.  Needs the bf16 TMA epilogue, no GEGLU (its accumulator pairs value | gate columns) and a caller-provided
@@ -1039,7 +1099,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   p.tail_parts = 1;
   p.total_items = units;
   p.ws = nullptr;
-  if (splitk_env > 0 && !mixed && p.num_k_iters >= splitk_env && splitk_ws && p.tma_epilogue &&
+  if (splitk_env > 0 && !QUAD && !mixed && p.num_k_iters >= splitk_env && splitk_ws && p.tma_epilogue &&
       p.epilogue != DS_EPI_GEGLU && units > groups) {
     const int full = (units / groups) * groups, left = units - full;
     if (left > 0 && left <= 128) {
@@ -1055,7 +1115,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
       }
     }
   }
-  cfg.gridDim = dim3(groups * PAIR);
+  cfg.gridDim = dim3(groups * GRP);
   GemmLaunch<1> L;
   L.tm[0][0] = tmA;
   L.tm[0][1] = tmB;
@@ -1069,7 +1129,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   L.dep_stride = 0;
   L.sched = nullptr;
   L.sched_items = 0;
-  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR, STATS, 1>, L));
+  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR, STATS, 1, QUAD>, L));
   DS_LAUNCH_OK("gemm_bf16_tcgen05");
   return DS_OK;
 }
@@ -1078,7 +1138,7 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
 struct PreparedGemm {
   CUtensorMap tm[6];
   GemmParams p;
-  int bn, pair;
+  int bn, pair, quad;
 };
 
 // Static schedule of a chain: which CTA pair runs which units, in which order.  Round-robin per problem (what a single
@@ -1157,18 +1217,19 @@ static int chain_schedule(const PreparedGemm* pr, int n, int groups, cudaStream_
 
 // ds_gemm_chain: n dependent GEMMs (problem q+1 reads problem q's output rows) as ONE persistent launch of
 // <256, 2> tiles; see GemmLaunch.  `dep` = kMaxChain * dep_stride + 1 zeroed ints the kernel hands back zeroed.
+template <bool QUAD>
 static int launch_chain(PreparedGemm* pr, int n, int* dep, int dep_len, int num_sms, cudaStream_t stream) {
-  constexpr int BN = 256, PAIR = 2;
+  constexpr int BN = 256, PAIR = 2, GRP = QUAD ? 4 : PAIR;
   using Cfg = GemmCfg<BN, PAIR>;
   const int slot = device_slot();
   static bool attr_set[kMaxDevices] = {};
   if (!attr_set[slot]) {
-    DS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, false, kMaxChain>,
+    DS_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, PAIR, false, kMaxChain, QUAD>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set[slot] = true;
   }
   GemmLaunch<kMaxChain> L;
-  const int m_groups = (pr[0].p.num_m_tiles + PAIR - 1) / PAIR;
+  const int m_groups = (pr[0].p.num_m_tiles + GRP - 1) / GRP;
   int max_units = 0;
   for (int q = 0; q < n; ++q) {
     GemmParams& p = pr[q].p;
@@ -1190,10 +1251,10 @@ static int launch_chain(PreparedGemm* pr, int n, int* dep, int dep_len, int num_
   }
   L.nq = n;
   L.dep = dep;
-  L.dep_stride = m_groups * PAIR;
+  L.dep_stride = m_groups * GRP;
   DS_REQUIRE(kMaxChain * L.dep_stride + 1 <= dep_len,
              "ds_gemm_chain: dependency buffer too small (%d ints for %d row blocks)", dep_len, L.dep_stride);
-  const int max_groups = resident_groups<BN, PAIR>(num_sms);
+  const int max_groups = resident_groups<BN, PAIR, QUAD>(num_sms);
   const int groups = max_units < max_groups ? max_units : max_groups;
   ChainSchedule sc;
   const int rc = chain_schedule(pr, n, groups, stream, &sc);
@@ -1206,27 +1267,28 @@ static int launch_chain(PreparedGemm* pr, int n, int* dep, int dep_len, int num_
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR;
+  attr[0].val.clusterDim.x = GRP;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   pdl_attr(&attr[1]);
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cfg.gridDim = dim3(groups * PAIR);
-  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR, false, kMaxChain>, L));
+  cfg.gridDim = dim3(groups * GRP);
+  DS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05<BN, PAIR, false, kMaxChain, QUAD>, L));
   DS_LAUNCH_OK("gemm_bf16_tcgen05(chain)");
   return DS_OK;
 }
 
-template <int BN, int PAIR>
+template <int BN, int PAIR, bool QUAD = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                        const CUtensorMap& tmR, const CUtensorMap& tmA2, const CUtensorMap& tmB2, const GemmParams& p,
                        int num_sms, cudaStream_t stream, void* splitk_ws, long long splitk_ws_bytes) {
   // the statistics epilogue is a separate instantiation: the default one keeps its register budget
   if (p.chan_stats)
-    return launch_gemm_t<BN, PAIR, true>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, num_sms, stream, splitk_ws,
-                                         splitk_ws_bytes);
-  return launch_gemm_t<BN, PAIR, false>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, num_sms, stream, splitk_ws, splitk_ws_bytes);
+    return launch_gemm_t<BN, PAIR, true, QUAD>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, num_sms, stream, splitk_ws,
+                                               splitk_ws_bytes);
+  return launch_gemm_t<BN, PAIR, false, QUAD>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, num_sms, stream, splitk_ws,
+                                              splitk_ws_bytes);
 }
 
 static int pick_bn(int N, int epilogue) {
@@ -1286,6 +1348,16 @@ static int prepare_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const v
     return e ? atoi(e) : 1;
   }();
   const int pair = chain ? 2 : ((pair_env != 0 && p.num_m_tiles >= 2) ? 2 : 1);
+  // QUAD clusters (two pairs sharing the weight tile by TMA multicast, see the kernel): 256-column tiles whose M tiles
+  // group by four.  MEASURED (B200, profiles/r02_gemm_sweep_l2pf.log): correct on the first run (all GEMM / conv / chain
+  // tests pass with it on) but never faster — FF1 156 -> 164 us, conv 128x128 640->640 713 -> 804 us, the rest within
+  // +-3 %: halving the weight reads of a cluster does not relieve what the MMA thread waits for (12-15 % of its loop on
+  // `full` barriers, DS_GEMM_TRACE build), and the two pairs now stall together.  Opt-in: DS_GEMM_QUAD=1.
+  static const int quad_env = [] {
+    const char* e = getenv("DS_GEMM_QUAD");
+    return e ? atoi(e) : 0;
+  }();
+  const int quad = (quad_env != 0 && pair == 2 && bn == 256 && p.num_m_tiles % 4 == 0 && p.num_m_tiles >= 8) ? 1 : 0;
   // coalesced TMA epilogue whenever the bf16 output (and residual) rows are 16-byte addressable
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.tma_epilogue = !p.out_fp32 && p.n_out % 8 == 0 && p.ldo % 8 == 0 && aligned16(p.out) &&
@@ -1317,6 +1389,13 @@ static int prepare_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const v
     return e ? atoi(e) : 0;
   }();
   if (!early_w_env) p.w_const = 0;
+  // MEASURED: no gain at 4 / 8 / 16 k-blocks (FF1 161.8 -> 163.4 / 164.8 / 168.8 us, convs 3-8 % slower): the producer's
+  // waits are not HBM first-touch latency.  Opt-in only.
+  static const int l2pf_env = [] {  // DS_GEMM_L2PF = k-blocks of weights requested into the L2 ahead of the smem ring
+    const char* e = getenv("DS_GEMM_L2PF");
+    return e ? atoi(e) : 0;
+  }();
+  p.l2_prefetch = l2pf_env;
   p.num_n_tiles = (p.N + bn - 1) / bn;
   p.wide_units = 0;
   p.wide_m_pairs = 0;
@@ -1343,7 +1422,8 @@ static int prepare_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const v
     const char* e = getenv("DS_GEMM_TAIL");
     return e ? atoi(e) : 1;
   }();
-  if (tail_env && !chain && pair == 2 && bn == 256 && p.epilogue != DS_EPI_GEGLU && p.N % 128 == 0 && !p.last_narrow) {
+  if (tail_env && !chain && !quad && pair == 2 && bn == 256 && p.epilogue != DS_EPI_GEGLU && p.N % 128 == 0 &&
+      !p.last_narrow) {
     const int G = resident_groups<256, 2>(dev.num_sms);
     const int mp = (p.num_m_tiles + 1) / 2, nt = p.num_n_tiles;
     const int units = mp * nt;
@@ -1366,11 +1446,12 @@ static int prepare_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const v
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-    const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn / pair)};
+    const int loaders = quad ? 4 : pair;  // CTAs that each fetch an equal share of the tile's weight rows
+    const uint32_t box[2] = {kBK, static_cast<uint32_t>(bn / loaders)};
     if (!encode_tmap_bf16(&tmB, w, 2, dims, strides, box, nullptr)) return DS_ERR_CUDA;
     tmB2 = tmB;
     if (p.nt_narrow > 0 || p.last_narrow) {
-      const uint32_t box2[2] = {kBK, static_cast<uint32_t>(kNarrowBN / pair)};
+      const uint32_t box2[2] = {kBK, static_cast<uint32_t>(kNarrowBN / loaders)};
       if (!encode_tmap_bf16(&tmB2, w, 2, dims, strides, box2, nullptr)) return DS_ERR_CUDA;
     }
   }
@@ -1383,6 +1464,7 @@ static int prepare_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const v
   out->p = p;
   out->bn = bn;
   out->pair = pair;
+  out->quad = quad;
   return DS_OK;
 }
 
@@ -1397,6 +1479,8 @@ static int run_gemm(const CUtensorMap& tmA_in, const CUtensorMap& tmA2_in, const
   const CUtensorMap &tmA = g.tm[0], &tmB = g.tm[1], &tmC = g.tm[2], &tmR = g.tm[3], &tmA2 = g.tm[4], &tmB2 = g.tm[5];
   const GemmParams& p = g.p;
   const int bn = g.bn, pair = g.pair;
+  if (g.quad)
+    return launch_gemm<256, 2, true>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
   if (pair == 2) {
     if (bn == 256) return launch_gemm<256, 2>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
     if (bn == 192) return launch_gemm<192, 2>(tmA, tmB, tmC, tmR, tmA2, tmB2, p, dev.num_sms, stream, splitk_ws, splitk_ws_bytes);
@@ -1530,7 +1614,8 @@ extern "C" int ds_gemm_chain(const ds_gemm_args* args, int n, int* dep, int dep_
     if (rc2 != DS_OK) return rc2;
     DS_REQUIRE(pr[q].p.tma_epilogue, "ds_gemm_chain: problem %d needs a 16-byte addressable bf16 output", q);
   }
-  return launch_chain(pr, n, dep, dep_len, dev.num_sms, static_cast<cudaStream_t>(stream));
+  if (pr[0].quad) return launch_chain<true>(pr, n, dep, dep_len, dev.num_sms, static_cast<cudaStream_t>(stream));
+  return launch_chain<false>(pr, n, dep, dep_len, dev.num_sms, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ds_gemm_chain_max(void) { return ds::kMaxChain; }
