@@ -63,6 +63,7 @@ SIGNATURES = {
     "ds_dialog_embed_add": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "ds_ip_mask": [_vp, _vp, _i, _i, _d, _i, _i, _i, _vp],
     "ds_gemm_bf16": [C.POINTER(GemmArgs), _vp],
+    "ds_zero_async": [_vp, _i64, _vp],
     "ds_gemm_chain": [C.POINTER(GemmArgs), _i, _vp, _i, _vp],
     "ds_gemm_chain_max": [],
     "ds_conv3x3_nhwc": [C.POINTER(Conv3x3Args), _vp],

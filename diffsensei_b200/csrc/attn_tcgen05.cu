@@ -634,6 +634,9 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int chunks = (g == 0 ? p.nt_pad : p.nip_pad) / 16;        // 16-key chunks of this group's softmax
     const int n_real = g == 0 ? p.n_text : p.n_ip;                  // keys that are not padding
     const uint32_t tSg = tS + lane_base + (g == 0 ? 0 : p.nt_pad);  // this group's scores; its P goes over their head
+#ifdef DS_ATTN_TRACE
+    long long tr_s = 0, tr_p1 = 0, tr_p2 = 0, tr_o = 0, tr_ep = 0, tr_t0 = clock64(), tr_a;
+#endif
 
     for (int n = 0; n < n_items; ++n) {
       const int item = i0 + n;
@@ -659,7 +662,14 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         return open ? 0.0f : kMask2;
       };
 
+#ifdef DS_ATTN_TRACE
+      tr_a = clock64();
+#endif
       mbar_wait(s_full, n & 1);
+#ifdef DS_ATTN_TRACE
+      tr_s += clock64() - tr_a;
+      tr_a = clock64();
+#endif
       tc_fence_after();
       // ---- pass 1: row maximum (log2 domain)
       float m = -INFINITY;
@@ -709,6 +719,10 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           tmem_ld_wait();
           max_chunk(c, ra);
         }
+#ifdef DS_ATTN_TRACE
+        tr_p1 += clock64() - tr_a;
+        tr_a = clock64();
+#endif
 #pragma unroll 1
         for (int c = 0; c < chunks; ++c) {
           tmem_ld16(tSg + c * 16, ra);
@@ -723,10 +737,18 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+#ifdef DS_ATTN_TRACE
+      tr_p2 += clock64() - tr_a;
+      tr_a = clock64();
+#endif
 
       // ---- epilogue: out = O_text / l_t + scale * O_ip / l_i   (blend BEFORE to_out, reference :258);
       //      group g writes output columns [32g, 32g+32)
       mbar_wait(o_full, n & 1);
+#ifdef DS_ATTN_TRACE
+      tr_o += clock64() - tr_a;
+      tr_a = clock64();
+#endif
       tc_fence_after();
       const float w_t = 1.0f / s_l[row], w_i = p.ip_scale / s_l[kTile + row];
       __nv_bfloat16* orow = p.out + (static_cast<size_t>(batch) * p.N + q_row) * p.C + head * kHd + g * 32;
@@ -754,7 +776,15 @@ cross_ip_attn_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
+#ifdef DS_ATTN_TRACE
+      tr_ep += clock64() - tr_a;
+#endif
     }
+#ifdef DS_ATTN_TRACE
+    if ((blockIdx.x % 97) == 0 && lane == 0 && (warp == 2 || warp == 6))
+      printf("[trace] cross blk %d warp %d items %d: total %lld | wait S %lld, pass1 %lld, pass2 %lld, wait O %lld, epilogue %lld\n",
+             blockIdx.x, warp, n_items, clock64() - tr_t0, tr_s, tr_p1, tr_p2, tr_o, tr_ep);
+#endif
   }
 
   tc_fence_before();

@@ -122,4 +122,11 @@ const char* ds_last_error(void) { return ds::t_last_error.c_str(); }
 
 uint64_t ds_launch_count(void) { return ds::g_launches.load(std::memory_order_relaxed); }
 
+int ds_zero_async(void* ptr, int64_t bytes, void* stream) {
+  using namespace ds;
+  DS_REQUIRE(ptr != nullptr && bytes >= 0, "ds_zero_async: bad arguments");
+  if (bytes > 0) DS_CUDA_OK(cudaMemsetAsync(ptr, 0, static_cast<size_t>(bytes), static_cast<cudaStream_t>(stream)));
+  return DS_OK;
+}
+
 }  // extern "C"

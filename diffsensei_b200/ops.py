@@ -72,7 +72,7 @@ def channel_stats(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.
     B, Cc = x.shape[0], x.shape[-1]
     HW = x.numel() // (B * Cc)
     if out is None:
-        out = torch.zeros(B, Cc, 2, dtype=torch.float64, device=x.device)
+        out = zero_(torch.empty(B, Cc, 2, dtype=torch.float64, device=x.device))
     else:
         _req(out, torch.float64, "channel_stats.out")
         if out.numel() != 2 * B * Cc:
@@ -197,6 +197,15 @@ def _splitk_ws():
         ws = torch.zeros(int(lib.ds_gemm_splitk_ws_bytes()) // 4, dtype=f32, device=f"cuda:{dev}")
         _SPLITK_WS[dev] = ws
     return ws
+
+
+def zero_(t: torch.Tensor) -> torch.Tensor:
+    """Clear a contiguous tensor with a memset node on the current stream (ds_zero_async)."""
+    if not t.is_contiguous():
+        raise DsEngineError("zero_: tensor must be contiguous")
+    _on_current_device(t, "zero_")
+    check(lib.ds_zero_async(t.data_ptr(), t.numel() * t.element_size(), _stream()), "ds_zero_async")
+    return t
 
 
 def gemm(*a, **kw) -> torch.Tensor:

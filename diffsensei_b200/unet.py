@@ -321,7 +321,8 @@ class UNetMangaEngine:
     # producer could not emit it (conv_in, token counts that are not a multiple of 128) -> ops.channel_stats.
     class _Pool:
         def __init__(self, B: int, cmax: int, device, slots: int = 64):
-            self.buf = torch.zeros(slots * B * cmax * 2, dtype=torch.float64, device=device)   # ONE memset per forward
+            self.buf = torch.empty(slots * B * cmax * 2, dtype=torch.float64, device=device)
+            ops.zero_(self.buf)                                               # ONE memset node per forward
             self.off, self.B = 0, B
 
         def take(self, C: int) -> torch.Tensor:

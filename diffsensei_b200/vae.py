@@ -29,7 +29,7 @@ bf16, f32 = torch.bfloat16, torch.float32
 
 class _Pool:                       # per-decode pool of fp64 [B, C, 2] channel-statistics buffers (one memset)
     def __init__(self, B, cmax, device, slots=48):
-        self.buf = torch.zeros(slots * B * cmax * 2, dtype=torch.float64, device=device)
+        self.buf = ops.zero_(torch.empty(slots * B * cmax * 2, dtype=torch.float64, device=device))
         self.off, self.B = 0, B
 
     def take(self, C):

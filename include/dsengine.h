@@ -34,6 +34,8 @@ int ds_version(void);
 const char* ds_last_error(void);
 /* number of kernels this library has launched in the calling process (for bench.py's gpu_launches) */
 uint64_t ds_launch_count(void);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream`: a memset node (not a fill kernel) for the statistics pools the step clears */
+int ds_zero_async(void* ptr, int64_t bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GroupNorm (+ optional SiLU), NHWC bf16.                     [HBM-bound]

@@ -3,7 +3,7 @@
   ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/kernels \
       python tools/profile_kernels.py
 Launch order inside the profiled range: chan_stats, gn_apply2 (two-pass form), gn_apply2 (in-step form), gemm<256> FF1/GEGLU, gemm<128> (N=640 out-proj with
-residual), gemm M8192 N1280 K1280 + residual, conv3x3 (8,64,64,640->640), flash_attn (B8 N4096 h10), cross_ip_attn (B8 N4096 h10), layernorm."""
+residual), gemm M8192 N1280 K1280 + residual, conv3x3 (8,64,64,640->640), flash_attn (B8 N4096 h10), cross_ip_attn (B8 N4096 h10), layernorm, the 4-link GEMM chain of a level-2 transformer block."""
 import os
 import sys
 
@@ -30,6 +30,22 @@ bbox = torch.tensor([[[0.0] * 4] * 4] * 4 + [[[.05, .10, .50, .95], [.50, .15, .
 ln_g, ln_b = torch.ones(640, device=dev), torch.zeros(640, device=dev)
 
 
+# the 4-link chain of a level-2 BasicTransformerBlock (attn2.to_out -> ff.net.0 -> ff.net.2 -> next to_qkv), LayerNorms folded
+hch = r(8192, 1280)
+w_ff2, b_ff2 = r(1280, 5120) * 0.014, torch.zeros(1280, device=dev)
+w_qkv, b_qkv = r(3840, 1280) * 0.03, torch.zeros(3840, device=dev)
+cs1, csq = torch.randn(10240, device=dev), torch.randn(3840, device=dev)
+stc = [torch.zeros(2 * 8192, dtype=torch.float64, device=dev) for _ in range(3)]
+
+
+def chain():
+    return ops.gemm_chain([
+        ((a3, w3, b3), dict(residual=hch, out=hch, row_stats_out=stc[0], row_stats_zeroed=True)),
+        ((None, w1, b1), dict(epilogue=ops.EPI_GEGLU, ln_stats=stc[0], ln_colsum=cs1, zero_rows=stc[2])),
+        ((None, w_ff2, b_ff2), dict(residual=hch, out=hch, row_stats_out=stc[1], row_stats_zeroed=True)),
+        ((None, w_qkv, b_qkv), dict(ln_stats=stc[1], ln_colsum=csq, zero_rows=stc[0]))])
+
+
 cst = ops.channel_stats(x)
 cst_conv = torch.zeros(8, 640, 2, dtype=torch.float64, device=dev)
 
@@ -45,6 +61,8 @@ def run():
     ops.attention_self(qkv, 10)
     ops.attention_cross_ip(q, kvt, kvi, bbox, 10, 1.0, 0.6, 16, 16)
     ops.layernorm(a2, ln_g, ln_b)
+    stc[1].zero_()
+    chain()
 
 
 run()
