@@ -86,6 +86,7 @@ struct GemmParams {
   // 1: the weight operand is constant data (never written by a kernel that may still be in flight), so the producer
   // may request its first tiles BEFORE griddepcontrol.wait.  0 (e.g. K / V^T of the VAE attention used as `w`): after.
   int w_const;
+  int n_block;      // > 0: wide units are ordered in column blocks of n_block n-tiles (m-major inside a block), see run_gemm
   int l2_prefetch;  // k-blocks of weight tile the producer requests into the L2 ahead of its smem ring (0 = off)
   // second A operand: k-blocks [k1_iters, num_k_iters) of a plain GEMM come from tmA2 (the channel concatenation
   // [a | a2] along K is never materialised); k1_iters == num_k_iters: off
@@ -279,8 +280,21 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
   // unit -> (m-pair, first weight row of its columns, tile width)
   auto unit_geom = [&](int unit, int& m_pair, int& n_org, int& bn) {
     if (unit < p.wide_units) {
-      m_pair = unit / p.num_n_tiles;
-      const int k = unit - m_pair * p.num_n_tiles;
+      int k;
+      if (p.n_block > 0) {
+        // column-blocked order: the CTA groups resident at one time cover ~(groups / n_block) row groups x n_block
+        // column tiles instead of ~2 x 37 — fewer distinct operand tiles in flight, more identical requests at the L2
+        const int per_blk = p.wide_m_pairs * p.n_block;
+        const int nb = unit / per_blk;
+        const int r = unit - nb * per_blk;
+        const int left = p.num_n_tiles - nb * p.n_block;
+        const int wcur = left < p.n_block ? left : p.n_block;
+        m_pair = r / wcur;
+        k = nb * p.n_block + (r - m_pair * wcur);
+      } else {
+        m_pair = unit / p.num_n_tiles;
+        k = unit - m_pair * p.num_n_tiles;
+      }
       n_org = k * BN;
       bn = (p.last_narrow && k == p.num_n_tiles - 1) ? kNarrowBN : BN;
     } else {
@@ -1396,7 +1410,13 @@ static int prepare_gemm(const CUtensorMap& tmA, const CUtensorMap& tmA2, const v
     return e ? atoi(e) : 0;
   }();
   p.l2_prefetch = l2pf_env;
+  // DS_GEMM_NBLOCK = w: order the units in column blocks of w n-tiles when a problem has more than w of them
+  static const int nblock_env = [] {
+    const char* e = getenv("DS_GEMM_NBLOCK");
+    return e ? atoi(e) : 0;
+  }();
   p.num_n_tiles = (p.N + bn - 1) / bn;
+  p.n_block = (nblock_env > 0 && p.num_n_tiles > nblock_env) ? nblock_env : 0;
   p.wide_units = 0;
   p.wide_m_pairs = 0;
   p.nt_narrow = 0;
