@@ -14,7 +14,8 @@ region.  Timing: CUDA events on the launching stream, barrier + synchronize on b
 Printed JSON line (rank 0): see the contract in the task statement; extra keys `roofline` (dominant kernel: the
 tcgen05 GEMM at the FF1/GEGLU shape, timed live with CUDA events, against MEASURED_PEAKS.json), `roofline_family`
 (the same kernel time-weighted over the step's real shape census), `roofline_gn` / `roofline_attn` (the two
-north-star kernels), `roofline_cross` (fused text+IP cross-attention against its byte floor), `panel` (MEASURED
+north-star kernels), `roofline_chain` (the GEMM kernel in chain mode: the four linears between two attention kernels as
+one launch), `roofline_cross` (fused text+IP cross-attention against its byte floor), `panel` (MEASURED
 panels/sec: whole 50-step panels through DiffSenseiPipeline.denoise, per-panel setup included), `mfu` (with and
 without the hoisted K|V projections), `cfg1_gpu` + `cpu_baseline.cfg1_measured` (one same-config CPU/GPU pair),
 `gpu_library_baseline` (the torch/cuBLAS/cuDNN/SDPA stack the reference would dispatch — stated, not the product),
@@ -220,6 +221,33 @@ def kernel_rooflines(ds, peaks, device):
                        "frac": round(flops / ms / 1e9 / peaks["bf16_tflops"], 4), "traffic": traffic.get("gemm_ff1"),
                        "ms_per_launch": round(ms, 4), "peak_source": peaks["source"] + " burst (kernel timed alone)",
                        "algorithmic_GFLOP": round(flops / 1e9, 1)}
+    del sets
+    # the same kernel in chain mode: the four linears between a level-2 block's cross-attention and the next block's
+    # self-attention (attn2.to_out -> ff.net.0 -> ff.net.2 -> to_qkv, LayerNorms folded) as ONE launch; 60 per step
+    C4 = 1280
+    sets = []
+    for i in range(3):                                   # 3 x 52 MB of weights + activations > L2
+        g = lambda *s_, k=1.0: (torch.randn(*s_, device=device) * k)
+        a = g(M, C4).to(bf)
+        h = g(M, C4).to(bf)
+        st = [torch.zeros(2 * M, dtype=torch.float64, device=device) for _ in range(3)]
+        qkv = torch.empty(M, 3 * C4, dtype=bf, device=device)
+        f = torch.empty(M, 4 * C4, dtype=bf, device=device)
+        W = [(g(C4, C4, k=C4 ** -0.5).to(bf), g(C4)), (g(8 * C4, C4, k=C4 ** -0.5).to(bf), g(8 * C4)),
+             (g(C4, 4 * C4, k=(4 * C4) ** -0.5).to(bf), g(C4)), (g(3 * C4, C4, k=C4 ** -0.5).to(bf), g(3 * C4))]
+        cs1, csq = g(8 * C4), g(3 * C4)
+        sets.append([((a,) + W[0], dict(residual=h, out=h, row_stats_out=st[0], row_stats_zeroed=True)),
+                     ((None,) + W[1], dict(epilogue=ops.EPI_GEGLU, ln_stats=st[0], ln_colsum=cs1, zero_rows=st[2],
+                                           out=f)),
+                     ((None,) + W[2], dict(residual=h, out=h, row_stats_out=st[1], row_stats_zeroed=True)),
+                     ((None,) + W[3], dict(ln_stats=st[1], ln_colsum=csq, zero_rows=st[0], out=qkv))])
+    ms = timed([(lambda s=s: ops.gemm_chain(s)) for s in sets], 4)
+    flops = 2.0 * M * (C4 * C4 + 8 * C4 * C4 + 4 * C4 * C4 + 3 * C4 * C4)
+    out["roofline_chain"] = {"kernel": "gemm_bf16_tcgen05<256,2,chain> attn2.to_out>ff.net.0>ff.net.2>to_qkv, M8192 "
+                                       "C1280 (4 linears, one launch)", "bound": "tensor",
+                             "achieved": round(flops / ms / 1e9, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                             "frac": round(flops / ms / 1e9 / peaks["bf16_tflops"], 4), "traffic": None,
+                             "ms_per_launch": round(ms, 4), "algorithmic_GFLOP": round(flops / 1e9, 1)}
     del sets
     # fused GroupNorm+SiLU at (8, 128, 128, 320): algorithmic bytes = read x + write y.  In the step the statistics
     # come from the producing conv's epilogue, so the GroupNorm IS the apply kernel (`roofline_gn`); the stand-alone

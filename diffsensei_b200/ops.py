@@ -251,19 +251,20 @@ def _chain_counters() -> torch.Tensor:
     return pool[i]
 
 
-def gemm_chain(calls, min_links: int = 2) -> list:
+def gemm_chain(calls, min_links: int = 2, enable: bool = True) -> list:
     """Run ``calls`` — a list of ``(args, kwargs)`` of :func:`gemm`, each one reading the previous one's output as its
     ``a`` (pass ``None`` for ``a`` to say exactly that) — as ONE persistent launch (ds_gemm_chain, include/dsengine.h).  Bit-identical to calling :func:`gemm` on
     each; returns the outputs.  Falls back to separate launches for shapes a chain does not take (M <= 128 or more
     than 65536 rows, fp32 outputs, channel statistics, or more links than the kernel holds).  ``min_links=1`` runs even
-    a single GEMM through the chain kernel (same tile geometry as a longer chain: what the tests compare against)."""
+    a single GEMM through the chain kernel (same tile geometry as a longer chain: what the tests compare against);
+    ``enable=False`` is the separate-launch path with the same call syntax."""
     prepared = []
     for a, kw in calls:
         if a[0] is None:                     # "the previous link's output"
             a = (prepared[-1][1],) + tuple(a[1:])
         prepared.append(_gemm_args(*a, **kw))
     M = prepared[0][0].M
-    ok = min_links <= len(prepared) <= gemm_chain_max() and 128 < M <= _CHAIN_ROW_BLOCKS * 128
+    ok = enable and min_links <= len(prepared) <= gemm_chain_max() and 128 < M <= _CHAIN_ROW_BLOCKS * 128
     for i, (g, _) in enumerate(prepared):
         ok = ok and g.M == M and not g.out_fp32 and not g.chan_stats and not g.a2
         ok = ok and (g.N // 2 if g.epilogue == EPI_GEGLU else g.N) % 8 == 0

@@ -36,7 +36,7 @@ from .weights import (bf, colsum_bf16, fold_layernorm, fp, pack_conv3x3, pack_co
 # fp32 partial sums (last bit).  MEASURED (B200, cfg2, same box, 2 runs each): 60.43 / 60.67 ms per step with
 # separate launches, 59.74 / 59.39 ms chained (687 -> 418 launches).  DS_GEMM_CHAIN=0 restores one launch per linear.
 _CHAIN = os.environ.get("DS_GEMM_CHAIN", "1") not in ("", "0")
-_CHAIN_MIN_C = int(os.environ.get("DS_GEMM_CHAIN_MIN_C", "0"))
+_CHAIN_LONG_MIN_ROWS, _CHAIN_SHORT_MIN_ROWS, _CHAIN_SHORT_MIN_C = 4096, 8192, 1280     # see _transformer
 
 
 bf16, f32 = torch.bfloat16, torch.float32
@@ -371,49 +371,31 @@ class UNetMangaEngine:
             return (a, w, bias), dict(kw, ln_stats=st[(k - 1) % 3], ln_colsum=cs, ln_eps=1e-5,
                                       zero_rows=st[(k + 1) % 3])
 
-        def produce(*a, **kw):
-            a, kw = produce_args(*a, **kw)
-            return ops.gemm(*a, **kw)
-
-        def consume(*a, **kw):
-            a, kw = consume_args(*a, **kw)
-            return ops.gemm(*a, **kw)
-
-        if _CHAIN and Cc >= _CHAIN_MIN_C and 128 < M <= 65536:
-            # The linears between two attention kernels as ONE persistent launch each (ops.gemm_chain):
-            #   proj_in -> attn1.to_qkv,   attn1.to_out -> attn2.to_q,
-            #   attn2.to_out -> ff.net.0 (GEGLU) -> ff.net.2 -> the next block's attn1.to_qkv
-            b0 = t.blocks[0]
-            h, qkv = ops.gemm_chain([produce_args(h.view(B, H * W, Cc), t.w_in, t.b_in),
-                                     consume_args(None, b0.wqkv, b0.bqkv, b0.cs_qkv)])
-            for bi, blk in enumerate(t.blocks):
-                a = ops.attention_self(qkv, t.heads)
-                _, q = ops.gemm_chain([produce_args(a, blk.wo1, blk.bo1, residual=h, out=h),
-                                       consume_args(None, blk.wq2, blk.bq2, blk.cs_q2, out=a)])
-                a = ops.attention_cross_ip(q, cond.kv_text[blk.layer], cond.kv_ip[blk.layer], cond.bbox, t.heads,
-                                           cond.aspect_ratio, self._scale_of(blk), cfg.num_vision_tokens,
-                                           cfg.num_dummy_tokens)
-                links = [produce_args(a, blk.wo2, blk.bo2, residual=h, out=h),
-                         consume_args(None, blk.wff1, blk.bff1, blk.cs_ff1, epilogue=ops.EPI_GEGLU),
-                         produce_args(None, blk.wff2, blk.bff2, residual=h, out=h)]
-                if bi + 1 < len(t.blocks):
-                    nb = t.blocks[bi + 1]
-                    links.append(consume_args(None, nb.wqkv, nb.bqkv, nb.cs_qkv, out=qkv))
-                outs = ops.gemm_chain(links)
-            h = outs[2]
-        else:
-            h = produce(h.view(B, H * W, Cc), t.w_in, t.b_in)
-            for blk in t.blocks:
-                qkv = consume(h, blk.wqkv, blk.bqkv, blk.cs_qkv)
-                a = ops.attention_self(qkv, t.heads)
-                h = produce(a, blk.wo1, blk.bo1, residual=h, out=h)
-                q = consume(h, blk.wq2, blk.bq2, blk.cs_q2, out=a)
-                a = ops.attention_cross_ip(q, cond.kv_text[blk.layer], cond.kv_ip[blk.layer], cond.bbox, t.heads,
-                                           cond.aspect_ratio, self._scale_of(blk), cfg.num_vision_tokens,
-                                           cfg.num_dummy_tokens)
-                h = produce(a, blk.wo2, blk.bo2, residual=h, out=h)
-                f = consume(h, blk.wff1, blk.bff1, blk.cs_ff1, epilogue=ops.EPI_GEGLU)
-                h = produce(f, blk.wff2, blk.bff2, residual=h, out=h)
+        # The linears between two attention kernels go to ops.gemm_chain — ONE persistent launch per run where that
+        # is faster, separate launches (same calls, same order) where it is not.  MEASURED (tools/chain_bench.py,
+        # B200): the 3/4-link run attn2.to_out -> ff.net.0 (GEGLU) -> ff.net.2 -> next attn1.to_qkv wins from
+        # M = 4096 rows up (C1280: 207 -> 197 us at M4096, 412 -> 365 at M8192; C640: 89.2 -> 87.9 at M4096, 147 -> 134
+        # at M8192) and loses 1-5 % below; the 2-link runs (proj_in -> to_qkv, attn1.to_out -> attn2.to_q) only win
+        # at C1280 / M8192 (60.7 -> 57.9 us) and lose 3-8 % elsewhere.
+        long_run = _CHAIN and _CHAIN_LONG_MIN_ROWS <= M <= 65536
+        short_run = _CHAIN and Cc >= _CHAIN_SHORT_MIN_C and _CHAIN_SHORT_MIN_ROWS <= M <= 65536
+        b0 = t.blocks[0]
+        h, qkv = ops.gemm_chain([produce_args(h.view(B, H * W, Cc), t.w_in, t.b_in),
+                                 consume_args(None, b0.wqkv, b0.bqkv, b0.cs_qkv)], enable=short_run)
+        for bi, blk in enumerate(t.blocks):
+            a = ops.attention_self(qkv, t.heads)
+            _, q = ops.gemm_chain([produce_args(a, blk.wo1, blk.bo1, residual=h, out=h),
+                                   consume_args(None, blk.wq2, blk.bq2, blk.cs_q2, out=a)], enable=short_run)
+            a = ops.attention_cross_ip(q, cond.kv_text[blk.layer], cond.kv_ip[blk.layer], cond.bbox, t.heads,
+                                       cond.aspect_ratio, self._scale_of(blk), cfg.num_vision_tokens,
+                                       cfg.num_dummy_tokens)
+            links = [produce_args(a, blk.wo2, blk.bo2, residual=h, out=h),
+                     consume_args(None, blk.wff1, blk.bff1, blk.cs_ff1, epilogue=ops.EPI_GEGLU),
+                     produce_args(None, blk.wff2, blk.bff2, residual=h, out=h)]
+            if bi + 1 < len(t.blocks):
+                nb = t.blocks[bi + 1]
+                links.append(consume_args(None, nb.wqkv, nb.bqkv, nb.cs_qkv, out=qkv))
+            h = ops.gemm_chain(links, enable=long_run)[2]
         # proj_out (+ the block's residual) writes an NHWC activation again: publish its channel statistics when a
         # 128-row tile cannot straddle two samples
         ost = pool.take(Cc) if (want_stats and (H * W) % 128 == 0) else None
