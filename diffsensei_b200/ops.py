@@ -224,7 +224,7 @@ def gemm_chain_max() -> int:
     return int(lib.ds_gemm_chain_max())
 
 
-_CHAIN_SLOTS = 16
+_CHAIN_SLOTS = 72          # torch hands out streams from two pools of 32 per device (+ the default stream)
 
 
 def gemm_chain_prepare() -> None:
