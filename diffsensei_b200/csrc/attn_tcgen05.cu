@@ -121,8 +121,14 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
 constexpr int kFlash5Threads = 320;  // warp 0: TMA + TMEM alloc, warp 1: MMA issue, warps 2-9: two softmax streams
 constexpr int kFlash5SmemBytes = kTileBytes * (1 + kFlash3Ring) + 1024 + 256 + 2 * kTile * 2 * 4;
 
-template <int POLY, bool F2, bool ELECT>
-__global__ void __launch_bounds__(kFlash5Threads, 2)
+// DUAL: one MMA-issue thread PER STREAM (warp 1 lane 0 -> stream 0, warp 10 lane 0 -> stream 1; 352 threads).  The
+// -DDS_ATTN_TRACE build shows why: the single issuer spends ~1200 clk per 128-key tile inside its 16 tcgen05.mma
+// (M128 N64 K16: 32 clk of tensor time each, ~75 clk each to dispatch from one thread — the converged `elect.sync`
+// variant is no faster, so it is not ptxas's waterfall), and a stream whose P is ready queues behind the other stream's
+// 8 dispatches.  With one issuer per stream the two dispatch sequences run side by side; K/V ring slots are released by
+// BOTH issuers' commits (`empty` barriers count 2).
+template <int POLY, bool F2, bool ELECT, bool DUAL = false>
+__global__ void __launch_bounds__(DUAL ? kFlash5Threads + 32 : kFlash5Threads, 2)
 flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const FlashParams p) {
   constexpr int RING = kFlash3Ring;
@@ -155,13 +161,13 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_init(q_full, 1);
     for (int i = 0; i < RING; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], DUAL ? 2 : 1);
     }
     for (int h = 0; h < 2; ++h) {
       mbar_init(&s_full[h], 1);
       mbar_init(&p_full[h], 4);  // one arrival per softmax warp of the stream
     }
-    mbar_init(o_full, 1);
+    mbar_init(o_full, DUAL ? 2 : 1);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -191,6 +197,47 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     (which == 0 ? p.k_col0 : p.v_col0) + head * kHd, j * kTile, batch);
       }
     }
+  } else if (DUAL && (warp == 1 || warp == 10)) {
+    if (lane == 0) {
+      // one issuer per stream: S_h(0); then per tile PV_h(j), S_h(j+1); every ring slot it has finished with gets one
+      // of the two commits its `empty` barrier waits for
+      const int h = warp == 1 ? 0 : 1;
+      constexpr uint32_t idesc_qk = make_idesc_bf16(kTile, kHalf, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kHd, 0, 1);
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_s = [&](uint32_t k_addr) {
+#pragma unroll
+        for (int k = 0; k < kHd / 16; ++k)
+          umma_ss(tS + h * kHalf, make_sw128_desc(q_addr + k * 32, 1024, 16),
+                  make_sw128_desc(k_addr + h * (kHalf * 128) + k * 32, 1024, 16), idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[h]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&full[0], 0);
+      tc_fence_after();
+      issue_s(smem_u32(sRing));
+      umma_commit(&empty[0]);
+      for (int j = 0; j < num_kv_tiles; ++j) {
+        const int vi = 2 * j + 1, vslot = vi % RING;
+        const int ki = 2 * j + 2, kslot = ki % RING;
+        const bool more = j + 1 < num_kv_tiles;
+        mbar_wait(&full[vslot], (vi / RING) & 1);
+        if (more) mbar_wait(&full[kslot], (ki / RING) & 1);
+        const uint32_t v_addr = smem_u32(sRing + vslot * kTileBytes);
+        mbar_wait(&p_full[h], j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kHalf / 16; ++k)
+          umma_ts(tO + h * kHd, tS + h * kHalf + k * 8, make_sw128_desc(v_addr + h * (kHalf * 128) + k * 2048, 1024, 1024),
+                  idesc_pv, (j == 0 && k == 0) ? 0u : 1u);
+        umma_commit(&empty[vslot]);
+        if (more) {
+          issue_s(smem_u32(sRing + kslot * kTileBytes));
+          umma_commit(&empty[kslot]);
+        }
+      }
+      umma_commit(o_full);
+    }
   } else if (warp == 1) {
     if (ELECT) {
       // MMA issue warp, CONVERGED: lane 0 alone polls the mbarriers (32 polling lanes made this variant slower:
@@ -217,6 +264,9 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     make_sw128_desc(v_addr + h * (kHalf * 128) + k * 2048, 1024, 1024), idesc_pv,
                     (first && k == 0) ? 0u : 1u);
       };
+#ifdef DS_ATTN_TRACE
+      long long fe_poll = 0, fe_issue = 0;
+#endif
       wait1(q_full, 0);
       wait1(&full[0], 0);
       tc_fence_after();
@@ -232,6 +282,9 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint32_t v_addr = smem_u32(sRing + vslot * kTileBytes);
         const uint32_t k_addr = smem_u32(sRing + kslot * kTileBytes);
         int first = 0;
+#ifdef DS_ATTN_TRACE
+        long long fe_a = clock64();
+#endif
         if (lane == 0) {
           for (;;) {
             if (mbar_try_wait(&p_full[0], j & 1)) break;
@@ -242,18 +295,36 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
         first = __shfl_sync(0xffffffffu, first, 0);
+#ifdef DS_ATTN_TRACE
+        fe_poll += clock64() - fe_a;
+#endif
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
           const int h = o == 0 ? first : 1 - first;
+#ifdef DS_ATTN_TRACE
+          fe_a = clock64();
+#endif
           if (o == 1) wait1(&p_full[h], j & 1);
+#ifdef DS_ATTN_TRACE
+          fe_poll += clock64() - fe_a;
+          fe_a = clock64();
+#endif
           tc_fence_after();
           issue_pv(v_addr, h, j == 0);
           if (o == 1) umma_commit_e(&empty[vslot]);
           if (more) issue_s(k_addr, h);
           if (more && o == 1) umma_commit_e(&empty[kslot]);
+#ifdef DS_ATTN_TRACE
+          fe_issue += clock64() - fe_a;
+#endif
         }
       }
       umma_commit_e(o_full);
+#ifdef DS_ATTN_TRACE
+      if ((blockIdx.x % 601) == 0 && lane == 0)
+        printf("[trace] flash(elect) blk %d MMA warp: per kv tile: poll p_full %.0f clk, issue %.0f clk\n", blockIdx.x,
+               double(fe_poll) / num_kv_tiles, double(fe_issue) / num_kv_tiles);
+#endif
     } else if (lane == 0) {
       // MMA issue: ONE lane in a divergent region (ptxas wraps every tcgen05.mma in an ELECT / BRA.U.ANY waterfall)
       constexpr uint32_t idesc_qk = make_idesc_bf16(kTile, kHalf, 0, 0);  // M128 N64, both K-major
@@ -272,6 +343,9 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           umma_ts(tO + h * kHd, tS + h * kHalf + k * 8, make_sw128_desc(v_addr + h * (kHalf * 128) + k * 2048, 1024, 1024),
                   idesc_pv, (first && k == 0) ? 0u : 1u);
       };
+#ifdef DS_ATTN_TRACE
+      long long fm_poll = 0, fm_issue = 0;
+#endif
       mbar_wait(q_full, 0);
       mbar_wait(&full[0], 0);  // K_0
       tc_fence_after();
@@ -289,6 +363,9 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         // serve whichever stream has its P ready first (no head-of-line blocking behind the slower stream); both
         // streams of tile j use the same V_j / K_{j+1} slots, which are released after the second one is served
         int first = 0;
+#ifdef DS_ATTN_TRACE
+        long long fm_a = clock64();
+#endif
         for (;;) {
           if (mbar_try_wait(&p_full[0], j & 1)) break;
           if (mbar_try_wait(&p_full[1], j & 1)) {
@@ -296,18 +373,36 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             break;
           }
         }
+#ifdef DS_ATTN_TRACE
+        fm_poll += clock64() - fm_a;
+#endif
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
           const int h = o == 0 ? first : 1 - first;
+#ifdef DS_ATTN_TRACE
+          fm_a = clock64();
+#endif
           if (o == 1) mbar_wait(&p_full[h], j & 1);
+#ifdef DS_ATTN_TRACE
+          fm_poll += clock64() - fm_a;
+          fm_a = clock64();
+#endif
           tc_fence_after();
           issue_pv(v_addr, h, j == 0);
           if (o == 1) umma_commit(&empty[vslot]);
           if (more) issue_s(k_addr, h);  // executes after PV_h(j): P_h(j) is consumed before S_h(j+1) overwrites it
           if (more && o == 1) umma_commit(&empty[kslot]);
+#ifdef DS_ATTN_TRACE
+          fm_issue += clock64() - fm_a;
+#endif
         }
       }
       umma_commit(o_full);
+#ifdef DS_ATTN_TRACE
+      if ((blockIdx.x % 601) == 0)
+        printf("[trace] flash blk %d MMA thread: per kv tile: poll p_full %.0f clk, issue (2 x (4 PV + 4 S MMAs + commits)) %.0f clk\n",
+               blockIdx.x, double(fm_poll) / num_kv_tiles, double(fm_issue) / num_kv_tiles);
+#endif
     }
   } else {
     // ---------------------------------------------------------------- softmax: 2 streams x 4 warps, thread <-> (row, h)
@@ -360,9 +455,18 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     };
 
+#ifdef DS_ATTN_TRACE
+    long long fr_wait = 0, fr_t0 = clock64(), fr_a;
+#endif
     for (int j = 0; j < num_kv_tiles; ++j) {
       const int valid = p.Nkv - j * kTile - h * kHalf;  // >= 64: whole half valid; <= 0: nothing valid
+#ifdef DS_ATTN_TRACE
+      fr_a = clock64();
+#endif
       mbar_wait(&s_full[h], j & 1);
+#ifdef DS_ATTN_TRACE
+      fr_wait += clock64() - fr_a;
+#endif
       tc_fence_after();
       bool need_max = (j == 0);
       float lsum;
@@ -421,6 +525,12 @@ flash_attn_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[h]);
     }
+#ifdef DS_ATTN_TRACE
+    if ((blockIdx.x % 601) == 0 && lane == 0 && wq == 0)
+      printf("[trace] flash blk %d stream %d: %d kv tiles, loop %lld clk, wait s_full %lld (%.0f / tile), softmax %.0f / tile\n",
+             blockIdx.x, h, num_kv_tiles, clock64() - fr_t0, fr_wait, double(fr_wait) / num_kv_tiles,
+             double(clock64() - fr_t0 - fr_wait) / num_kv_tiles);
+#endif
     // ---- epilogue: merge the two streams, normalise, store (thread (row, h) writes output columns [32h, 32h+32))
     s_ml[h * kTile + row] = make_float2(m_ref, l);
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -838,6 +948,10 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
       const char* e = getenv("DS_FLASH_ELECT");
       return e ? atoi(e) : 0;
     }();
+    static const int flash_dual = [] {  // DS_FLASH_DUAL=1: one MMA-issue thread per stream
+      const char* e = getenv("DS_FLASH_DUAL");
+      return e ? atoi(e) : 0;
+    }();
     static bool attr5_set_dev[kMaxDevices] = {};
     bool& attr5_set = attr5_set_dev[device_slot()];
 #define DS_F5_ATTR(P, F, E) \
@@ -849,6 +963,8 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
       DS_F5_ATTR(0, false, false);
       DS_F5_ATTR(0, true, true);
       DS_F5_ATTR(2, true, true);
+      DS_CUDA_OK(cudaFuncSetAttribute(flash_attn_v5_kernel<0, true, false, true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kFlash5SmemBytes));
       attr5_set = true;
     }
 #undef DS_F5_ATTR
@@ -862,7 +978,10 @@ static int launch_flash(const void* q, int ldq, int q_cols, const void* k, const
     cfg.attrs = attr;
     cfg.numAttrs = 1;
 #define DS_F5_LAUNCH(P, F, E) DS_CUDA_OK(cudaLaunchKernelEx(&cfg, flash_attn_v5_kernel<P, F, E>, tmQ, tmK, tmV, p))
-    if (!flash_f2)
+    if (flash_dual && flash_f2 && !flash_elect && flash_poly == 0) {
+      cfg.blockDim = dim3(kFlash5Threads + 32);
+      DS_CUDA_OK(cudaLaunchKernelEx(&cfg, flash_attn_v5_kernel<0, true, false, true>, tmQ, tmK, tmV, p));
+    } else if (!flash_f2)
       DS_F5_LAUNCH(0, false, false);
     else if (flash_elect && flash_poly >= 2)
       DS_F5_LAUNCH(2, true, true);
