@@ -555,6 +555,10 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
     const bool chain_sig = MAXQ > 1 && L.dep != nullptr && q + 1 < nq;
     const bool sig_issuer = (wq == 0) && (lane == 0);
     int pend_blk = -1;  // row block whose signal is pending (group-uniform)
+#ifdef DS_GEMM_TRACE
+    long long te_tfull = 0, te_stage = 0, te_body = 0, te_bar2 = 0, te_ld = 0, te_fence = 0, te_t0 = clock64();
+    int te_tiles = 0, te_lds = 0;
+#endif
     auto post_signal = [&]() {  // issuer thread, after a barrier of the group
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the bulk stores have been WRITTEN
       asm volatile("fence.proxy.async;" ::: "memory");
@@ -699,7 +703,14 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
         }
       }
 
+#ifdef DS_GEMM_TRACE
+      long long te_a = clock64();
+#endif
       mbar_wait(&tfull_bar[acc], acc_phase);
+#ifdef DS_GEMM_TRACE
+      te_tfull += clock64() - te_a;
+      ++te_tiles;
+#endif
       tc_fence_after();
       if (MAXQ > 1) row_stats_io();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
@@ -754,8 +765,15 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
           }
         } else {
           uint32_t raw[32];
+#ifdef DS_GEMM_TRACE
+          const long long tl_a = clock64();
+#endif
           tmem_ld32(t_row + c0, raw);
           tmem_ld_wait();
+#ifdef DS_GEMM_TRACE
+          te_ld += clock64() - tl_a;
+          ++te_lds;
+#endif
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
         }
@@ -803,8 +821,15 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
           const int no0 = no_org + cb;  // first output column of this 64-wide block
           if (no0 >= p.n_out) break;            // group-uniform
           // the previous TMA store must have finished READING the staging tile before anyone overwrites it
+#ifdef DS_GEMM_TRACE
+          te_a = clock64();
+#endif
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#ifdef DS_GEMM_TRACE
+          te_stage += clock64() - te_a;
+          te_a = clock64();
+#endif
           if (chain_sig && pend_blk >= 0) {  // the previous item of this group: see post_signal
             if (issuer) post_signal();
             pend_blk = -1;
@@ -865,8 +890,19 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
             release_acc(acc);
             released = true;
           }
+#ifdef DS_GEMM_TRACE
+          const long long tf_a = clock64();
+#endif
           fence_proxy_async_smem();  // st.shared -> visible to the TMA (async proxy)
+#ifdef DS_GEMM_TRACE
+          te_fence += clock64() - tf_a;
+          te_body += clock64() - te_a;
+          te_a = clock64();
+#endif
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#ifdef DS_GEMM_TRACE
+          te_bar2 += clock64() - te_a;
+#endif
           if (issuer) {
             if (p.conv)
               asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -978,6 +1014,13 @@ gemm_bf16_tcgen05(const __grid_constant__ GemmLaunch<MAXQ> L) {
       }
       release_acc(acc);
     }
+#ifdef DS_GEMM_TRACE
+    if ((blockIdx.x % 37) == 0 && warp == 4 && lane == 0 && te_tiles > 2)
+      printf("[trace] blk %d epilogue warp 4, K%d N%d, %d tiles: loop %lld clk | wait tfull %lld, staging free + bar %lld, "
+             "tmem/math/st.shared %lld (of which %d x tcgen05.ld.x32+wait: %lld = %.0f each; fence.proxy.async %lld), 2nd bar %lld, other %lld\n",
+             blockIdx.x, p.K, p.N, te_tiles, clock64() - te_t0, te_tfull, te_stage, te_body, te_lds, te_ld,
+             double(te_ld) / (te_lds > 0 ? te_lds : 1), te_fence, te_bar2, clock64() - te_t0 - te_tfull - te_stage - te_body - te_bar2);
+#endif
     if (chain_sig && pend_blk >= 0) {  // the group's last item of this problem
       asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
       if (sig_issuer) post_signal();
