@@ -36,7 +36,9 @@ from .weights import (bf, colsum_bf16, fold_layernorm, fp, pack_conv3x3, pack_co
 # fp32 partial sums (last bit).  MEASURED (B200, cfg2, same box, 2 runs each): 60.43 / 60.67 ms per step with
 # separate launches, 59.74 / 59.39 ms chained (687 -> 418 launches).  DS_GEMM_CHAIN=0 restores one launch per linear.
 _CHAIN = os.environ.get("DS_GEMM_CHAIN", "1") not in ("", "0")
-_CHAIN_LONG_MIN_ROWS, _CHAIN_SHORT_MIN_ROWS, _CHAIN_SHORT_MIN_C = 4096, 8192, 1280     # see _transformer
+# shape rule for the chains (see _transformer); DS_GEMM_CHAIN_RULE="long_rows,short_rows,short_c,long_c" overrides
+_CHAIN_LONG_MIN_ROWS, _CHAIN_SHORT_MIN_ROWS, _CHAIN_SHORT_MIN_C, _CHAIN_LONG_MIN_C = (
+    int(v) for v in os.environ.get("DS_GEMM_CHAIN_RULE", "4096,8192,1280,0").split(","))
 
 
 bf16, f32 = torch.bfloat16, torch.float32
@@ -377,7 +379,7 @@ class UNetMangaEngine:
         # M = 4096 rows up (C1280: 207 -> 197 us at M4096, 412 -> 365 at M8192; C640: 89.2 -> 87.9 at M4096, 147 -> 134
         # at M8192) and loses 1-5 % below; the 2-link runs (proj_in -> to_qkv, attn1.to_out -> attn2.to_q) only win
         # at C1280 / M8192 (60.7 -> 57.9 us) and lose 3-8 % elsewhere.
-        long_run = _CHAIN and _CHAIN_LONG_MIN_ROWS <= M <= 65536
+        long_run = _CHAIN and Cc >= _CHAIN_LONG_MIN_C and _CHAIN_LONG_MIN_ROWS <= M <= 65536
         short_run = _CHAIN and Cc >= _CHAIN_SHORT_MIN_C and _CHAIN_SHORT_MIN_ROWS <= M <= 65536
         b0 = t.blocks[0]
         h, qkv = ops.gemm_chain([produce_args(h.view(B, H * W, Cc), t.w_in, t.b_in),

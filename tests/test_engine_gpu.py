@@ -391,7 +391,7 @@ def test_chained_linears_do_not_change_the_unet_output(tiny, monkeypatch):
     monkeypatch.setattr(unet_mod, "_CHAIN", False)
     want, n_plain = run()
     monkeypatch.setattr(unet_mod, "_CHAIN", True)
-    for name in ("_CHAIN_LONG_MIN_ROWS", "_CHAIN_SHORT_MIN_ROWS", "_CHAIN_SHORT_MIN_C"):
+    for name in ("_CHAIN_LONG_MIN_ROWS", "_CHAIN_SHORT_MIN_ROWS", "_CHAIN_SHORT_MIN_C", "_CHAIN_LONG_MIN_C"):
         monkeypatch.setattr(unet_mod, name, 0)          # the production thresholds keep TINY shapes unchained
     for _ in range(3):
         got, n_chain = run()
