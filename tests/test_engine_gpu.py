@@ -148,6 +148,30 @@ def test_concurrent_chains_do_not_change_the_result(tiny):
         assert rel_l2(v, base) < 1e-3, k
 
 
+def test_concurrent_streams_with_chained_linears(tiny, monkeypatch):
+    """ops.gemm_chain keeps one set of dependency counters per stream: batch rows running as concurrent kernel chains
+    on side streams (and as graph branches) must not disturb each other's GEMM chains."""
+    from diffsensei_b200 import unet as unet_mod
+    for name in ("_CHAIN_LONG_MIN_ROWS", "_CHAIN_SHORT_MIN_ROWS", "_CHAIN_SHORT_MIN_C", "_CHAIN_LONG_MIN_C"):
+        monkeypatch.setattr(unet_mod, name, 0)
+    monkeypatch.setattr(unet_mod, "_CHAIN", True)
+    ds, _oracle, engine = tiny
+    bs, h, w = 2, 32, 32                       # 2 x 256 rows per stream at the first transformer level: chains engage
+    lat, ehs, pooled, time_ids, bbox, dialog = _inputs(ds.TINY, bs, h, w, seed=11)
+    pipe = ds.DiffSenseiPipeline(engine)
+    outs = {}
+    for chains in (1, 2):
+        for use_graph in (False, True):
+            st = pipe.make_stepper(lat, ehs, pooled, time_ids, bbox, 1.0, dialog, 3, 7.5, use_graph=use_graph,
+                                   chains=chains)
+            for i in range(3):
+                st.step(i)
+            outs[(chains, use_graph)] = st.latents_nchw().float().cpu()
+    base = outs[(1, False)]
+    for k, v in outs.items():
+        assert rel_l2(v, base) < 1e-3, k
+
+
 def test_pipeline_call_surface(tiny):
     ds, _oracle, engine = tiny
     from oracle.resampler import OracleResampler
