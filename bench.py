@@ -246,7 +246,8 @@ def kernel_rooflines(ds, peaks, device):
     out["roofline_chain"] = {"kernel": "gemm_bf16_tcgen05<256,2,chain> attn2.to_out>ff.net.0>ff.net.2>to_qkv, M8192 "
                                        "C1280 (4 linears, one launch)", "bound": "tensor",
                              "achieved": round(flops / ms / 1e9, 1), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                             "frac": round(flops / ms / 1e9 / peaks["bf16_tflops"], 4), "traffic": None,
+                             "frac": round(flops / ms / 1e9 / peaks["bf16_tflops"], 4),
+                             "traffic": traffic.get("gemm_chain"),
                              "ms_per_launch": round(ms, 4), "algorithmic_GFLOP": round(flops / 1e9, 1)}
     del sets
     # fused GroupNorm+SiLU at (8, 128, 128, 320): algorithmic bytes = read x + write y.  In the step the statistics
